@@ -1,0 +1,96 @@
+// rl_selftest.cu — single-CTA tcgen05 GEMM used by tests to pin the descriptor conventions of rl_umma.cuh
+// (chunk layout as K-major / MN-major operand, row-shifted start addresses, 1-D bulk TMA operand fill).
+#include "rl_common.cuh"
+#include "rl_umma.cuh"
+
+namespace rl {
+
+// Copies a row-major bf16 matrix [rows × cols] (cols % 8 == 0) into the chunk layout T[cols/8][rows][8].
+__device__ void fill_chunk_layout(uint8_t* smem, const __nv_bfloat16* g, int rows, int cols) {
+  const int nchunk = cols >> 3;
+  for (int i = threadIdx.x; i < rows * nchunk; i += blockDim.x) {
+    int r = i % rows, j = i / rows;
+    uint4 v = *reinterpret_cast<const uint4*>(g + (size_t)r * cols + j * 8);
+    *reinterpret_cast<uint4*>(smem + ((size_t)j * rows + r) * 16) = v;
+  }
+}
+
+__global__ void __launch_bounds__(128, 1)
+umma_selftest_kernel(const __nv_bfloat16* A, int a_rows, int a_cols, int a_mn, int a_shift,
+                     const __nv_bfloat16* B, int b_rows, int b_cols, int b_mn, int b_shift,
+                     int N, int K, float* D, int bulk_b) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ uint64_t bar_mma, bar_tma;
+  __shared__ uint32_t tmem_base_s;
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + (((size_t)a_rows * a_cols * 2 + 127) & ~(size_t)127);
+  const int warp = threadIdx.x >> 5;
+
+  if (threadIdx.x == 0) {
+    mbar_init(&bar_mma, 1);
+    mbar_init(&bar_tma, 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) tmem_alloc(&tmem_base_s, 256);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+
+  fill_chunk_layout(sA, A, a_rows, a_cols);
+  if (bulk_b) {
+    if (threadIdx.x == 0) {
+      uint32_t bytes = (uint32_t)b_rows * b_cols * 2;
+      mbar_arrive_expect_tx(&bar_tma, bytes);
+      bulk_g2s(sB, B, bytes, &bar_tma);
+    }
+  } else {
+    fill_chunk_layout(sB, B, b_rows, b_cols);
+  }
+  fence_proxy_async();
+  __syncthreads();
+
+  if (threadIdx.x == 0) {
+    if (bulk_b) mbar_wait(&bar_tma, 0);
+    tc_fence_after();
+    const uint32_t idesc = umma_idesc_bf16((uint32_t)N, (uint32_t)a_mn, (uint32_t)b_mn);
+    const uint32_t a0 = smem_u32(sA) + 16u * a_shift, b0 = smem_u32(sB) + 16u * b_shift;
+    for (int kk = 0; kk < K / 16; ++kk) {
+      uint64_t ad = a_mn ? desc_mnmajor(a0 + kk * 256u, a_rows) : desc_kmajor(a0 + kk * 2u * 16u * a_rows, a_rows);
+      uint64_t bd = b_mn ? desc_mnmajor(b0 + kk * 256u, b_rows) : desc_kmajor(b0 + kk * 2u * 16u * b_rows, b_rows);
+      umma_ss(tmem_base, ad, bd, idesc, kk > 0);
+    }
+    umma_commit(&bar_mma);
+  }
+  mbar_wait(&bar_mma, 0);
+  tc_fence_after();
+
+  const int row = threadIdx.x;
+  for (int c0 = 0; c0 < N; c0 += 16) {
+    float v[16];
+    tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + c0, v);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) D[(size_t)row * N + c0 + i] = v[i];
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, 256);
+}
+
+}  // namespace rl
+
+extern "C" int rl_selftest_umma(const void* A, int a_rows, int a_cols, int a_mn_major, int a_row_shift,
+                                const void* B, int b_rows, int b_cols, int b_mn_major, int b_row_shift, int N,
+                                int K, float* D, int bulk_b, void* stream) {
+  using namespace rl;
+  if (N % 16 || N < 16 || N > 256 || K % 16 || a_cols % 8 || b_cols % 8) return rl_fail(RL_ERR_ARG, "selftest: bad shape");
+  size_t sa = (((size_t)a_rows * a_cols * 2 + 127) & ~(size_t)127), sb = (size_t)b_rows * b_cols * 2;
+  size_t smem = sa + sb;
+  if (smem > 200 * 1024) return rl_fail(RL_ERR_ARG, "selftest: tile too large");
+  RL_CUDA(cudaFuncSetAttribute(umma_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  umma_selftest_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)A, a_rows, a_cols, a_mn_major, a_row_shift, (const __nv_bfloat16*)B, b_rows, b_cols,
+      b_mn_major, b_row_shift, N, K, D, bulk_b);
+  RL_CUDA(cudaGetLastError());
+  return RL_OK;
+}

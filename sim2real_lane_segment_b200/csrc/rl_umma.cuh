@@ -1,0 +1,176 @@
+// rl_umma.cuh — sm_100a primitives used by every tensor-core kernel in this library:
+// mbarrier, 1-D bulk TMA (cp.async.bulk → SASS UBLKCP), tcgen05 alloc/mma/commit/ld (→ UTCHMMA/LDTM),
+// and the shared-memory matrix descriptors for the un-swizzled ("interleave") canonical layout.
+//
+// Shared-memory operand layout used throughout ("chunk layout"):
+//     T[j][r][8]   j = chunk of 8 bf16 along the contiguous (channel) axis, r = row, 16 bytes per (j,r)
+// With R rows allocated this single physical layout can be read by tcgen05.mma either as
+//   * a K-major operand   (MN index = r, K index = 8j+e):  SBO = 128 B, LBO = 16·R B
+//   * an MN-major operand (MN index = 8j+e, K index = r):  SBO = 16·R B, LBO = 128 B
+// and a *row shift* by s rows is a start-address offset of 16·s bytes, which is how the 3×3 taps are
+// applied on the 16-channel side of the growth-16 convolutions without materialising an im2col matrix.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace rl {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+
+// ----------------------------------------------------------------------------------------------
+// mbarrier
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a protocol bug must surface as a CUDA error (trap), never as a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if (++spins > (1u << 24)) __trap();
+  }
+}
+
+// ----------------------------------------------------------------------------------------------
+// 1-D bulk TMA: global → shared, completion on an mbarrier (bytes % 16 == 0, 16-byte aligned)
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(smem_dst)),
+               "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+// generic-proxy smem writes → visible to the async proxy (tcgen05.mma / TMA reads of smem)
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// ----------------------------------------------------------------------------------------------
+// TMEM
+// ----------------------------------------------------------------------------------------------
+// ncols: power of two in [32, 512]; executed by one full warp; result lands in *smem_dst
+__device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)),
+               "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// tcgen05.commit: mbarrier arrives once all previously issued tcgen05.mma of this thread completed
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+
+// ----------------------------------------------------------------------------------------------
+// descriptors
+// ----------------------------------------------------------------------------------------------
+// shared-memory matrix descriptor, SWIZZLE_NONE, Blackwell version field = 1
+__device__ __forceinline__ uint64_t umma_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFFu);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
+  d |= (uint64_t)1 << 46;
+  return d;
+}
+// chunk layout T[j][r][8] with R rows, read as K-major (rows are the M/N index)
+__device__ __forceinline__ uint64_t desc_kmajor(uint32_t saddr, uint32_t R) {
+  return umma_smem_desc(saddr, 16u * R, 128u);
+}
+// chunk layout T[j][r][8] with R rows, read as MN-major (rows are the K index)
+__device__ __forceinline__ uint64_t desc_mnmajor(uint32_t saddr, uint32_t R) {
+  return umma_smem_desc(saddr, 128u, 16u * R);
+}
+// instruction descriptor: kind::f16, A=B=bf16, D=f32, M=128
+__host__ __device__ constexpr uint32_t umma_idesc_bf16(uint32_t N, uint32_t a_mn_major, uint32_t b_mn_major,
+                                                       uint32_t M = 128) {
+  return (1u << 4)               // D format f32
+         | (1u << 7)             // A format bf16
+         | (1u << 10)            // B format bf16
+         | (a_mn_major << 15)    // A major
+         | (b_mn_major << 16)    // B major
+         | ((N >> 3) << 17)      // N
+         | ((M >> 4) << 24);     // M
+}
+// D[tmem] (+)= A[smem] · B[smem]; one thread issues on behalf of the CTA. K = 16 per instruction.
+__device__ __forceinline__ void umma_ss(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                        uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+// ----------------------------------------------------------------------------------------------
+// TMEM → registers. Warp w may only touch lanes [32·(w%4), 32·(w%4)+32). taddr = (lane<<16)|column.
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
+  uint32_t r[8];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x8.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// ----------------------------------------------------------------------------------------------
+// small numeric helpers
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ float2 unpack_bf16x2(uint32_t u) {
+  __nv_bfloat162 h = *reinterpret_cast<__nv_bfloat162*>(&u);
+  return __bfloat1622float2(h);
+}
+__device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
+
+}  // namespace rl
