@@ -1,0 +1,105 @@
+/* rightlane.h — C ABI of librightlane.so: the B200-native (sm_100a) replacement for the arithmetic behind
+ * timurlenk07/sim2real_lane_segment's segmentation step.  The reference has no native code and therefore no FFI;
+ * each entry point cites the reference Python it stands in for (paths relative to rightLaneNetwork/).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer owned by the caller unless stated otherwise; the library allocates nothing
+ *     on the device: the caller provides one workspace of rl_plan_workspace_bytes() bytes (256-byte aligned)
+ *   - every call is asynchronous on the given cudaStream_t (passed as void*), performs no host synchronisation and no
+ *     host callback, so a whole step can be captured in a CUDA graph
+ *   - return value: 0 = ok, <0 = error (RL_ERR_*), message via rl_last_error() (thread-local); nothing throws or aborts
+ *   - parameters / gradients / optimizer state are flat fp32 arenas in the reference's nn.Module registration order
+ *     (state_dict order: featureExtractor.* then classifier.*); BN running statistics are a second flat fp32 arena
+ *     ([running_mean, running_var] per BatchNorm, registration order)
+ *   - activations are internal (NHWC bf16 concat arenas inside the workspace); images enter as fp32 NCHW exactly as the
+ *     reference's DataLoader delivers them, probabilities leave as fp32 NCHW, masks as uint8 [B,H,W]
+ */
+#ifndef RIGHTLANE_H_
+#define RIGHTLANE_H_
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum { RL_OK = 0, RL_ERR_ARG = -1, RL_ERR_SHAPE = -2, RL_ERR_CUDA = -3, RL_ERR_STATE = -4 };
+
+typedef struct rl_plan rl_plan;
+
+int rl_abi_version(void);
+const char* rl_last_error(void);
+
+/* FC-DenseNet67 + classifier for a fixed batch geometry.  Stands in for the module construction at
+ * trainingModules/TrainingBase.py:32-33 (FCDenseNet67Base + FCDenseNet67Classifier, models/FCDenseNet/tiramisu.py:178-194).
+ * training != 0 additionally reserves gradient arenas.  H, W >= 32; 2 <= num_cls <= 4. */
+int rl_plan_create(rl_plan** out, int B, int H, int W, int num_cls, int training);
+void rl_plan_destroy(rl_plan* p);
+long rl_plan_workspace_bytes(const rl_plan* p);
+long rl_plan_num_params(const rl_plan* p);     /* 3 461 220 for num_cls = 4 */
+long rl_plan_num_bn_buffers(const rl_plan* p); /* floats in the BN running-statistics arena */
+int rl_plan_bind(rl_plan* p, void* workspace, void* stream);
+
+/* introspection used by tests and by the Python mirror (no device work) */
+enum {
+  RL_Q_NUM_LAYERS = 0,
+  RL_Q_LEVEL_ACT_OFF = 1,   /* index = level 0..5 -> byte offset of the NHWC bf16 arena */
+  RL_Q_LEVEL_DACT_OFF = 2,
+  RL_Q_LEVEL_CT = 3,
+  RL_Q_LEVEL_H = 4,
+  RL_Q_LEVEL_W = 5,
+  RL_Q_LEVEL_CSKIP = 6,
+  RL_Q_SCALARS_OFF = 7,     /* struct: int hist[8]; int cm[64]; double loss_num, loss_den; int bad_label */
+  RL_Q_LAYER_TYPE = 8,      /* index = layer in forward order: 0 first conv, 1 dense, 2 transition down, 3 transition up */
+  RL_Q_LAYER_MASK_OFF = 9,  /* byte offset of float[B][cout] dropout keep-scale (dense / transition-down layers) */
+  RL_Q_LAYER_COUT = 10,
+  RL_Q_LAYER_PARAM_W = 11,  /* float offset of the layer's conv weight in the parameter arena */
+  RL_Q_LEVEL_STATS_OFF = 12 /* byte offset of double[2][Ct]: per-channel sum, sum of squares */
+};
+int rl_plan_query(const rl_plan* p, int what, int index, long* out);
+
+/* bf16 repack of all convolution weights into tensor-core operand layout; call after every parameter change
+ * (load_state_dict, optimizer step). */
+int rl_pack_weights(rl_plan* p, const float* params, void* stream);
+
+/* nn.Dropout2d(0.2) keep-scales (models/FCDenseNet/layers.py:12,51) for all layers: p_drop = 0 writes 1.0 everywhere
+ * (eval / parity runs); tests may overwrite the per-layer float[B][cout] blocks (RL_Q_LAYER_MASK_OFF). */
+int rl_set_dropout(rl_plan* p, float p_drop, unsigned long long seed, unsigned long long step, void* stream);
+
+/* FCDenseNetFeatureExtractor.forward without the final F.normalize (tiramisu.py:89-103): x fp32 [B,3,H,W] ->
+ * level-0 arena (288 channels).  train != 0: BatchNorm uses batch statistics (and they are retained for
+ * rl_bn_running_update / rl_backward); else running statistics from bn_buffers. */
+int rl_forward(rl_plan* p, const float* params, const float* bn_buffers, const float* x, int train, void* stream);
+
+/* F.normalize (tiramisu.py:105) + FCDenseNetClassifier.forward (tiramisu.py:120-125) + cross_entropy on the
+ * probabilities + argmax + confusion counts (SimpleTrain.py:15-20, TrainingBase.py:84-93, test.py:93-100).
+ *   y: labels uint8 or int64 [B,H,W] or NULL; weighted: class weights 1/count as getClassWeight (TrainingBase.py:12-23)
+ *   probs (fp32 [B,C,H,W]) / mask (uint8 [B,H,W]) may be NULL.  Loss sums and counts land in the scalars block.
+ *   backward: 0 = forward only; 1 = also start the backward pass with the fused CE gradient times grad_scale;
+ *   2 = backward from an external d(loss)/d(probs) (dprobs fp32 [B,C,H,W]).  feat_grad_sign = -1 realises
+ *   GradReverse (tiramisu.py:7-18).  Classifier gradients are accumulated into grads. */
+int rl_head(rl_plan* p, const float* params, const void* y, int y_is_i64, int weighted, float* probs, uint8_t* mask,
+            int backward, const float* dprobs, float grad_scale, float feat_grad_sign, float* grads, void* stream);
+
+/* loss.backward() for everything below the head (SimpleTrain.py:25 + autograd): accumulates into grads (fp32 arena,
+ * same layout as params).  Requires rl_forward(train=1) and rl_head(backward != 0) on the same plan. */
+int rl_backward(rl_plan* p, const float* params, const float* x, float* grads, void* stream);
+
+/* running_mean / running_var momentum update of all 60 BatchNorm2d layers from the last training forward */
+int rl_bn_running_update(rl_plan* p, float* bn_buffers, float momentum, void* stream);
+
+/* torch.optim.AdamW step (SimpleTrain.py:28) over a flat arena; step >= 1; grad_scale multiplies g first */
+int rl_adamw_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long n, float lr, float beta1,
+                  float beta2, float eps, float weight_decay, long step, float grad_scale, void* stream);
+/* torch.optim.SGD(momentum, nesterov=True, weight_decay) step (MMETrainingModule.py:16-19) */
+int rl_sgd_nesterov_step(float* params, const float* grads, float* momentum_buf, long n, float lr, float momentum,
+                         float weight_decay, int first_step, float grad_scale, void* stream);
+
+/* test hook: one 128 x N x K tcgen05 GEMM through the shared-memory operand conventions of csrc/rl_umma.cuh */
+int rl_selftest_umma(const void* A, int a_rows, int a_cols, int a_mn_major, int a_row_shift, const void* B, int b_rows,
+                     int b_cols, int b_mn_major, int b_row_shift, int N, int K, float* D, int bulk_b, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RIGHTLANE_H_ */

@@ -59,6 +59,7 @@ class _Ctx:
         self.drop_masks = drop_masks
         self.update_running = update_running
         self.new_running: Dict[str, torch.Tensor] = {}
+        self.taps: Dict[str, torch.Tensor] = {}
 
 
 def _bn_relu(ctx: _Ctx, x, prefix):
@@ -98,6 +99,7 @@ def _dense_block(ctx, x, prefix, n_layers, only_new):
         out = _dense_layer(ctx, x, f"{prefix}.layers.{i}")
         x = torch.cat([x, out], 1)
         new.append(out)
+    ctx.taps[prefix] = x  # full concat in the reference's channel order (test introspection only)
     return torch.cat(new, 1) if only_new else x
 
 
@@ -117,9 +119,11 @@ def _transition_up(ctx, x, skip, prefix):
 
 
 def feature_extractor(sd, x, cfg: NetConfig = FCDENSENET67, train=False, drop_masks=None, update_running=False,
-                      prefix="featureExtractor.", normalize=True):
+                      prefix="featureExtractor.", normalize=True, taps=None):
     """tiramisu.py:89-106.  Returns (features, dict of updated running stats)."""
     ctx = _Ctx(sd, train, drop_masks, update_running)
+    if taps is not None:
+        ctx.taps = taps
     p = prefix
     out = F.conv2d(x, sd[p + "firstconv.weight"], sd[p + "firstconv.bias"], padding=1)
     skips = []

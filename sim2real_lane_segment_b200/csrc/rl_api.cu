@@ -1,0 +1,547 @@
+// rl_api.cu — extern "C" boundary (include/rightlane.h) and the host-side layer schedule.
+#include <string.h>
+
+#include <algorithm>
+#include <new>
+
+#include "rl_common.cuh"
+#include "rl_kernels.h"
+#include "rl_plan.h"
+
+using namespace rl;
+
+struct rl_plan {
+  Plan p;
+};
+
+namespace rl {
+int td_parts(int C, int* n0, int* np);
+}
+
+static inline uint8_t* wsb(const Plan* p) { return (uint8_t*)p->ws; }
+static inline __nv_bfloat16* act_of(const Plan* p, int l) { return (__nv_bfloat16*)(wsb(p) + p->lv[l].act_off); }
+static inline __nv_bfloat16* dact_of(const Plan* p, int l) { return (__nv_bfloat16*)(wsb(p) + p->lv[l].dact_off); }
+static inline double* stats_of(const Plan* p, int l) { return (double*)(wsb(p) + p->lv[l].stats_off); }
+static inline double* acc_of(const Plan* p, int l) { return (double*)(wsb(p) + p->lv[l].acc_off); }
+static inline Scalars* scal_of(const Plan* p) { return (Scalars*)(wsb(p) + p->scal_off); }
+
+static BnSrc make_bn(const Plan* p, const Layer& L, const float* params, const float* bnbuf, int train) {
+  BnSrc b;
+  b.stats = train ? stats_of(p, L.lvl_in) : nullptr;
+  b.Ct = p->lv[L.lvl_in].Ct;
+  b.inv_n = 1.0 / (double)p->lv[L.lvl_in].px;
+  b.gamma = params + L.p_gamma;
+  b.beta = params + L.p_beta;
+  b.rmean = bnbuf ? bnbuf + L.b_rm : nullptr;
+  b.rvar = bnbuf ? bnbuf + L.b_rv : nullptr;
+  b.cs_perm = L.cs_perm;
+  b.eval = train ? 0 : 1;
+  return b;
+}
+
+extern "C" {
+
+int rl_plan_create(rl_plan** out, int B, int H, int W, int num_cls, int training) {
+  if (!out) return rl_fail(RL_ERR_ARG, "rl_plan_create: out is null");
+  rl_plan* h = new (std::nothrow) rl_plan();
+  if (!h) return rl_fail(RL_ERR_STATE, "rl_plan_create: out of host memory");
+  if (build_plan(&h->p, B, H, W, num_cls, training) != 0) {
+    int rc = rl_fail(RL_ERR_SHAPE, "%s", h->p.err);
+    delete h;
+    return rc;
+  }
+  int dev = 0, sms = 148;
+  if (cudaGetDevice(&dev) == cudaSuccess) {
+    int v = 0;
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && v > 0) sms = v;
+  } else {
+    cudaGetLastError();
+  }
+  h->p.sm_count = sms;
+  *out = h;
+  return RL_OK;
+}
+
+void rl_plan_destroy(rl_plan* h) { delete h; }
+long rl_plan_workspace_bytes(const rl_plan* h) { return h ? (long)h->p.ws_bytes : 0; }
+long rl_plan_num_params(const rl_plan* h) { return h ? h->p.n_params : 0; }
+long rl_plan_num_bn_buffers(const rl_plan* h) { return h ? h->p.n_bnbuf : 0; }
+
+int rl_plan_query(const rl_plan* h, int what, int index, long* out) {
+  if (!h || !out) return rl_fail(RL_ERR_ARG, "rl_plan_query: null argument");
+  const Plan& p = h->p;
+  const bool lvl_ok = index >= 0 && index < kLevels, lay_ok = index >= 0 && index < (int)p.layers.size();
+  switch (what) {
+    case 0: *out = (long)p.layers.size(); return RL_OK;
+    case 1: if (!lvl_ok) break; *out = (long)p.lv[index].act_off; return RL_OK;
+    case 2: if (!lvl_ok) break; *out = (long)p.lv[index].dact_off; return RL_OK;
+    case 3: if (!lvl_ok) break; *out = p.lv[index].Ct; return RL_OK;
+    case 4: if (!lvl_ok) break; *out = p.lv[index].H; return RL_OK;
+    case 5: if (!lvl_ok) break; *out = p.lv[index].W; return RL_OK;
+    case 6: if (!lvl_ok) break; *out = p.lv[index].Cskip; return RL_OK;
+    case 7: *out = (long)p.scal_off; return RL_OK;
+    case 8: if (!lay_ok) break; *out = p.layers[index].type; return RL_OK;
+    case 9: if (!lay_ok) break; *out = (long)p.layers[index].mask_off; return RL_OK;
+    case 10: if (!lay_ok) break; *out = p.layers[index].cout; return RL_OK;
+    case 11: if (!lay_ok) break; *out = p.layers[index].p_w; return RL_OK;
+    case 12: if (!lvl_ok) break; *out = (long)p.lv[index].stats_off; return RL_OK;
+    default: return rl_fail(RL_ERR_ARG, "rl_plan_query: unknown selector %d", what);
+  }
+  return rl_fail(RL_ERR_ARG, "rl_plan_query: index %d out of range for selector %d", index, what);
+}
+
+int rl_plan_bind(rl_plan* h, void* workspace, void* stream) {
+  if (!h || !workspace) return rl_fail(RL_ERR_ARG, "rl_plan_bind: null argument");
+  if (((uintptr_t)workspace & 255) != 0) return rl_fail(RL_ERR_ARG, "rl_plan_bind: workspace must be 256-byte aligned");
+  Plan& p = h->p;
+  p.ws = workspace;
+  cudaStream_t st = (cudaStream_t)stream;
+  // ---- weight packing table
+  std::vector<PackEntry> pk;
+  for (const Layer& L : p.layers) {
+    PackEntry e;
+    memset(&e, 0, sizeof(e));
+    e.cin = L.cin;
+    e.cs_perm = L.cs_perm;
+    e.p_w = L.p_w;
+    if (L.type == L_DENSE) {
+      int nkc = (L.cin + 63) / 64, nmb = (L.cin + 127) / 128;
+      e.kind = 0; e.dst_off = (long)L.wpk_fwd; e.n16 = (long)nkc * 8 * 144; pk.push_back(e);
+      e.kind = 1; e.dst_off = (long)L.wpk_bwd; e.n16 = (long)nmb * 18 * 128; pk.push_back(e);
+    } else if (L.type == L_TD) {
+      int nkc = (L.cin + 63) / 64, nmb = (L.cin + 127) / 128;
+      int n0[3], np[3];
+      td_parts(L.cin, n0, np);
+      e.np0 = np[0];
+      e.kind = 2; e.dst_off = (long)L.wpk_fwd; e.n16 = (long)nkc * 8 * L.cin; pk.push_back(e);
+      e.kind = 3; e.dst_off = (long)L.wpk_bwd; e.n16 = (long)nmb * nkc * 8 * 128; pk.push_back(e);
+    } else if (L.type == L_TU) {
+      e.kind = 4; e.dst_off = (long)L.wpk_fwd; e.n16 = 3L * 2 * 8 * 240; pk.push_back(e);
+      e.kind = 5; e.dst_off = (long)L.wpk_bwd; e.n16 = 12L * 8 * 80; pk.push_back(e);
+    }
+  }
+  p.n_pack = (int)pk.size();
+  RL_CUDA(cudaMemcpyAsync(wsb(&p) + p.packtab_off, pk.data(), pk.size() * sizeof(PackEntry), cudaMemcpyHostToDevice, st));
+  // ---- BN table
+  std::vector<BnTabEntry> bt;
+  for (const Layer& L : p.layers) {
+    if (L.bn_index < 0) continue;
+    BnTabEntry e;
+    const Level& lv = p.lv[L.lvl_in];
+    e.stats_byte_off = (long)lv.stats_off;
+    e.rm = L.b_rm;
+    e.rv = L.b_rv;
+    e.C = L.cin;
+    e.Ct = lv.Ct;
+    e.cs_perm = L.cs_perm;
+    e.inv_n = (float)(1.0 / (double)lv.px);
+    e.unbias = lv.px > 1 ? (float)((double)lv.px / (double)(lv.px - 1)) : 1.f;
+    bt.push_back(e);
+  }
+  p.n_bn = (int)bt.size();
+  RL_CUDA(cudaMemcpyAsync(wsb(&p) + p.bntab_off, bt.data(), bt.size() * sizeof(BnTabEntry), cudaMemcpyHostToDevice, st));
+  RL_CUDA(cudaStreamSynchronize(st));  // host vectors go out of scope
+  // dropout scales default to 1 (no dropout)
+  return rl_set_dropout(h, 0.f, 0, 0, stream);
+}
+
+int rl_pack_weights(rl_plan* h, const float* params, void* stream) {
+  if (!h || !h->p.ws) return rl_fail(RL_ERR_STATE, "rl_pack_weights: plan not bound");
+  return launch_pack_weights(&h->p, params, (cudaStream_t)stream);
+}
+
+int rl_set_dropout(rl_plan* h, float p_drop, unsigned long long seed, unsigned long long step, void* stream) {
+  if (!h || !h->p.ws) return rl_fail(RL_ERR_STATE, "rl_set_dropout: plan not bound");
+  if (p_drop < 0.f || p_drop >= 1.f) return rl_fail(RL_ERR_ARG, "rl_set_dropout: p_drop %f out of range", p_drop);
+  return launch_fill_masks((float*)(wsb(&h->p) + h->p.mask_off_all), (long)(h->p.mask_bytes / sizeof(float)), p_drop, seed,
+                           step, (cudaStream_t)stream);
+}
+
+int rl_forward(rl_plan* h, const float* params, const float* bnbuf, const float* x, int train, void* stream) {
+  if (!h || !h->p.ws) return rl_fail(RL_ERR_STATE, "rl_forward: plan not bound");
+  if (!params || !x || (!train && !bnbuf)) return rl_fail(RL_ERR_ARG, "rl_forward: null argument");
+  Plan* p = &h->p;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int sm = p->sm_count;
+  if (train) RL_CUDA(cudaMemsetAsync(wsb(p) + p->stats_off_all, 0, p->stats_bytes, st));
+  int rc;
+  for (const Layer& L : p->layers) {
+    const Level& li = p->lv[L.lvl_in];
+    const Level& lo = p->lv[L.lvl_out];
+    if (L.type == L_FIRST) {
+      if ((rc = launch_first_fwd(p, x, params, st))) return rc;
+      if (train && (rc = launch_channel_stats(act_of(p, 0), lo.px, lo.Ct, 0, kFirst, stats_of(p, 0), sm, st))) return rc;
+    } else if (L.type == L_DENSE) {
+      DenseFwdArgs a;
+      a.act = act_of(p, L.lvl_in);
+      a.act_out = act_of(p, L.lvl_in);
+      a.Ct = li.Ct;
+      a.Cin = L.cin;
+      a.H = li.H;
+      a.W = li.W;
+      a.rows_total = p->B * li.H;
+      a.strip_w = 160;
+      a.nstrips = (li.W + a.strip_w - 1) / a.strip_w;
+      int nruns = std::max(1, std::min(a.rows_total, (2 * sm) / a.nstrips));
+      a.rows_per_cta = (a.rows_total + nruns - 1) / nruns;
+      nruns = (a.rows_total + a.rows_per_cta - 1) / a.rows_per_cta;
+      a.wpk = wsb(p) + L.wpk_fwd;
+      a.bias = params + L.p_b;
+      a.mask = train ? (const float*)(wsb(p) + L.mask_off) : nullptr;
+      a.bn = make_bn(p, L, params, bnbuf, train);
+      a.stats_out = train ? stats_of(p, L.lvl_in) : nullptr;
+      if ((rc = launch_dense_fwd(a, nruns * a.nstrips, st))) return rc;
+    } else if (L.type == L_TD) {
+      GemmPxArgs a;
+      memset(&a, 0, sizeof(a));
+      a.A = act_of(p, L.lvl_in);
+      a.lda = li.Ct;
+      a.a_off = 0;
+      a.K = L.cin;
+      a.mode = GEMM_POOL;
+      a.H = li.H;
+      a.W = li.W;
+      a.Hp = lo.H;
+      a.Wp = lo.W;
+      a.wblocks = (lo.W + 31) / 32;
+      a.ntiles = (long)p->B * lo.H * a.wblocks;
+      a.transform = 1;
+      a.bn = make_bn(p, L, params, bnbuf, train);
+      a.wpk = wsb(p) + L.wpk_fwd;
+      a.N = L.cout;
+      int nparts = td_parts(L.cout, a.part_n0, a.part_np);
+      a.bias = params + L.p_b;
+      a.mask = train ? (const float*)(wsb(p) + L.mask_off) : nullptr;
+      a.out = act_of(p, L.lvl_out);
+      a.ldo = lo.Ct;
+      a.o_off = 0;
+      a.amax = (train && p->training) ? wsb(p) + L.amax_off : nullptr;
+      int gx = (int)std::max(1L, std::min(a.ntiles, (long)(2 * sm) / nparts));
+      if ((rc = launch_gemm_px(a, gx, nparts, st))) return rc;
+      if (train && (rc = launch_channel_stats(act_of(p, L.lvl_out), lo.px, lo.Ct, 0, L.cout, stats_of(p, L.lvl_out), sm, st)))
+        return rc;
+    } else {  // L_TU
+      GemmPxArgs a;
+      memset(&a, 0, sizeof(a));
+      a.A = act_of(p, L.lvl_in);
+      a.lda = li.Ct;
+      a.a_off = L.in_off;
+      a.K = kUpCh;
+      a.M = li.px;
+      a.ntiles = (li.px + 127) / 128;
+      a.mode = GEMM_LINEAR;
+      a.transform = 0;
+      a.wpk = wsb(p) + L.wpk_fwd;
+      a.N = 720;
+      for (int q = 0; q < 3; ++q) {
+        a.part_n0[q] = q * 240;
+        a.part_np[q] = 240;
+      }
+      a.out = (__nv_bfloat16*)(wsb(p) + p->tmp_off);
+      a.ldo = 720;
+      a.o_off = 0;
+      int gx = (int)std::max(1L, std::min(a.ntiles, (long)(2 * sm) / 3));
+      if ((rc = launch_gemm_px(a, gx, 3, st))) return rc;
+      if ((rc = launch_tu_col2im((const __nv_bfloat16*)(wsb(p) + p->tmp_off), act_of(p, L.lvl_out), params + L.p_b, p->B, li.H,
+                                 li.W, lo.H, lo.W, lo.Ct, L.out_off, st)))
+        return rc;
+      if (train && (rc = launch_channel_stats(act_of(p, L.lvl_out), lo.px, lo.Ct, L.out_off, kUpCh, stats_of(p, L.lvl_out), sm, st)))
+        return rc;
+    }
+  }
+  return RL_OK;
+}
+
+int rl_head(rl_plan* h, const float* params, const void* y, int y_is_i64, int weighted, float* probs, uint8_t* mask,
+            int backward, const float* dprobs, float grad_scale, float feat_grad_sign, float* grads, void* stream) {
+  if (!h || !h->p.ws) return rl_fail(RL_ERR_STATE, "rl_head: plan not bound");
+  Plan* p = &h->p;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (backward && (!p->training || !grads)) return rl_fail(RL_ERR_STATE, "rl_head: backward needs a training plan and grads");
+  if (backward == 2 && !dprobs) return rl_fail(RL_ERR_ARG, "rl_head: backward=2 needs dprobs");
+  if (backward == 1 && !y) return rl_fail(RL_ERR_ARG, "rl_head: fused CE backward needs labels");
+  RL_CUDA(cudaMemsetAsync(scal_of(p), 0, sizeof(Scalars), st));
+  int rc;
+  if (y && (rc = launch_label_hist(y, y_is_i64, p->lv[0].px, p->num_cls, scal_of(p), st))) return rc;
+  HeadArgs a;
+  memset(&a, 0, sizeof(a));
+  a.feat = act_of(p, 0);
+  a.Ct = p->lv[0].Ct;
+  a.npx = p->lv[0].px;
+  a.HW = p->H * p->W;
+  a.num_cls = p->num_cls;
+  a.w = params + p->p_cls_w;
+  a.b = params + p->p_cls_b;
+  a.y = y;
+  a.y_is_i64 = y_is_i64;
+  a.probs = probs;
+  a.mask_out = mask;
+  a.sc = scal_of(p);
+  a.weighted = weighted;
+  a.dprobs = backward == 2 ? dprobs : nullptr;
+  a.grad_scale = grad_scale;
+  a.feat_grad_sign = feat_grad_sign;
+  a.dact = backward ? dact_of(p, 0) : nullptr;
+  a.dl = backward ? (__nv_bfloat16*)(wsb(p) + p->dl_off) : nullptr;
+  a.g_b = backward ? grads + p->p_cls_b : nullptr;
+  return launch_head(a, p->sm_count, st);
+}
+
+int rl_bn_running_update(rl_plan* h, float* bnbuf, float momentum, void* stream) {
+  if (!h || !h->p.ws || !bnbuf) return rl_fail(RL_ERR_STATE, "rl_bn_running_update: plan not bound / null buffers");
+  return launch_bn_running(&h->p, bnbuf, momentum, (cudaStream_t)stream);
+}
+
+int rl_adamw_step(float* params, const float* grads, float* m, float* v, long n, float lr, float b1, float b2, float eps,
+                  float wd, long step, float grad_scale, void* stream) {
+  if (!params || !grads || !m || !v || n <= 0 || step < 1) return rl_fail(RL_ERR_ARG, "rl_adamw_step: bad argument");
+  const float bc1 = (float)(1.0 - pow((double)b1, (double)step)), bc2 = (float)(1.0 - pow((double)b2, (double)step));
+  return launch_adamw(params, grads, m, v, n, lr, b1, b2, eps, wd, bc1, bc2, grad_scale, (cudaStream_t)stream);
+}
+
+int rl_sgd_nesterov_step(float* params, const float* grads, float* buf, long n, float lr, float momentum, float wd,
+                         int first_step, float grad_scale, void* stream) {
+  if (!params || !grads || !buf || n <= 0) return rl_fail(RL_ERR_ARG, "rl_sgd_nesterov_step: bad argument");
+  return launch_sgd_nesterov(params, grads, buf, n, lr, momentum, wd, first_step, grad_scale, (cudaStream_t)stream);
+}
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------------------
+// backward schedule: reverse of the forward layer list
+// ------------------------------------------------------------------------------------------------
+static int wgrad_runs(const Plan* p, long npx, int nmb, int nparts, long* px_per_cta) {
+  long want = std::max(1L, (long)(2 * p->sm_count) / std::max(1, nmb * nparts));
+  long chunks = (npx + 63) / 64;
+  long runs = std::min(want, chunks);
+  long cpr = (chunks + runs - 1) / runs;
+  *px_per_cta = cpr * 64;
+  return (int)((npx + *px_per_cta - 1) / *px_per_cta);
+}
+
+extern "C" int rl_backward(rl_plan* h, const float* params, const float* x, float* grads, void* stream) {
+  if (!h || !h->p.ws) return rl_fail(RL_ERR_STATE, "rl_backward: plan not bound");
+  Plan* p = &h->p;
+  if (!p->training) return rl_fail(RL_ERR_STATE, "rl_backward: plan was created without training arenas");
+  if (!params || !grads) return rl_fail(RL_ERR_ARG, "rl_backward: null argument");
+  (void)x;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int sm = p->sm_count;
+  int rc;
+  RL_CUDA(cudaMemsetAsync(wsb(p) + p->acc_off_all, 0, p->acc_bytes, st));
+  __nv_bfloat16* tmp = (__nv_bfloat16*)(wsb(p) + p->tmp_off);
+  {  // classifier weight gradient: dW[k, c] = sum_p dl[p, k] * f[p, c]
+    WgradArgs w;
+    memset(&w, 0, sizeof(w));
+    w.kind = WG_HEAD;
+    w.A = act_of(p, 0);
+    w.lda = p->lv[0].Ct;
+    w.a_off = 0;
+    w.Ca = 288;
+    w.transform = 0;
+    w.Bm = (const __nv_bfloat16*)(wsb(p) + p->dl_off);
+    w.ldb = 16;
+    w.N = 16;
+    w.part_n0[0] = 0;
+    w.part_np[0] = 16;
+    w.npx = p->lv[0].px;
+    w.H = p->H;
+    w.W = p->W;
+    w.gw = grads + p->p_cls_w;
+    w.Cin_w = 288;
+    w.num_cls = p->num_cls;
+    int nruns = wgrad_runs(p, w.npx, 3, 1, &w.px_per_cta);
+    if ((rc = launch_wgrad(w, nruns, 3, 1, st))) return rc;
+  }
+  for (int li = (int)p->layers.size() - 1; li >= 0; --li) {
+    const Layer& L = p->layers[li];
+    const Level& lin = p->lv[L.lvl_in];
+    const Level& lout = p->lv[L.lvl_out];
+    DzArgs z;
+    memset(&z, 0, sizeof(z));
+    z.act = act_of(p, L.lvl_out);
+    z.dact = dact_of(p, L.lvl_out);
+    z.stats = stats_of(p, L.lvl_out);
+    z.acc = acc_of(p, L.lvl_out);
+    z.Ct = lout.Ct;
+    z.c_off = L.out_off;
+    z.nch = L.cout;
+    z.npx_out = lout.px;
+    z.inv_n_out = 1.0 / (double)lout.px;
+    z.HW_out = lout.H * lout.W;
+    z.dz = tmp;
+    z.g_bias = grads + L.p_b;
+    z.B = p->B;
+    if (L.type == L_DENSE) {
+      z.kind = 0;
+      z.mask = (const float*)(wsb(p) + L.mask_off);
+      if ((rc = launch_dz_prepare(z, sm, st))) return rc;
+      DgradArgs d;
+      memset(&d, 0, sizeof(d));
+      d.dense = 1;
+      d.dz = tmp;
+      d.Kdz = 16;
+      d.wpk = wsb(p) + L.wpk_bwd;
+      d.act = act_of(p, L.lvl_in);
+      d.dact = dact_of(p, L.lvl_in);
+      d.Ct = lin.Ct;
+      d.Cin = L.cin;
+      d.H = lin.H;
+      d.W = lin.W;
+      d.B = p->B;
+      d.rmw_from = L.rmw_from;
+      d.bn = make_bn(p, L, params, nullptr, 1);
+      d.g_gamma = grads + L.p_gamma;
+      d.g_beta = grads + L.p_beta;
+      d.acc = acc_of(p, L.lvl_in);
+      d.strip_w = 160;
+      d.nstrips = (lin.W + d.strip_w - 1) / d.strip_w;
+      const int vrows = p->B * (lin.H + 1);
+      int nruns = std::max(1, std::min(vrows, (3 * sm) / d.nstrips));
+      d.vrows_per_cta = (vrows + nruns - 1) / nruns;
+      nruns = (vrows + d.vrows_per_cta - 1) / d.vrows_per_cta;
+      if ((rc = launch_dgrad(d, nruns * d.nstrips, st))) return rc;
+      WgradArgs w;
+      memset(&w, 0, sizeof(w));
+      w.kind = WG_DENSE;
+      w.A = act_of(p, L.lvl_in);
+      w.lda = lin.Ct;
+      w.Ca = L.cin;
+      w.transform = 1;
+      w.bn = d.bn;
+      w.Bm = tmp;
+      w.ldb = 16;
+      w.N = 144;
+      w.part_n0[0] = 0;
+      w.part_np[0] = 144;
+      w.npx = lin.px;
+      w.H = lin.H;
+      w.W = lin.W;
+      w.gw = grads + L.p_w;
+      w.Cin_w = L.cin;
+      w.cs_perm = L.cs_perm;
+      const int nmb = (L.cin + 127) / 128;
+      int wr = wgrad_runs(p, w.npx, nmb, 1, &w.px_per_cta);
+      if ((rc = launch_wgrad(w, wr, nmb, 1, st))) return rc;
+    } else if (L.type == L_TD) {
+      z.kind = 1;
+      z.mask = (const float*)(wsb(p) + L.mask_off);
+      z.amax = wsb(p) + L.amax_off;
+      z.H = lin.H;
+      z.W = lin.W;
+      z.Hp = lout.H;
+      z.Wp = lout.W;
+      if ((rc = launch_dz_prepare(z, sm, st))) return rc;
+      DgradArgs d;
+      memset(&d, 0, sizeof(d));
+      d.dense = 0;
+      d.dz = tmp;
+      d.Kdz = L.cout;
+      d.wpk = wsb(p) + L.wpk_bwd;
+      d.act = act_of(p, L.lvl_in);
+      d.dact = dact_of(p, L.lvl_in);
+      d.Ct = lin.Ct;
+      d.Cin = L.cin;
+      d.H = lin.H;
+      d.W = lin.W;
+      d.B = p->B;
+      d.rmw_from = L.rmw_from;
+      d.bn = make_bn(p, L, params, nullptr, 1);
+      d.g_gamma = grads + L.p_gamma;
+      d.g_beta = grads + L.p_beta;
+      d.acc = acc_of(p, L.lvl_in);
+      d.ntiles = (lin.px + 127) / 128;
+      int grid = (int)std::max(1L, std::min(d.ntiles, (long)3 * sm));
+      if ((rc = launch_dgrad(d, grid, st))) return rc;
+      WgradArgs w;
+      memset(&w, 0, sizeof(w));
+      w.kind = WG_TD;
+      w.A = act_of(p, L.lvl_in);
+      w.lda = lin.Ct;
+      w.Ca = L.cin;
+      w.transform = 1;
+      w.bn = d.bn;
+      w.Bm = tmp;
+      w.ldb = L.cout;
+      w.N = L.cout;
+      int nparts = td_parts(L.cout, w.part_n0, w.part_np);
+      w.npx = lin.px;
+      w.H = lin.H;
+      w.W = lin.W;
+      w.gw = grads + L.p_w;
+      w.Cin_w = L.cin;
+      const int nmb = (L.cin + 127) / 128;
+      int wr = wgrad_runs(p, w.npx, nmb, nparts, &w.px_per_cta);
+      if ((rc = launch_wgrad(w, wr, nmb, nparts, st))) return rc;
+    } else if (L.type == L_TU) {
+      z.kind = 2;
+      z.H = lout.H;
+      z.W = lout.W;
+      z.Hp = lin.H;
+      z.Wp = lin.W;
+      if ((rc = launch_dz_prepare(z, sm, st))) return rc;
+      GemmPxArgs a;
+      memset(&a, 0, sizeof(a));
+      a.A = tmp;
+      a.lda = 720;
+      a.a_off = 0;
+      a.K = 720;
+      a.M = lin.px;
+      a.ntiles = (lin.px + 127) / 128;
+      a.mode = GEMM_LINEAR;
+      a.transform = 0;
+      a.wpk = wsb(p) + L.wpk_bwd;
+      a.N = kUpCh;
+      a.part_n0[0] = 0;
+      a.part_np[0] = kUpCh;
+      a.out = dact_of(p, L.lvl_in);
+      a.ldo = lin.Ct;
+      a.o_off = L.in_off;
+      int gx = (int)std::max(1L, std::min(a.ntiles, (long)2 * sm));
+      if ((rc = launch_gemm_px(a, gx, 1, st))) return rc;
+      WgradArgs w;
+      memset(&w, 0, sizeof(w));
+      w.kind = WG_TU;
+      w.A = act_of(p, L.lvl_in);
+      w.lda = lin.Ct;
+      w.a_off = L.in_off;
+      w.Ca = kUpCh;
+      w.transform = 0;
+      w.Bm = tmp;
+      w.ldb = 720;
+      w.N = 720;
+      for (int q = 0; q < 3; ++q) {
+        w.part_n0[q] = q * 240;
+        w.part_np[q] = 240;
+      }
+      w.npx = lin.px;
+      w.H = lin.H;
+      w.W = lin.W;
+      w.gw = grads + L.p_w;
+      int wr = wgrad_runs(p, w.npx, 1, 3, &w.px_per_cta);
+      if ((rc = launch_wgrad(w, wr, 1, 3, st))) return rc;
+    } else {  // L_FIRST: weight gradient only (the image needs no gradient)
+      z.kind = 0;
+      if ((rc = launch_dz_prepare(z, sm, st))) return rc;
+      WgradArgs w;
+      memset(&w, 0, sizeof(w));
+      w.kind = 4;  // WG_FIRST
+      w.A = (const __nv_bfloat16*)(wsb(p) + p->xcol_off);
+      w.lda = 32;
+      w.Ca = 27;
+      w.transform = 0;
+      w.Bm = tmp;
+      w.ldb = kFirst;
+      w.N = kFirst;
+      w.part_n0[0] = 0;
+      w.part_np[0] = kFirst;
+      w.npx = lout.px;
+      w.H = lout.H;
+      w.W = lout.W;
+      w.gw = grads + L.p_w;
+      int wr = wgrad_runs(p, w.npx, 1, 1, &w.px_per_cta);
+      if ((rc = launch_wgrad(w, wr, 1, 1, st))) return rc;
+    }
+  }
+  return RL_OK;
+}

@@ -6,7 +6,7 @@
 #include <stdint.h>
 #include <stdio.h>
 
-enum { RL_OK = 0, RL_ERR_ARG = -1, RL_ERR_SHAPE = -2, RL_ERR_CUDA = -3, RL_ERR_STATE = -4 };
+#include "rightlane.h"
 
 namespace rl {
 int rl_fail(int code, const char* fmt, ...);

@@ -1,0 +1,437 @@
+// rl_conv_fwd.cu — forward tensor-core kernels (tcgen05 / TMEM, operands staged in shared memory, weights by
+// 1-D bulk TMA):
+//   dense_fwd_kernel : BN -> ReLU -> Conv3x3(Cin -> 16) -> +bias -> Dropout2d scale -> concat-slice store (+ Σx, Σx²)
+//                      reference layers.py:5-12 (DenseLayer) and the torch.cat at layers.py:33,39
+//   gemm_px_kernel   : [pixels x K] x [K x N] pointwise GEMM with either the TransitionDown epilogue
+//                      (+bias, Dropout2d scale, MaxPool2d(2) floor; layers.py:43-52) or a plain bf16 store
+//                      (ConvTranspose2d column matrix, layers.py:61-63, and its input gradient)
+//
+// The growth-16 convolution is computed "taps-as-N": one GEMM  Y[p, (tap,co)] = Σ_c relu(bn(x))[p,c] · W[(tap,co), c]
+// with N = 9*16 = 144 and K = Cin, so every activation is read exactly once and never needs a halo; the
+// 3x3 structure is resolved on the 16-channel side by a shift-add (col2im) of the 9 tap planes in shared memory.
+#include "rl_common.cuh"
+#include "rl_dev.cuh"
+#include "rl_kernels.h"
+
+namespace rl {
+
+constexpr int kRing = 512;  // col2im ring, pixels
+
+// ================================================================================================
+// dense_fwd_kernel
+// ================================================================================================
+__global__ void __launch_bounds__(128, 2) dense_fwd_kernel(DenseFwdArgs a) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  // smem carve-up: s[Cin], t[Cin] floats | zs ring [4][kRing][4] floats | 2 stages x (A 16 KB + W 18 KB)
+  float* s_s = reinterpret_cast<float*>(smem);
+  float* s_t = s_s + a.Cin;
+  float* zs = reinterpret_cast<float*>(smem + (((size_t)a.Cin * 8 + 127) & ~(size_t)127));
+  uint8_t* stage_base = reinterpret_cast<uint8_t*>(zs) + 4 * kRing * 16;
+  constexpr int kStageBytes = 16384 + 18432;
+  __shared__ uint64_t bar_full[2], bar_done[2];
+  __shared__ uint32_t tmem_base_s;
+  __shared__ float red[4][32];
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  // ---- work item: rows [R0,R1) of the level (all images stacked), columns [x0,x1)
+  const int run = blockIdx.x / a.nstrips, strip = blockIdx.x % a.nstrips;
+  const int R0 = run * a.rows_per_cta, R1 = min(R0 + a.rows_per_cta, a.rows_total);
+  const int x0 = strip * a.strip_w, x1 = min(x0 + a.strip_w, a.W);
+  const int rin0 = max(R0 - 1, 0), rin1 = min(R1 + 1, a.rows_total);
+  const int xi0 = max(x0 - 1, 0), xi1 = min(x1 + 1, a.W);
+  const int SW = xi1 - xi0;
+  const int n_in = (rin1 - rin0) * SW;
+  const int ntiles = (n_in + 127) / 128;
+  const int nkc = (a.Cin + 63) / 64;
+
+  if (tid == 0) {
+    mbar_init(&bar_full[0], 1);
+    mbar_init(&bar_full[1], 1);
+    mbar_init(&bar_done[0], 1);
+    mbar_init(&bar_done[1], 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) tmem_alloc(&tmem_base_s, 256);
+  for (int c = tid; c < a.Cin; c += 128) {
+    BnCoef k = bn_coef(a.bn, c);
+    s_s[c] = k.s;
+    s_t[c] = k.t;
+  }
+  for (int i = tid; i < 4 * kRing * 4; i += 128) zs[i] = 0.f;
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_s;
+  const uint32_t idesc = umma_idesc_bf16(144, 0, 0);
+
+  float st_sum[16], st_sq[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) st_sum[i] = st_sq[i] = 0.f;
+
+  uint32_t g = 0;  // running chunk counter: stage = g & 1, use index = g >> 1
+  int emit_pos = 0;
+  TileLoader<128> ld;
+  const __nv_bfloat16* rowptr[4];
+
+  auto set_rowptrs = [&](int t0) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int t = t0 + TileLoader<128>::row_of(i);
+      if (t < n_in) {
+        const int rr = t / SW, cc = t - rr * SW;
+        rowptr[i] = a.act + ((size_t)(rin0 + rr) * a.W + (xi0 + cc)) * a.Ct;
+      } else {
+        rowptr[i] = nullptr;
+      }
+    }
+  };
+  auto shifted = [&](int kc) {
+    // row pointers advanced to the K-chunk (pointer arithmetic on nullptr avoided)
+  };
+  (void)shifted;
+
+  for (int tile = 0; tile < ntiles; ++tile) {
+    const int t0 = tile * 128;
+    set_rowptrs(t0);
+    // ---------------- main loop over K chunks of 64 channels
+    {
+      const __nv_bfloat16* rp[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) rp[i] = rowptr[i];
+      ld.load(rp, min(8, a.Cin / 8));
+    }
+    for (int kc = 0; kc < nkc; ++kc) {
+      const int ck = min(64, a.Cin - kc * 64);
+      const uint32_t s = g & 1, u = g >> 1;
+      uint8_t* sA = stage_base + s * kStageBytes;
+      uint8_t* sW = sA + 16384;
+      if (u > 0) mbar_wait(&bar_done[s], (u - 1) & 1);  // MMAs that read this stage have retired
+      if (tid == 0) {
+        const uint32_t wbytes = (uint32_t)(ck / 8) * 144 * 16;
+        mbar_arrive_expect_tx(&bar_full[s], wbytes);
+        bulk_g2s(sW, a.wpk + (size_t)kc * 18432, wbytes, &bar_full[s]);
+      }
+      ld.store(sA, rowptr, ck / 8, s_s + kc * 64, s_t + kc * 64);
+      if (kc + 1 < nkc) {  // prefetch next chunk while this one is consumed
+        const __nv_bfloat16* rp[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) rp[i] = rowptr[i] ? rowptr[i] + (kc + 1) * 64 : nullptr;
+        ld.load(rp, min(8, (a.Cin - (kc + 1) * 64) / 8));
+      }
+      fence_proxy_async();
+      __syncthreads();
+      if (tid == 0) {
+        mbar_wait(&bar_full[s], u & 1);
+        tc_fence_after();
+        const uint32_t aaddr = smem_u32(sA), waddr = smem_u32(sW);
+        for (int kk = 0; kk < ck / 16; ++kk)
+          umma_ss(tmem, desc_kmajor(aaddr + kk * 2 * 16 * 128, 128), desc_kmajor(waddr + kk * 2 * 16 * 144, 144), idesc,
+                  (kc | kk) != 0);
+        umma_commit(&bar_done[s]);
+      }
+      ++g;
+    }
+    // ---------------- accumulator ready: the commit of the last chunk covers every MMA of this tile
+    {
+      const uint32_t s = (g - 1) & 1, u = (g - 1) >> 1;
+      mbar_wait(&bar_done[s], u & 1);
+      tc_fence_after();
+    }
+    // ---------------- col2im scatter of the 9 tap planes
+    const int t = t0 + tid;
+    const bool in_valid = t < n_in;
+    int rr = 0, cc = 0;
+    if (in_valid) {
+      rr = t / SW;
+      cc = t - rr * SW;
+    }
+    const int r = rin0 + rr, xx = xi0 + cc;
+    const int ri = r % a.H;
+#pragma unroll 1
+    for (int tap = 0; tap < 9; ++tap) {
+      const int dy = tap / 3 - 1, dx = tap % 3 - 1;
+      float v[16];
+      tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16) + tap * 16, v);
+      const int qr = r - dy, qx = xx - dx, qi = ri - dy;
+      if (in_valid && qi >= 0 && qi < a.H && qr >= R0 && qr < R1 && qx >= x0 && qx < x1) {
+        const int uidx = (t - dy * SW - dx + SW + 1) & (kRing - 1);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          float4* p = reinterpret_cast<float4*>(zs + ((size_t)q * kRing + uidx) * 4);
+          float4 o = *p;
+          o.x += v[q * 4 + 0];
+          o.y += v[q * 4 + 1];
+          o.z += v[q * 4 + 2];
+          o.w += v[q * 4 + 3];
+          *p = o;
+        }
+      }
+      tc_fence_before();
+      __syncthreads();
+    }
+    // ---------------- emit finished output pixels
+    const int lim = (tile == ntiles - 1) ? n_in : max(0, min(t0 + 128 - SW - 1, n_in));
+    for (int e0 = emit_pos; e0 < lim; e0 += 128) {
+      const int e = e0 + tid;
+      if (e < lim) {
+        const int er = e / SW, ec = e - er * SW;
+        const int orow = rin0 + er, ox = xi0 + ec;
+        if (orow >= R0 && orow < R1 && ox >= x0 && ox < x1) {
+          const int uidx = (e + SW + 1) & (kRing - 1);
+          const int img = orow / a.H;
+          float o[16];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            float4* p = reinterpret_cast<float4*>(zs + ((size_t)q * kRing + uidx) * 4);
+            float4 z = *p;
+            *p = make_float4(0.f, 0.f, 0.f, 0.f);
+            o[q * 4 + 0] = z.x;
+            o[q * 4 + 1] = z.y;
+            o[q * 4 + 2] = z.z;
+            o[q * 4 + 3] = z.w;
+          }
+          uint32_t pk[8];
+#pragma unroll
+          for (int c = 0; c < 16; c += 2) {
+            float m0 = a.mask ? a.mask[img * 16 + c] : 1.f, m1 = a.mask ? a.mask[img * 16 + c + 1] : 1.f;
+            float y0 = (o[c] + a.bias[c]) * m0, y1 = (o[c + 1] + a.bias[c + 1]) * m1;
+            pk[c >> 1] = pack_bf16x2(y0, y1);
+            float2 rb = unpack_bf16x2(pk[c >> 1]);
+            st_sum[c] += rb.x;
+            st_sq[c] += rb.x * rb.x;
+            st_sum[c + 1] += rb.y;
+            st_sq[c + 1] += rb.y * rb.y;
+          }
+          uint4* dst = reinterpret_cast<uint4*>(a.act_out + ((size_t)orow * a.W + ox) * a.Ct + a.Cin);
+          dst[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          dst[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+        }
+      }
+    }
+    emit_pos = max(emit_pos, lim);
+    __syncthreads();
+  }
+
+  // ---------------- per-channel Σx, Σx² of the 16 new channels (fp32 per thread -> fp64 atomics)
+  if (a.stats_out != nullptr) {
+#pragma unroll
+    for (int c = 0; c < 16; ++c) {
+      float s1 = warp_sum(st_sum[c]), s2 = warp_sum(st_sq[c]);
+      if (lane == 0) {
+        red[warp][c] = s1;
+        red[warp][16 + c] = s2;
+      }
+    }
+    __syncthreads();
+    if (tid < 32) {
+      float v = red[0][tid] + red[1][tid] + red[2][tid] + red[3][tid];
+      const int c = tid & 15;
+      atomicAdd(a.stats_out + (tid < 16 ? 0 : a.Ct) + a.Cin + c, (double)v);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 256);
+}
+
+size_t dense_fwd_smem(int Cin) { return (((size_t)Cin * 8 + 127) & ~(size_t)127) + 4 * kRing * 16 + 2 * (16384 + 18432); }
+
+// ================================================================================================
+// gemm_px_kernel
+// ================================================================================================
+__global__ void __launch_bounds__(128, 2) gemm_px_kernel(GemmPxArgs a) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  float* s_s = reinterpret_cast<float*>(smem);
+  float* s_t = s_s + a.K;
+  uint8_t* stage_base = smem + (((size_t)a.K * 8 + 127) & ~(size_t)127);
+  const int part = blockIdx.y;
+  const int n0 = a.part_n0[part], np = a.part_np[part];
+  const int stageB = 8 * np * 16;           // bytes of one packed weight chunk slot for this part
+  const int kStageBytes = 16384 + stageB;
+  __shared__ uint64_t bar_full[2], bar_done[2];
+  __shared__ uint32_t tmem_base_s;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int nkc = (a.K + 63) / 64;
+  const uint8_t* wpart = a.wpk + (size_t)nkc * 8 * 16 * n0;  // parts are stored back to back
+
+  if (tid == 0) {
+    mbar_init(&bar_full[0], 1);
+    mbar_init(&bar_full[1], 1);
+    mbar_init(&bar_done[0], 1);
+    mbar_init(&bar_done[1], 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) tmem_alloc(&tmem_base_s, 256);
+  if (a.transform)
+    for (int c = tid; c < a.K; c += 128) {
+      BnCoef k = bn_coef(a.bn, c);
+      s_s[c] = k.s;
+      s_t[c] = k.t;
+    }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_s;
+  const uint32_t idesc = umma_idesc_bf16((uint32_t)np, 0, 0);
+
+  uint32_t g = 0;
+  TileLoader<128> ld;
+  const __nv_bfloat16* rowptr[4];
+
+  for (long tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
+    // ---- row -> pixel mapping
+    int pr = 0, wb = 0;
+    if (a.mode == GEMM_POOL) {
+      pr = (int)(tile / a.wblocks);
+      wb = (int)(tile % a.wblocks);
+    }
+    auto pixel_of_row = [&](int m) -> long {
+      if (a.mode == GEMM_POOL) {
+        const int win = m >> 2, q = m & 3;
+        const int wi = wb * 32 + win;
+        if (wi >= a.Wp) return -1;
+        const int img = pr / a.Hp, py = pr % a.Hp;
+        return ((long)img * a.H + 2 * py + (q >> 1)) * a.W + 2 * wi + (q & 1);
+      } else {
+        const long P = tile * 128 + m;
+        return P < a.M ? P : -1;
+      }
+    };
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const long P = pixel_of_row(TileLoader<128>::row_of(i));
+      rowptr[i] = P >= 0 ? a.A + (size_t)P * a.lda + a.a_off : nullptr;
+    }
+    ld.load(rowptr, min(8, a.K / 8));
+    for (int kc = 0; kc < nkc; ++kc) {
+      const int ck = min(64, a.K - kc * 64);
+      const uint32_t s = g & 1, u = g >> 1;
+      uint8_t* sA = stage_base + s * kStageBytes;
+      uint8_t* sW = sA + 16384;
+      if (u > 0) mbar_wait(&bar_done[s], (u - 1) & 1);
+      if (tid == 0) {
+        const uint32_t wbytes = (uint32_t)(ck / 8) * np * 16;
+        mbar_arrive_expect_tx(&bar_full[s], wbytes);
+        bulk_g2s(sW, wpart + (size_t)kc * stageB, wbytes, &bar_full[s]);
+      }
+      ld.store(sA, rowptr, ck / 8, a.transform ? s_s + kc * 64 : nullptr, s_t + kc * 64);
+      if (kc + 1 < nkc) {
+        const __nv_bfloat16* rp[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) rp[i] = rowptr[i] ? rowptr[i] + (kc + 1) * 64 : nullptr;
+        ld.load(rp, min(8, (a.K - (kc + 1) * 64) / 8));
+      }
+      fence_proxy_async();
+      __syncthreads();
+      if (tid == 0) {
+        mbar_wait(&bar_full[s], u & 1);
+        tc_fence_after();
+        const uint32_t aaddr = smem_u32(sA), waddr = smem_u32(sW);
+        for (int kk = 0; kk < ck / 16; ++kk)
+          umma_ss(tmem, desc_kmajor(aaddr + kk * 2 * 16 * 128, 128), desc_kmajor(waddr + kk * 2 * 16 * np, np), idesc,
+                  (kc | kk) != 0);
+        umma_commit(&bar_done[s]);
+      }
+      ++g;
+    }
+    {
+      const uint32_t s = (g - 1) & 1, u = (g - 1) >> 1;
+      mbar_wait(&bar_done[s], u & 1);
+      tc_fence_after();
+    }
+    // ---- epilogue: thread = accumulator row
+    const long P = pixel_of_row(tid);
+    if (a.mode == GEMM_POOL) {
+      const int win = tid >> 2, q = tid & 3, wi = wb * 32 + win;
+      const int img = pr / a.Hp, py = pr % a.Hp;
+      const bool valid = wi < a.Wp;
+      const size_t opx = ((size_t)img * a.Hp + py) * a.Wp + wi;
+      for (int c0 = 0; c0 < np; c0 += 16) {
+        float v[16];
+        tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16) + c0, v);
+        uint32_t pk[8];
+        uint32_t am[4] = {0, 0, 0, 0};
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const int n = n0 + c0 + i;
+          float m = a.mask ? a.mask[img * a.N + n] : 1.f;
+          float y = (v[i] + a.bias[n]) * m;
+          int bq = q;
+#pragma unroll
+          for (int o = 1; o <= 2; o <<= 1) {
+            float oy = __shfl_xor_sync(0xffffffffu, y, o);
+            int oq = __shfl_xor_sync(0xffffffffu, bq, o);
+            if (oy > y || (oy == y && oq < bq)) {
+              y = oy;
+              bq = oq;
+            }
+          }
+          v[i] = y;
+          am[i >> 2] |= (uint32_t)bq << (8 * (i & 3));
+        }
+        if (valid && q == 0) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) pk[i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
+          uint4* dst = reinterpret_cast<uint4*>(a.out + opx * a.ldo + a.o_off + n0 + c0);
+          dst[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          dst[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+          if (a.amax) *reinterpret_cast<uint4*>(a.amax + opx * a.N + n0 + c0) = make_uint4(am[0], am[1], am[2], am[3]);
+        }
+      }
+    } else {
+      for (int c0 = 0; c0 < np; c0 += 16) {
+        float v[16];
+        tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16) + c0, v);
+        if (P >= 0) {
+          uint32_t pk[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) pk[i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
+          uint4* dst = reinterpret_cast<uint4*>(a.out + (size_t)P * a.ldo + a.o_off + n0 + c0);
+          dst[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          dst[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+        }
+      }
+    }
+    tc_fence_before();
+    __syncthreads();
+  }
+  (void)lane;
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 256);
+}
+
+size_t gemm_px_smem(int K, int np_max) { return (((size_t)K * 8 + 127) & ~(size_t)127) + 2 * (16384 + (size_t)8 * np_max * 16); }
+
+// ------------------------------------------------------------------------------------------------ launchers
+int launch_dense_fwd(const DenseFwdArgs& a, int grid, cudaStream_t st) {
+  size_t smem = dense_fwd_smem(a.Cin);
+  static size_t configured = 0;
+  if (smem > configured) {
+    RL_CUDA(cudaFuncSetAttribute(dense_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
+    configured = 110 * 1024;
+  }
+  if (smem > 110 * 1024) return rl_fail(RL_ERR_SHAPE, "dense_fwd: smem %zu too large", smem);
+  dense_fwd_kernel<<<grid, 128, smem, st>>>(a);
+  RL_CUDA(cudaGetLastError());
+  return RL_OK;
+}
+
+int launch_gemm_px(const GemmPxArgs& a, int grid_x, int nparts, cudaStream_t st) {
+  int npmax = 0;
+  for (int i = 0; i < nparts; ++i) npmax = a.part_np[i] > npmax ? a.part_np[i] : npmax;
+  size_t smem = gemm_px_smem(a.K, npmax);
+  static bool configured = false;
+  if (!configured) {
+    RL_CUDA(cudaFuncSetAttribute(gemm_px_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
+    configured = true;
+  }
+  if (smem > 110 * 1024) return rl_fail(RL_ERR_SHAPE, "gemm_px: smem %zu too large (K=%d np=%d)", smem, a.K, npmax);
+  gemm_px_kernel<<<dim3(grid_x, nparts), 128, smem, st>>>(a);
+  RL_CUDA(cudaGetLastError());
+  return RL_OK;
+}
+
+}  // namespace rl

@@ -1,0 +1,155 @@
+// rl_kernels.h — argument blocks and launchers of the device kernels (internal to librightlane.so).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include "rl_dev.cuh"
+#include "rl_plan.h"
+
+namespace rl {
+
+// ---------------------------------------------------------------- forward, tensor core
+struct DenseFwdArgs {
+  const __nv_bfloat16* act;  // level arena (input prefix [0,Cin))
+  __nv_bfloat16* act_out;    // same arena (output slice [Cin, Cin+16))
+  int Ct, Cin, H, W, rows_total;
+  int rows_per_cta, nstrips, strip_w;
+  const uint8_t* wpk;        // packed bf16 weights, K chunks of 64: [jc][144][8]
+  const float* bias;         // [16]
+  const float* mask;         // [B][16] dropout scale or null
+  BnSrc bn;
+  double* stats_out;         // level stats base (Σx at [c], Σx² at [Ct+c]) or null
+};
+int launch_dense_fwd(const DenseFwdArgs& a, int grid, cudaStream_t st);
+
+enum { GEMM_LINEAR = 0, GEMM_POOL = 1 };
+struct GemmPxArgs {
+  const __nv_bfloat16* A;
+  int lda, a_off, K;
+  long M;           // rows (LINEAR)
+  long ntiles;
+  int mode;
+  int H, W, Hp, Wp, wblocks;  // POOL geometry
+  int transform;
+  BnSrc bn;
+  const uint8_t* wpk;
+  int N;            // total output columns (all parts)
+  int part_n0[3], part_np[3];
+  const float* bias;
+  const float* mask;
+  __nv_bfloat16* out;
+  int ldo, o_off;
+  uint8_t* amax;
+};
+int launch_gemm_px(const GemmPxArgs& a, int grid_x, int nparts, cudaStream_t st);
+
+// ---------------------------------------------------------------- backward, tensor core
+struct DgradArgs {
+  // G^T[c, p] = Σ_k W^T[c, k] · dz[p(-tap shift), k]; epilogue: ReLU mask, BN-backward sums, accumulate into dX
+  int dense;                 // 1: 3x3 growth-16 layer (9 taps, halo tile); 0: 1x1 TransitionDown (K = Kdz, streamed)
+  const __nv_bfloat16* dz;   // dense: [px][16]; td: [px][Kdz]
+  int Kdz;
+  const uint8_t* wpk;        // dense: per M-block [18][128][8]; td: per M-block, per K chunk [8][128][8]
+  const __nv_bfloat16* act;  // level arena
+  __nv_bfloat16* dact;       // gradient arena (same geometry)
+  int Ct, Cin, H, W, B;
+  int rmw_from;
+  BnSrc bn;
+  float* g_gamma;            // reference-ordered gradient slots
+  float* g_beta;
+  double* acc;               // level accumulators: A at [c], B at [Ct+c]
+  int vrows_per_cta, nstrips, strip_w;  // dense work decomposition (virtual rows: H+1 per image)
+  long ntiles;                           // td: 128-pixel tiles
+};
+int launch_dgrad(const DgradArgs& a, int grid, cudaStream_t st);
+
+enum { WG_DENSE = 0, WG_TD = 1, WG_TU = 2, WG_HEAD = 3 };
+struct WgradArgs {
+  // dW^T[c, n] = Σ_p A[p, c] · Bm[p, n]   (A optionally relu(bn(.)))
+  int kind;
+  const __nv_bfloat16* A;    // arena
+  int lda, a_off, Ca;        // Ca = valid A channels
+  int transform;
+  BnSrc bn;
+  const __nv_bfloat16* Bm;   // dense: dz16 [px][16]; else row-major [px][ldb]
+  int ldb;
+  int N;                     // total B columns (dense: 144)
+  int part_n0[3], part_np[3];
+  long npx;
+  int H, W;                  // dense: level geometry for the tap gather
+  long px_per_cta;
+  float* gw;                 // gradient slot of the weight tensor (fp32 atomics)
+  int Cin_w;                 // dense/td: Cin of the weight tensor; head: 288
+  int cs_perm;
+  int num_cls;
+};
+int launch_wgrad(const WgradArgs& a, int nruns, int nmb, int nparts, cudaStream_t st);
+
+// ---------------------------------------------------------------- CUDA-core kernels (rl_misc.cu)
+int launch_pack_weights(const Plan* p, const float* params, cudaStream_t st);
+int launch_first_fwd(const Plan* p, const float* x, const float* params, cudaStream_t st);
+int launch_channel_stats(const __nv_bfloat16* arena, long npx, int Ct, int c_off, int nch, double* stats, int sm,
+                         cudaStream_t st);
+int launch_tu_col2im(const __nv_bfloat16* ycol, __nv_bfloat16* out, const float* bias, int B, int h, int w, int H,
+                     int W, int Ct, int o_off, cudaStream_t st);
+int launch_label_hist(const void* y, int y_is_i64, long n, int num_cls, Scalars* sc, cudaStream_t st);
+
+struct HeadArgs {
+  const __nv_bfloat16* feat;  // level-0 arena (288 channels)
+  int Ct;
+  long npx;
+  int HW;                     // pixels per image
+  int num_cls;
+  const float* w;             // [C][288] reference order
+  const float* b;             // [C]
+  const void* y;              // labels (uint8 or int64) or null
+  int y_is_i64;
+  float* probs;               // [B][C][H][W] fp32 or null
+  uint8_t* mask_out;          // argmax [px] or null
+  Scalars* sc;                // histogram in, loss / confusion out
+  int weighted;               // 1: class-weighted CE (training_step), 0: plain CE (evaluate_batch)
+  // backward (null dact = forward only)
+  const float* dprobs;        // external d(loss)/d(probs) [B][C][H][W] or null -> fused CE gradient
+  float grad_scale;           // multiplies the fused CE gradient (grad_output of the loss)
+  float feat_grad_sign;       // -1 for GradReverse between extractor and classifier (tiramisu.py:7-18)
+  __nv_bfloat16* dact;
+  __nv_bfloat16* dl;          // [px][16] bf16: d(logits)/||f||
+  float* g_b;                 // classifier bias gradient slot
+};
+int launch_head(const HeadArgs& a, int sm, cudaStream_t st);
+
+struct DzArgs {
+  int kind;                   // 0: same-resolution slice (dense / first conv); 1: TD (max-pool scatter); 2: TU (column matrix)
+  const __nv_bfloat16* act;   // producer's output arena
+  const __nv_bfloat16* dact;
+  const double* stats;        // of the output arena
+  const double* acc;
+  int Ct, c_off, nch;
+  long npx_out;               // pixels of the output arena
+  double inv_n_out;
+  const float* mask;          // [B][nch] or null
+  int HW_out;                 // pixels per image of the output arena
+  __nv_bfloat16* dz;          // result
+  float* g_bias;              // Σ dz per channel -> conv bias gradient (fp32 atomics)
+  // TD: output arena is the pooled level; dz is written at the input resolution [px_in][nch]
+  const uint8_t* amax;
+  int H, W, Hp, Wp, B;        // TD: input H,W and pooled Hp,Wp.  TU: input (low-res) h=Hp,w=Wp and output H,W
+};
+int launch_dz_prepare(const DzArgs& a, int sm, cudaStream_t st);
+
+int launch_first_wgrad(const Plan* p, const float* x, const __nv_bfloat16* dz48, float* gw, cudaStream_t st);
+
+struct BnTabEntry {
+  long stats_byte_off;  // level stats base in workspace
+  long rm, rv;          // float offsets into the BN-buffer arena
+  int C, Ct, cs_perm;
+  float inv_n, unbias;  // 1/N, N/(N-1)
+};
+int launch_bn_running(const Plan* p, float* bnbuf, float momentum, cudaStream_t st);
+int launch_adamw(float* p, const float* g, float* m, float* v, long n, float lr, float b1, float b2, float eps, float wd,
+                 float bc1, float bc2, float grad_scale, cudaStream_t st);
+int launch_sgd_nesterov(float* p, const float* g, float* buf, long n, float lr, float momentum, float wd, int first,
+                        float grad_scale, cudaStream_t st);
+int launch_fill_masks(float* masks, long n, float p_drop, unsigned long long seed, unsigned long long step, cudaStream_t st);
+
+}  // namespace rl

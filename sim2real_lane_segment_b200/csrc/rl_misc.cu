@@ -1,0 +1,731 @@
+// rl_misc.cu — memory-bound CUDA-core kernels: weight packing, first conv (K=27), channel statistics,
+// transposed-conv col2im, the fused classifier head (normalize -> 1x1 -> /T -> softmax -> CE-on-probabilities ->
+// argmax -> confusion counts, forward and backward), output-gradient preparation (deferred BatchNorm
+// correction, max-pool scatter, transposed-conv column matrix), BN running statistics, AdamW / SGD, dropout masks.
+#include "rl_common.cuh"
+#include "rl_dev.cuh"
+#include "rl_kernels.h"
+
+namespace rl {
+
+static inline int cdiv(long a, long b) { return (int)((a + b - 1) / b); }
+
+// ================================================================================================
+// weight packing (fp32 reference layouts -> bf16 chunk-layout operands), one table-driven launch
+// ================================================================================================
+__device__ __forceinline__ uint4 pack8(const float* v) {
+  return make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+}
+
+__global__ void pack_weights_kernel(const PackEntry* tab, const float* __restrict__ params, uint8_t* ws) {
+  const PackEntry e = tab[blockIdx.y];
+  const float* w = params + e.p_w;
+  uint4* dst = reinterpret_cast<uint4*>(ws + e.dst_off);
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < e.n16; i += (long)gridDim.x * blockDim.x) {
+    float v[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = 0.f;
+    const int C = e.cin;
+    switch (e.kind) {
+      case 0: {  // dense fwd: [kc][jc][n=tap*16+co][8 c]
+        int kc = (int)(i / (8 * 144)), rem = (int)(i % (8 * 144)), jc = rem / 144, n = rem % 144;
+        int c0 = kc * 64 + jc * 8, tap = n / 16, co = n % 16;
+        if (c0 < C)
+          for (int k = 0; k < 8; ++k) v[k] = w[((long)co * C + ref_channel(c0 + k, e.cs_perm)) * 9 + tap];
+        break;
+      }
+      case 1: {  // dense bwd: [mb][j=tap*2+half][cl][8 co]
+        int mb = (int)(i / (18 * 128)), rem = (int)(i % (18 * 128)), j = rem / 128, cl = rem % 128;
+        int tap = j >> 1, half = j & 1, c = mb * 128 + cl;
+        if (c < C)
+          for (int k = 0; k < 8; ++k) v[k] = w[((long)(half * 8 + k) * C + ref_channel(c, e.cs_perm)) * 9 + tap];
+        break;
+      }
+      case 2: {  // TD fwd: parts back to back, [kc][jc][nl][8 c]
+        int nkc = (C + 63) / 64;
+        long p0 = (long)nkc * 8 * e.np0;
+        int n0 = 0, np = e.np0;
+        long il = i;
+        if (i >= p0) {
+          il = i - p0;
+          n0 = e.np0;
+          np = C - e.np0;
+        }
+        int kc = (int)(il / (8 * np)), jc = (int)((il % (8 * np)) / np), nl = (int)(il % np);
+        int c0 = kc * 64 + jc * 8, co = n0 + nl;
+        for (int k = 0; k < 8; ++k)
+          if (c0 + k < C) v[k] = w[(long)co * C + c0 + k];
+        break;
+      }
+      case 3: {  // TD bwd: [mb][kc][jc][cl][8 co]
+        int nkc = (C + 63) / 64;
+        int mb = (int)(i / ((long)nkc * 8 * 128)), rem = (int)(i % ((long)nkc * 8 * 128));
+        int kc = rem / (8 * 128), jc = (rem / 128) % 8, cl = rem % 128;
+        int c = mb * 128 + cl, co0 = kc * 64 + jc * 8;
+        if (c < C)
+          for (int k = 0; k < 8; ++k)
+            if (co0 + k < C) v[k] = w[(long)(co0 + k) * C + c];
+        break;
+      }
+      case 4: {  // TU fwd: [q][kc][jc][nl][8 ci], n = q*240+nl = tap*80+co; weight [ci][co][3][3]
+        int q = (int)(i / (2 * 8 * 240)), kc = (int)((i / (8 * 240)) % 2), jc = (int)((i / 240) % 8), nl = (int)(i % 240);
+        int ci0 = kc * 64 + jc * 8, n = q * 240 + nl, tap = n / 80, co = n % 80;
+        for (int k = 0; k < 8; ++k)
+          if (ci0 + k < 80) v[k] = w[((long)(ci0 + k) * 80 + co) * 9 + tap];
+        break;
+      }
+      case 5: {  // TU bwd: [kc][jc][ci][8 n]
+        int kc = (int)(i / (8 * 80)), jc = (int)((i / 80) % 8), ci = (int)(i % 80);
+        int nb = kc * 64 + jc * 8;
+        for (int k = 0; k < 8; ++k) {
+          int n = nb + k;
+          if (n < 720) v[k] = w[((long)ci * 80 + n % 80) * 9 + n / 80];
+        }
+        break;
+      }
+    }
+    dst[i] = pack8(v);
+  }
+}
+
+int launch_pack_weights(const Plan* p, const float* params, cudaStream_t st) {
+  const PackEntry* tab = reinterpret_cast<const PackEntry*>((const uint8_t*)p->ws + p->packtab_off);
+  pack_weights_kernel<<<dim3(24, p->n_pack), 256, 0, st>>>(tab, params, (uint8_t*)p->ws);
+  RL_CUDA(cudaGetLastError());
+  return RL_OK;
+}
+
+// ================================================================================================
+// first convolution: Conv3x3(3 -> 48, pad 1) on fp32 NCHW input (reference tiramisu.py:33-35)
+// ================================================================================================
+__global__ void __launch_bounds__(256) first_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                        const float* __restrict__ bias, __nv_bfloat16* act, int Ct, int B,
+                                                        int H, int W, __nv_bfloat16* xcol) {
+  __shared__ float sw[48 * 27 + 48];
+  for (int i = threadIdx.x; i < 48 * 27; i += blockDim.x) sw[i] = w[i];
+  for (int i = threadIdx.x; i < 48; i += blockDim.x) sw[48 * 27 + i] = bias[i];
+  __syncthreads();
+  const long npx = (long)B * H * W;
+  const long HW = (long)H * W;
+  for (long P = blockIdx.x * (long)blockDim.x + threadIdx.x; P < npx; P += (long)gridDim.x * blockDim.x) {
+    const int b = (int)(P / HW), hw = (int)(P % HW), y = hw / W, xx = hw % W;
+    float in[27];
+#pragma unroll
+    for (int ci = 0; ci < 3; ++ci)
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+          const int yy = y + ky - 1, xq = xx + kx - 1;
+          in[ci * 9 + ky * 3 + kx] =
+              (yy >= 0 && yy < H && xq >= 0 && xq < W) ? __ldg(x + ((long)(b * 3 + ci) * H + yy) * W + xq) : 0.f;
+        }
+    if (xcol != nullptr) {  // bf16 im2col row kept for the weight gradient (27 taps + 5 zero columns)
+      uint32_t pk[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) pk[i] = pack_bf16x2(2 * i < 27 ? in[2 * i] : 0.f, 2 * i + 1 < 27 ? in[2 * i + 1] : 0.f);
+      uint4* d = reinterpret_cast<uint4*>(xcol + P * 32);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) d[i] = make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
+    }
+    uint4* dst = reinterpret_cast<uint4*>(act + P * Ct);
+#pragma unroll
+    for (int g = 0; g < 6; ++g) {
+      float o[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int co = g * 8 + k;
+        float acc = sw[48 * 27 + co];
+#pragma unroll
+        for (int i = 0; i < 27; ++i) acc = fmaf(in[i], sw[co * 27 + i], acc);
+        o[k] = acc;
+      }
+      dst[g] = pack8(o);
+    }
+  }
+}
+
+int launch_first_fwd(const Plan* p, const float* x, const float* params, cudaStream_t st) {
+  const Layer& L = p->layers[0];
+  __nv_bfloat16* act = (__nv_bfloat16*)((uint8_t*)p->ws + p->lv[0].act_off);
+  __nv_bfloat16* xcol = p->training ? (__nv_bfloat16*)((uint8_t*)p->ws + p->xcol_off) : nullptr;
+  first_fwd_kernel<<<p->sm_count * 4, 256, 0, st>>>(x, params + L.p_w, params + L.p_b, act, p->lv[0].Ct, p->B, p->H, p->W,
+                                                    xcol);
+  RL_CUDA(cudaGetLastError());
+  return RL_OK;
+}
+
+// ================================================================================================
+// per-channel Σx, Σx² of an arena slice (channels [c_off, c_off+nch), nch % 8 == 0)
+// ================================================================================================
+__global__ void __launch_bounds__(256) channel_stats_kernel(const __nv_bfloat16* __restrict__ arena, long npx, int Ct,
+                                                            int c_off, int nch, double* stats) {
+  extern __shared__ float sred[];  // [blockDim][16]
+  const int nchunk = nch / 8;
+  const int ppb = blockDim.x / nchunk;  // pixel lanes per block
+  const int j = threadIdx.x % nchunk, pl = threadIdx.x / nchunk;
+  float s[8], q[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) s[k] = q[k] = 0.f;
+  if (pl < ppb) {
+    for (long P = (long)blockIdx.x * ppb + pl; P < npx; P += (long)gridDim.x * ppb) {
+      uint4 v = ldg128(arena + P * Ct + c_off + j * 8);
+      float2 a = unpack_bf16x2(v.x), b = unpack_bf16x2(v.y), c = unpack_bf16x2(v.z), d = unpack_bf16x2(v.w);
+      float f[8] = {a.x, a.y, b.x, b.y, c.x, c.y, d.x, d.y};
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        s[k] += f[k];
+        q[k] += f[k] * f[k];
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    sred[threadIdx.x * 16 + k] = s[k];
+    sred[threadIdx.x * 16 + 8 + k] = q[k];
+  }
+  __syncthreads();
+  // thread t < nch*2 reduces one (channel, moment) over the pixel lanes
+  for (int o = threadIdx.x; o < nch * 2; o += blockDim.x) {
+    const int mom = o / nch, c = o % nch, jj = c / 8, k = c % 8;
+    float acc = 0.f;
+    for (int l = 0; l < ppb; ++l) acc += sred[(l * nchunk + jj) * 16 + mom * 8 + k];
+    atomicAdd(stats + (mom ? Ct : 0) + c_off + c, (double)acc);
+  }
+}
+
+int launch_channel_stats(const __nv_bfloat16* arena, long npx, int Ct, int c_off, int nch, double* stats, int sm,
+                         cudaStream_t st) {
+  int nchunk = nch / 8, ppb = 256 / nchunk;
+  int grid = (int)std::min<long>((npx + ppb - 1) / ppb, (long)sm * 4);
+  channel_stats_kernel<<<grid, 256, 256 * 16 * sizeof(float), st>>>(arena, npx, Ct, c_off, nch, stats);
+  RL_CUDA(cudaGetLastError());
+  return RL_OK;
+}
+
+// ================================================================================================
+// ConvTranspose2d(80->80, k3, s2, p0) col2im + bias + center_crop (offset 0) -> concat slice
+// ycol[p_in][tap*80+co] holds in[p_in,:] · W[:,co,tap]   (reference layers.py:61-68, 82-86)
+// ================================================================================================
+__global__ void __launch_bounds__(256) tu_col2im_kernel(const __nv_bfloat16* __restrict__ ycol, __nv_bfloat16* out,
+                                                        const float* __restrict__ bias, int B, int h, int w, int H, int W,
+                                                        int Ct, int o_off) {
+  const long total = (long)B * H * W * 10;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int j = (int)(i % 10);
+    const long P = i / 10;
+    const int X = (int)(P % W), Y = (int)((P / W) % H), b = (int)(P / ((long)W * H));
+    float acc[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[k] = bias[j * 8 + k];
+    for (int ky = (Y & 1); ky < 3; ky += 2) {
+      const int ii = (Y - ky) >> 1;
+      if (ii < 0 || ii >= h) continue;
+      for (int kx = (X & 1); kx < 3; kx += 2) {
+        const int jj = (X - kx) >> 1;
+        if (jj < 0 || jj >= w) continue;
+        uint4 v = ldg128(ycol + (((long)b * h + ii) * w + jj) * 720 + (ky * 3 + kx) * 80 + j * 8);
+        float2 a = unpack_bf16x2(v.x), bb = unpack_bf16x2(v.y), c = unpack_bf16x2(v.z), d = unpack_bf16x2(v.w);
+        acc[0] += a.x;
+        acc[1] += a.y;
+        acc[2] += bb.x;
+        acc[3] += bb.y;
+        acc[4] += c.x;
+        acc[5] += c.y;
+        acc[6] += d.x;
+        acc[7] += d.y;
+      }
+    }
+    *reinterpret_cast<uint4*>(out + P * Ct + o_off + j * 8) = pack8(acc);
+  }
+}
+
+int launch_tu_col2im(const __nv_bfloat16* ycol, __nv_bfloat16* out, const float* bias, int B, int h, int w, int H,
+                     int W, int Ct, int o_off, cudaStream_t st) {
+  long total = (long)B * H * W * 10;
+  int grid = (int)std::min<long>((total + 255) / 256, 148L * 16);
+  tu_col2im_kernel<<<grid, 256, 0, st>>>(ycol, out, bias, B, h, w, H, W, Ct, o_off);
+  RL_CUDA(cudaGetLastError());
+  return RL_OK;
+}
+
+// ================================================================================================
+// label histogram (getClassWeight, reference TrainingBase.py:12-23: integer counts, reciprocal later)
+// ================================================================================================
+__global__ void __launch_bounds__(256) label_hist_kernel(const void* y, int is64, long n, int num_cls, Scalars* sc) {
+  __shared__ int h[9];
+  if (threadIdx.x < 9) h[threadIdx.x] = 0;
+  __syncthreads();
+  int loc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    long v = is64 ? reinterpret_cast<const long long*>(y)[i] : (long)reinterpret_cast<const uint8_t*>(y)[i];
+    int k = (v >= 0 && v < num_cls) ? (int)v : 8;
+#pragma unroll
+    for (int c = 0; c < 9; ++c) loc[c] += (k == c);
+  }
+#pragma unroll
+  for (int c = 0; c < 9; ++c) {
+    int s = loc[c];
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0 && s) atomicAdd(&h[c], s);
+  }
+  __syncthreads();
+  if (threadIdx.x < 8 && h[threadIdx.x]) atomicAdd(&sc->hist[threadIdx.x], h[threadIdx.x]);
+  if (threadIdx.x == 8 && h[8]) atomicAdd(&sc->bad_label, h[8]);
+}
+
+int launch_label_hist(const void* y, int y_is_i64, long n, int num_cls, Scalars* sc, cudaStream_t st) {
+  int grid = (int)std::min<long>((n + 255) / 256, 148L * 8);
+  label_hist_kernel<<<grid, 256, 0, st>>>(y, y_is_i64, n, num_cls, sc);
+  RL_CUDA(cudaGetLastError());
+  return RL_OK;
+}
+
+// ================================================================================================
+// classifier head, forward and backward
+//   F.normalize(dim=1, eps=1e-12) (tiramisu.py:105) -> Conv1x1 288->C (+b) -> / T -> softmax (tiramisu.py:120-125)
+//   -> cross_entropy applied to the *probabilities* (SimpleTrain.py:16, TrainingBase.py:85) -> argmax (first max)
+//   -> confusion counts.  One warp handles 8 pixels: a quad of lanes per pixel, 9 chunks of 8 channels per lane.
+// ================================================================================================
+template <int C>
+__global__ void __launch_bounds__(256) head_kernel(HeadArgs a) {
+  __shared__ float sw[C * 288];  // physical channel order
+  __shared__ float sb[C], scw[C];
+  __shared__ int scm[C * C];
+  __shared__ float sred[8][2 + C];
+  __shared__ float s_den;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int i = tid; i < C * 288; i += 256) {
+    const int k = i / 288, c = i % 288;
+    sw[i] = a.w[k * 288 + ref_channel(c, 128)];
+  }
+  if (tid < C) {
+    sb[tid] = a.b[tid];
+    const int hcount = a.sc->hist[tid];
+    scw[tid] = a.weighted ? 1.0f / (float)hcount : 1.0f;  // 1/0 = inf for absent classes, as torch.reciprocal
+  }
+  for (int i = tid; i < C * C; i += 256) scm[i] = 0;
+  if (tid == 0) {
+    float den = 0.f;
+    if (a.weighted) {
+      for (int k = 0; k < C; ++k)
+        if (a.sc->hist[k] > 0) den += (float)a.sc->hist[k] * (1.0f / (float)a.sc->hist[k]);
+    } else {
+      den = (float)a.npx;
+    }
+    s_den = den;
+  }
+  __syncthreads();
+  const int q = lane & 3, pi = lane >> 2;
+  float loss_num = 0.f, loss_den = 0.f, db[C];
+#pragma unroll
+  for (int k = 0; k < C; ++k) db[k] = 0.f;
+  const float inv_den = 1.0f / s_den;
+
+  for (long base = ((long)blockIdx.x * 8 + warp) * 8; base < a.npx; base += (long)gridDim.x * 64) {
+    const long P = base + pi;
+    const bool valid = P < a.npx;
+    uint4 f[9];
+    float nsq = 0.f, dot[C];
+#pragma unroll
+    for (int k = 0; k < C; ++k) dot[k] = 0.f;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) {
+      const int j = q + 4 * i;
+      f[i] = valid ? ldg128(a.feat + P * a.Ct + j * 8) : make_uint4(0, 0, 0, 0);
+      const uint32_t u[4] = {f[i].x, f[i].y, f[i].z, f[i].w};
+#pragma unroll
+      for (int h = 0; h < 4; ++h) {
+        float2 v = unpack_bf16x2(u[h]);
+        nsq = fmaf(v.x, v.x, fmaf(v.y, v.y, nsq));
+#pragma unroll
+        for (int k = 0; k < C; ++k) dot[k] = fmaf(v.x, sw[k * 288 + j * 8 + 2 * h], fmaf(v.y, sw[k * 288 + j * 8 + 2 * h + 1], dot[k]));
+      }
+    }
+#pragma unroll
+    for (int o = 1; o <= 2; o <<= 1) {
+      nsq += __shfl_xor_sync(0xffffffffu, nsq, o);
+#pragma unroll
+      for (int k = 0; k < C; ++k) dot[k] += __shfl_xor_sync(0xffffffffu, dot[k], o);
+    }
+    const float nrm = fmaxf(sqrtf(nsq), 1e-12f);
+    const float inv_n = 1.0f / nrm;
+    float z[C], p[C];
+    float zmax = -INFINITY;
+#pragma unroll
+    for (int k = 0; k < C; ++k) {
+      z[k] = (dot[k] * inv_n + sb[k]) / 0.05f;
+      zmax = fmaxf(zmax, z[k]);
+    }
+    float esum = 0.f;
+#pragma unroll
+    for (int k = 0; k < C; ++k) {
+      p[k] = expf(z[k] - zmax);
+      esum += p[k];
+    }
+    int pred = 0;
+    float pmax = -1.f;
+#pragma unroll
+    for (int k = 0; k < C; ++k) {
+      p[k] = p[k] / esum;
+      if (p[k] > pmax) {
+        pmax = p[k];
+        pred = k;
+      }
+    }
+    const int b = valid ? (int)(P / a.HW) : 0, hw = valid ? (int)(P % a.HW) : 0;
+    if (valid && q == 0) {
+      if (a.probs)
+#pragma unroll
+        for (int k = 0; k < C; ++k) a.probs[((long)b * C + k) * a.HW + hw] = p[k];
+      if (a.mask_out) a.mask_out[P] = (uint8_t)pred;
+    }
+    int label = -1;
+    float sm2[C];  // softmax of the probabilities (second softmax inside cross_entropy)
+    float wl = 0.f;
+    if (a.y != nullptr && valid) {
+      long lv = a.y_is_i64 ? reinterpret_cast<const long long*>(a.y)[P] : (long)reinterpret_cast<const uint8_t*>(a.y)[P];
+      label = (lv >= 0 && lv < C) ? (int)lv : -1;
+    }
+    {
+      float e2 = 0.f;
+#pragma unroll
+      for (int k = 0; k < C; ++k) {
+        sm2[k] = expf(p[k] - pmax);
+        e2 += sm2[k];
+      }
+      const float lse = logf(e2) + pmax;
+#pragma unroll
+      for (int k = 0; k < C; ++k) sm2[k] = sm2[k] / e2;
+      if (label >= 0) {
+        float pl = 0.f;
+#pragma unroll
+        for (int k = 0; k < C; ++k) pl = (k == label) ? p[k] : pl;
+#pragma unroll
+        for (int k = 0; k < C; ++k) wl = (k == label) ? scw[k] : wl;
+        if (q == 0) {
+          loss_num += wl * (lse - pl);
+          loss_den += wl;
+          atomicAdd(&scm[label * C + pred], 1);
+        }
+      }
+    }
+    if (a.dact != nullptr) {
+      // d(loss)/d(probs)
+      float dp[C];
+#pragma unroll
+      for (int k = 0; k < C; ++k) {
+        if (a.dprobs)
+          dp[k] = valid ? a.dprobs[((long)b * C + k) * a.HW + hw] : 0.f;
+        else
+          dp[k] = (label >= 0) ? a.grad_scale * wl * inv_den * (sm2[k] - (k == label ? 1.f : 0.f)) : 0.f;
+      }
+      float dsum = 0.f;
+#pragma unroll
+      for (int k = 0; k < C; ++k) dsum = fmaf(dp[k], p[k], dsum);
+      float dl[C], gdot = 0.f;
+#pragma unroll
+      for (int k = 0; k < C; ++k) {
+        const float dlogit = p[k] * (dp[k] - dsum) / 0.05f;
+        if (q == 0 && valid) db[k] += dlogit;
+        dl[k] = dlogit * inv_n;
+        gdot = fmaf(dl[k], dot[k], gdot);
+      }
+      const float coef = gdot * inv_n * inv_n;
+      if (valid) {
+        if (q == 0) {
+          uint32_t pk[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+          for (int k = 0; k < C; k += 2) pk[k >> 1] = pack_bf16x2(dl[k], k + 1 < C ? dl[k + 1] : 0.f);
+          uint4* d = reinterpret_cast<uint4*>(a.dl + P * 16);
+          d[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          d[1] = make_uint4(0, 0, 0, 0);
+        }
+#pragma unroll
+        for (int i = 0; i < 9; ++i) {
+          const int j = q + 4 * i;
+          const uint32_t u[4] = {f[i].x, f[i].y, f[i].z, f[i].w};
+          float o[8];
+#pragma unroll
+          for (int h = 0; h < 4; ++h) {
+            float2 v = unpack_bf16x2(u[h]);
+            float g0 = -coef * v.x, g1 = -coef * v.y;
+#pragma unroll
+            for (int k = 0; k < C; ++k) {
+              g0 = fmaf(dl[k], sw[k * 288 + j * 8 + 2 * h], g0);
+              g1 = fmaf(dl[k], sw[k * 288 + j * 8 + 2 * h + 1], g1);
+            }
+            o[2 * h] = g0 * a.feat_grad_sign;
+            o[2 * h + 1] = g1 * a.feat_grad_sign;
+          }
+          *reinterpret_cast<uint4*>(a.dact + P * a.Ct + j * 8) = pack8(o);
+        }
+      }
+    }
+  }
+  // ---- block reductions
+  loss_num = warp_sum(loss_num);
+  loss_den = warp_sum(loss_den);
+#pragma unroll
+  for (int k = 0; k < C; ++k) db[k] = warp_sum(db[k]);
+  if (lane == 0) {
+    sred[warp][0] = loss_num;
+    sred[warp][1] = loss_den;
+#pragma unroll
+    for (int k = 0; k < C; ++k) sred[warp][2 + k] = db[k];
+  }
+  __syncthreads();
+  if (tid < 2 + C) {
+    float v = 0.f;
+    for (int w2 = 0; w2 < 8; ++w2) v += sred[w2][tid];
+    if (tid == 0 && a.y) atomicAdd(&a.sc->loss_num, (double)v);
+    if (tid == 1 && a.y) atomicAdd(&a.sc->loss_den, (double)v);
+    if (tid >= 2 && a.g_b) atomicAdd(a.g_b + tid - 2, v);
+  }
+  if (a.y)
+    for (int i = tid; i < C * C; i += 256)
+      if (scm[i]) atomicAdd(&a.sc->cm[i], scm[i]);
+}
+
+int launch_head(const HeadArgs& a, int sm, cudaStream_t st) {
+  int grid = (int)std::min<long>((a.npx + 63) / 64, (long)sm * 4);
+  switch (a.num_cls) {
+    case 2: head_kernel<2><<<grid, 256, 0, st>>>(a); break;
+    case 3: head_kernel<3><<<grid, 256, 0, st>>>(a); break;
+    case 4: head_kernel<4><<<grid, 256, 0, st>>>(a); break;
+    default: return rl_fail(RL_ERR_SHAPE, "head: num_cls %d unsupported", a.num_cls);
+  }
+  RL_CUDA(cudaGetLastError());
+  return RL_OK;
+}
+
+// ================================================================================================
+// output-gradient preparation:   dz = dropout_scale * (dX - A_c - xhat * B_c)
+// (A_c, B_c): BatchNorm-backward mean terms summed over all consumer layers of channel c.
+// ================================================================================================
+__device__ __forceinline__ void unpack8(uint4 v, float* f) {
+  float2 a = unpack_bf16x2(v.x), b = unpack_bf16x2(v.y), c = unpack_bf16x2(v.z), d = unpack_bf16x2(v.w);
+  f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
+}
+
+__global__ void __launch_bounds__(256) dz_prepare_kernel(DzArgs a) {
+  extern __shared__ float sm[];  // mean[nch], rstd[nch], A[nch], Bc[nch], then reduction scratch [256][8]
+  float* s_mean = sm;
+  float* s_rstd = sm + a.nch;
+  float* s_A = sm + 2 * a.nch;
+  float* s_B = sm + 3 * a.nch;
+  float* s_red = sm + 4 * a.nch;
+  for (int c = threadIdx.x; c < a.nch; c += blockDim.x) {
+    const int gc = a.c_off + c;
+    double m = a.stats[gc] * a.inv_n_out, v = a.stats[a.Ct + gc] * a.inv_n_out - m * m;
+    if (v < 0) v = 0;
+    s_mean[c] = (float)m;
+    s_rstd[c] = (float)(1.0 / sqrt(v + (double)kBnEps));
+    s_A[c] = (float)(a.acc[gc] * a.inv_n_out);
+    s_B[c] = (float)(a.acc[a.Ct + gc] * a.inv_n_out);
+  }
+  __syncthreads();
+  const int nchunk = a.nch / 8;
+  float bsum[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) bsum[k] = 0.f;
+  int jfix = -1;
+
+  auto corrected = [&](long Pout, int j, int img, float* o) {
+    float dx[8], xv[8];
+    unpack8(ldg128(a.dact + Pout * a.Ct + a.c_off + j * 8), dx);
+    unpack8(ldg128(a.act + Pout * a.Ct + a.c_off + j * 8), xv);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int c = j * 8 + k;
+      const float xh = (xv[k] - s_mean[c]) * s_rstd[c];
+      const float m = a.mask ? a.mask[(long)img * a.nch + c] : 1.f;
+      o[k] = m * (dx[k] - s_A[c] - xh * s_B[c]);
+    }
+  };
+
+  if (a.kind == 0) {
+    const int ppb = blockDim.x / nchunk;
+    const int j = threadIdx.x % nchunk, pl = threadIdx.x / nchunk;
+    jfix = j;
+    if (pl < ppb)
+      for (long P = (long)blockIdx.x * ppb + pl; P < a.npx_out; P += (long)gridDim.x * ppb) {
+        float o[8];
+        corrected(P, j, (int)(P / a.HW_out), o);
+        *reinterpret_cast<uint4*>(a.dz + P * a.nch + j * 8) = pack8(o);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) bsum[k] += o[k];
+      }
+  } else if (a.kind == 1) {
+    // TD: loop over input-resolution pixels; gradient goes to the arg-max position of each 2x2 window
+    const int ppb = blockDim.x / nchunk;
+    const int j = threadIdx.x % nchunk, pl = threadIdx.x / nchunk;
+    jfix = j;
+    const long npx_in = (long)a.B * a.H * a.W;
+    if (pl < ppb)
+      for (long P = (long)blockIdx.x * ppb + pl; P < npx_in; P += (long)gridDim.x * ppb) {
+        const int x = (int)(P % a.W), y = (int)((P / a.W) % a.H), b = (int)(P / ((long)a.W * a.H));
+        float o[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) o[k] = 0.f;
+        const int py = y >> 1, px = x >> 1;
+        if (py < a.Hp && px < a.Wp) {
+          const long Pout = ((long)b * a.Hp + py) * a.Wp + px;
+          const int qq = (y & 1) * 2 + (x & 1);
+          float c8[8];
+          corrected(Pout, j, b, c8);
+          const uint2 am = *reinterpret_cast<const uint2*>(a.amax + Pout * a.nch + j * 8);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const uint32_t word = k < 4 ? am.x : am.y;
+            const int sel = (word >> (8 * (k & 3))) & 0xff;
+            o[k] = (sel == qq) ? c8[k] : 0.f;
+            bsum[k] += o[k];
+          }
+        }
+        *reinterpret_cast<uint4*>(a.dz + P * a.nch + j * 8) = pack8(o);
+      }
+  } else {
+    // TU: column matrix row (b,i,j) holds dz at output pixels (2i+ky, 2j+kx) for the 9 taps
+    const int items = 9 * nchunk;  // per input pixel
+    const long npx_in = (long)a.B * a.Hp * a.Wp;
+    for (long it = blockIdx.x * (long)blockDim.x + threadIdx.x; it < npx_in * items; it += (long)gridDim.x * blockDim.x) {
+      const long Pin = it / items;
+      const int r = (int)(it % items), tap = r / nchunk, j = r % nchunk;
+      const int jj = (int)(Pin % a.Wp), ii = (int)((Pin / a.Wp) % a.Hp), b = (int)(Pin / ((long)a.Wp * a.Hp));
+      const int ky = tap / 3, kx = tap % 3, Y = 2 * ii + ky, X = 2 * jj + kx;
+      float o[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) o[k] = 0.f;
+      if (Y < a.H && X < a.W) {
+        corrected(((long)b * a.H + Y) * a.W + X, j, b, o);
+        const bool count = (ky < 2 || ii == a.Hp - 1) && (kx < 2 || jj == a.Wp - 1);
+        if (count && a.g_bias) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) atomicAdd(a.g_bias + j * 8 + k, o[k]);
+        }
+      }
+      *reinterpret_cast<uint4*>(a.dz + Pin * 720 + tap * a.nch + j * 8) = pack8(o);
+    }
+  }
+  if (a.kind != 2 && a.g_bias != nullptr) {
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s_red[threadIdx.x * 8 + k] = bsum[k];
+    __syncthreads();
+    const int ppb = blockDim.x / nchunk;
+    for (int c = threadIdx.x; c < a.nch; c += blockDim.x) {
+      float acc = 0.f;
+      for (int l = 0; l < ppb; ++l) acc += s_red[(l * nchunk + c / 8) * 8 + (c % 8)];
+      atomicAdd(a.g_bias + c, acc);
+    }
+  }
+  (void)jfix;
+}
+
+int launch_dz_prepare(const DzArgs& a, int sm, cudaStream_t st) {
+  size_t smem = (size_t)(4 * a.nch + 256 * 8) * sizeof(float);
+  long work = (a.kind == 0) ? a.npx_out : (a.kind == 1 ? (long)a.B * a.H * a.W : (long)a.B * a.Hp * a.Wp * 9);
+  int nchunk = a.nch / 8;
+  int ppb = 256 / nchunk;
+  long blocks = (a.kind == 2) ? (work * nchunk + 255) / 256 : (work + ppb - 1) / ppb;
+  int grid = (int)std::min<long>(blocks, (long)sm * 8);
+  if (grid < 1) grid = 1;
+  dz_prepare_kernel<<<grid, 256, smem, st>>>(a);
+  RL_CUDA(cudaGetLastError());
+  return RL_OK;
+}
+
+// ================================================================================================
+// BatchNorm running statistics (momentum 0.1, unbiased variance), all 60 layers in one launch
+// ================================================================================================
+__global__ void bn_running_kernel(const BnTabEntry* tab, const uint8_t* ws, float* bnbuf, float momentum) {
+  const BnTabEntry e = tab[blockIdx.x];
+  const double* stats = reinterpret_cast<const double*>(ws + e.stats_byte_off);
+  for (int c = threadIdx.x; c < e.C; c += blockDim.x) {
+    double m = stats[c] * (double)e.inv_n, v = stats[e.Ct + c] * (double)e.inv_n - m * m;
+    if (v < 0) v = 0;
+    const int rc = ref_channel(c, e.cs_perm);
+    bnbuf[e.rm + rc] = (1.f - momentum) * bnbuf[e.rm + rc] + momentum * (float)m;
+    bnbuf[e.rv + rc] = (1.f - momentum) * bnbuf[e.rv + rc] + momentum * (float)(v * (double)e.unbias);
+  }
+}
+
+int launch_bn_running(const Plan* p, float* bnbuf, float momentum, cudaStream_t st) {
+  const BnTabEntry* tab = reinterpret_cast<const BnTabEntry*>((const uint8_t*)p->ws + p->bntab_off);
+  bn_running_kernel<<<p->n_bn, 256, 0, st>>>(tab, (const uint8_t*)p->ws, bnbuf, momentum);
+  RL_CUDA(cudaGetLastError());
+  return RL_OK;
+}
+
+// ================================================================================================
+// optimizers over the flat parameter arena (reference SimpleTrain.py:28 AdamW; MMETrainingModule.py:16-19 SGD)
+// ================================================================================================
+__global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                                    float* __restrict__ v, long n, float lr, float b1, float b2, float eps,
+                                                    float wd, float bc1, float bc2, float gs) {
+  const float step_size = lr / bc1, inv_sqrt_bc2 = rsqrtf(bc2);
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    const float gi = g[i] * gs;
+    float pi = p[i] * (1.f - lr * wd);
+    const float mi = b1 * m[i] + (1.f - b1) * gi;
+    const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+    const float denom = sqrtf(vi) * inv_sqrt_bc2 + eps;
+    pi -= step_size * (mi / denom);
+    p[i] = pi;
+    m[i] = mi;
+    v[i] = vi;
+  }
+}
+
+int launch_adamw(float* p, const float* g, float* m, float* v, long n, float lr, float b1, float b2, float eps, float wd,
+                 float bc1, float bc2, float grad_scale, cudaStream_t st) {
+  int grid = (int)std::min<long>((n + 255) / 256, 148L * 8);
+  adamw_kernel<<<grid, 256, 0, st>>>(p, g, m, v, n, lr, b1, b2, eps, wd, bc1, bc2, grad_scale);
+  RL_CUDA(cudaGetLastError());
+  return RL_OK;
+}
+
+__global__ void __launch_bounds__(256) sgd_nesterov_kernel(float* __restrict__ p, const float* __restrict__ g,
+                                                           float* __restrict__ buf, long n, float lr, float mom, float wd,
+                                                           int first, float gs) {
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    float d = g[i] * gs + wd * p[i];
+    float b = first ? d : mom * buf[i] + d;
+    buf[i] = b;
+    p[i] -= lr * (d + mom * b);
+  }
+}
+
+int launch_sgd_nesterov(float* p, const float* g, float* buf, long n, float lr, float momentum, float wd, int first,
+                        float grad_scale, cudaStream_t st) {
+  int grid = (int)std::min<long>((n + 255) / 256, 148L * 8);
+  sgd_nesterov_kernel<<<grid, 256, 0, st>>>(p, g, buf, n, lr, momentum, wd, first, grad_scale);
+  RL_CUDA(cudaGetLastError());
+  return RL_OK;
+}
+
+// ================================================================================================
+// Dropout2d(0.2) keep-scales for every (layer, sample, channel): counter-based hash RNG
+// ================================================================================================
+__device__ __forceinline__ unsigned long long splitmix64(unsigned long long x) {
+  x += 0x9E3779B97F4A7C15ull;
+  x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+  x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+  return x ^ (x >> 31);
+}
+__global__ void fill_masks_kernel(float* masks, long n, float p_drop, unsigned long long seed, unsigned long long step) {
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    unsigned long long h = splitmix64(splitmix64(seed ^ (step * 0xD1B54A32D192ED03ull)) + (unsigned long long)i);
+    float u = (float)(h >> 40) * (1.0f / 16777216.0f);
+    masks[i] = (u >= p_drop) ? 1.0f / (1.0f - p_drop) : 0.f;
+  }
+}
+int launch_fill_masks(float* masks, long n, float p_drop, unsigned long long seed, unsigned long long step, cudaStream_t st) {
+  int grid = (int)std::min<long>((n + 255) / 256, 148L * 4);
+  fill_masks_kernel<<<grid, 256, 0, st>>>(masks, n, p_drop, seed, step);
+  RL_CUDA(cudaGetLastError());
+  return RL_OK;
+}
+
+}  // namespace rl

@@ -1,0 +1,196 @@
+// rl_plan.cu — builds the layer schedule / arena geometry of FC-DenseNet67 (reference
+// rightLaneNetwork/models/FCDenseNet/tiramisu.py:21-109, factory :178-183) for a fixed (B, H, W, C).
+#include "rl_plan.h"
+
+#include <stdio.h>
+#include <string.h>
+
+namespace rl {
+
+static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+int td_parts(int C, int* n0, int* np) {
+  if (C <= 256) {
+    n0[0] = 0;
+    np[0] = C;
+    return 1;
+  }
+  int h = ((C / 2 + 15) / 16) * 16;
+  n0[0] = 0;
+  np[0] = h;
+  n0[1] = h;
+  np[1] = C - h;
+  return 2;
+}
+
+int build_plan(Plan* p, int B, int H, int W, int num_cls, int training) {
+  p->B = B;
+  p->H = H;
+  p->W = W;
+  p->num_cls = num_cls;
+  p->training = training != 0;
+  p->ws = nullptr;
+  p->err[0] = 0;
+  if (B < 1 || H < 32 || W < 32 || num_cls < 2 || num_cls > 4) {
+    snprintf(p->err, sizeof(p->err), "unsupported shape B=%d H=%d W=%d num_cls=%d (need H,W>=32, 2<=C<=4)", B, H, W,
+             num_cls);
+    return -1;
+  }
+  // ---- levels
+  int cskip[kLevels] = {128, 208, 288, 368, 448, 448};
+  int h = H, w = W;
+  for (int l = 0; l < kLevels; ++l) {
+    p->lv[l].H = h;
+    p->lv[l].W = w;
+    p->lv[l].Cskip = cskip[l];
+    p->lv[l].Ct = (l < 5) ? cskip[l] + 2 * kUpCh : cskip[l] + kUpCh;
+    p->lv[l].px = (long)B * h * w;
+    h /= 2;
+    w /= 2;
+  }
+  // ---- layers in forward order
+  p->layers.clear();
+  auto mk = [&](int type, int li, int lo, int cin, int cout, int in_off, int out_off, int cs_perm) {
+    Layer L;
+    memset(&L, 0, sizeof(L));
+    L.type = type;
+    L.lvl_in = li;
+    L.lvl_out = lo;
+    L.cin = cin;
+    L.cout = cout;
+    L.in_off = in_off;
+    L.out_off = out_off;
+    L.cs_perm = cs_perm;
+    L.p_gamma = L.p_beta = L.p_w = L.p_b = -1;
+    L.b_rm = L.b_rv = -1;
+    L.bn_index = -1;
+    L.rmw_from = 0;
+    p->layers.push_back(L);
+    return (int)p->layers.size() - 1;
+  };
+  int id_first = mk(L_FIRST, 0, 0, 3, kFirst, 0, 0, 0);
+  int id_down[5][5], id_td[5], id_bott[5], id_tu[5], id_up[5][5];
+  int cin_l = kFirst;
+  for (int l = 0; l < 5; ++l) {
+    for (int j = 0; j < kBlockLayers; ++j) id_down[l][j] = mk(L_DENSE, l, l, cin_l + kGrowth * j, kGrowth, 0, cin_l + kGrowth * j, 0);
+    id_td[l] = mk(L_TD, l, l + 1, cskip[l], cskip[l], 0, 0, 0);
+    cin_l = cskip[l];
+  }
+  for (int j = 0; j < kBlockLayers; ++j) {
+    id_bott[j] = mk(L_DENSE, 5, 5, 448 + kGrowth * j, kGrowth, 0, 448 + kGrowth * j, 0);
+    if (j == kBlockLayers - 1) p->layers.back().rmw_from = 448;
+  }
+  for (int i = 0; i < 5; ++i) {
+    int l = 4 - i;
+    int src_off = (l + 1 == 5) ? 448 : cskip[l + 1] + kUpCh;
+    id_tu[i] = mk(L_TU, l + 1, l, kUpCh, kUpCh, src_off, cskip[l], 0);
+    for (int j = 0; j < kBlockLayers; ++j) {
+      int cin = cskip[l] + kUpCh + kGrowth * j;
+      id_up[i][j] = mk(L_DENSE, l, l, cin, kGrowth, 0, cin, cskip[l]);
+      if (j == kBlockLayers - 1 && l != 0) p->layers.back().rmw_from = cskip[l] + kUpCh;
+    }
+  }
+  // ---- parameter offsets in the reference's registration order (tiramisu.py:33-87, TrainingBase.py:32-33)
+  long off = 0, boff = 0;
+  int bn = 0;
+  auto take = [&](long n) {
+    long o = off;
+    off += n;
+    return o;
+  };
+  auto reg_bn_conv = [&](int id, int k) {
+    Layer& L = p->layers[id];
+    L.p_gamma = take(L.cin);
+    L.p_beta = take(L.cin);
+    L.p_w = take((long)L.cout * L.cin * k * k);
+    L.p_b = take(L.cout);
+    L.b_rm = boff;
+    boff += L.cin;
+    L.b_rv = boff;
+    boff += L.cin;
+    L.bn_index = bn++;
+  };
+  {
+    Layer& L = p->layers[id_first];
+    L.p_w = take(kFirst * 3 * 9);
+    L.p_b = take(kFirst);
+  }
+  for (int l = 0; l < 5; ++l)
+    for (int j = 0; j < 5; ++j) reg_bn_conv(id_down[l][j], 3);
+  for (int l = 0; l < 5; ++l) reg_bn_conv(id_td[l], 1);
+  for (int j = 0; j < 5; ++j) reg_bn_conv(id_bott[j], 3);
+  for (int i = 0; i < 5; ++i) {
+    Layer& L = p->layers[id_tu[i]];
+    L.p_w = take(kUpCh * kUpCh * 9);
+    L.p_b = take(kUpCh);
+  }
+  for (int i = 0; i < 5; ++i)
+    for (int j = 0; j < 5; ++j) reg_bn_conv(id_up[i][j], 3);
+  p->p_cls_w = take((long)num_cls * 288);
+  p->p_cls_b = take(num_cls);
+  p->n_params = off;
+  p->n_bnbuf = boff;
+
+  // ---- workspace carve-up
+  size_t ws = 0;
+  auto carve = [&](size_t bytes) {
+    size_t o = ws;
+    ws = align_up(ws + bytes, 1024);
+    return o;
+  };
+  p->scal_off = carve(1024);
+  p->bntab_off = carve(64 * 64);
+  p->packtab_off = carve(160 * sizeof(PackEntry));
+  // packed weights
+  p->wpk_off = ws;
+  for (Layer& L : p->layers) {
+    if (L.type == L_DENSE) {
+      int nkc = (L.cin + 63) / 64, nmb = (L.cin + 127) / 128;
+      L.wpk_fwd = carve((size_t)nkc * 18432);
+      L.wpk_bwd = carve((size_t)nmb * 36864);
+    } else if (L.type == L_TD) {
+      int nkc = (L.cin + 63) / 64, nmb = (L.cin + 127) / 128;
+      L.wpk_fwd = carve((size_t)nkc * 8 * L.cin * 16);  // all parts: sum(np) = C rows per chunk-slot
+      L.wpk_bwd = carve((size_t)nmb * nkc * 16384);
+    } else if (L.type == L_TU) {
+      L.wpk_fwd = carve((size_t)3 * 2 * 30720);
+      L.wpk_bwd = carve((size_t)12 * 10240);
+    }
+  }
+  p->wpk_bytes = ws - p->wpk_off;
+  p->mask_off_all = ws;
+  for (Layer& L : p->layers)
+    if (L.type == L_DENSE || L.type == L_TD) L.mask_off = carve((size_t)B * L.cout * sizeof(float));
+  p->mask_bytes = ws - p->mask_off_all;
+  p->stats_off_all = ws;
+  for (int l = 0; l < kLevels; ++l) p->lv[l].stats_off = carve((size_t)2 * p->lv[l].Ct * sizeof(double));
+  p->stats_bytes = ws - p->stats_off_all;
+  p->acc_off_all = ws;
+  for (int l = 0; l < kLevels; ++l) p->lv[l].acc_off = carve((size_t)2 * p->lv[l].Ct * sizeof(double));
+  p->acc_bytes = ws - p->acc_off_all;
+  for (int l = 0; l < kLevels; ++l) p->lv[l].act_off = carve((size_t)p->lv[l].px * p->lv[l].Ct * 2);
+  for (int l = 0; l < kLevels; ++l) p->lv[l].dact_off = training ? carve((size_t)p->lv[l].px * p->lv[l].Ct * 2) : 0;
+  for (Layer& L : p->layers)
+    if (L.type == L_TD) L.amax_off = training ? carve((size_t)p->lv[L.lvl_out].px * L.cout) : 0;
+  // scratch: convT column matrices [px(l+1) x 720] bf16, TD output gradients [px(l) x C] bf16, dz16/dz48
+  size_t tmp = 0;
+  for (Layer& L : p->layers) {
+    size_t need = 0;
+    if (L.type == L_TU) need = (size_t)p->lv[L.lvl_in].px * 720 * 2;
+    if (training) {
+      if (L.type == L_TD) need = (size_t)p->lv[L.lvl_in].px * L.cout * 2;
+      if (L.type == L_DENSE) need = (size_t)p->lv[L.lvl_in].px * 16 * 2;
+      if (L.type == L_FIRST) need = (size_t)p->lv[0].px * kFirst * 2;
+    }
+    if (need > tmp) tmp = need;
+  }
+  p->tmp_bytes = tmp;
+  p->tmp_off = carve(tmp);
+  p->xcol_off = training ? carve((size_t)p->lv[0].px * 32 * 2) : 0;
+  p->dl_bytes = training ? (size_t)p->lv[0].px * 16 * 2 : 0;
+  p->dl_off = carve(p->dl_bytes);
+  p->ws_bytes = ws;
+  return 0;
+}
+
+}  // namespace rl

@@ -1,0 +1,99 @@
+"""Forward parity of the CUDA path (through the C ABI) against the oracle and the reference-generated fixtures."""
+import glob
+import os
+
+import pytest
+import torch
+
+from oracle import fcdensenet as net
+from oracle import steps
+from sim2real_lane_segment_b200.engine import Engine
+from tests.util import flatten_state_dict, ref_to_phys, rel_err
+
+GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "ref_*.pt")))
+SKIPS = (128, 208, 288, 368, 448)
+
+
+def _arena_taps(eng):
+    return {l: eng.level_view(l).float().permute(0, 3, 1, 2).cpu() for l in range(6)}
+
+
+def _check_levels(eng, taps, tol):
+    """compare every concat arena with the oracle's intermediate activations; returns worst relative error"""
+    got = _arena_taps(eng)
+    worst = 0.0
+    for l in range(5):
+        want = ref_to_phys(taps[f"featureExtractor.denseBlocksUp.{4 - l}"], SKIPS[l])
+        for lo, hi, nm in ((0, SKIPS[l], "skip"), (SKIPS[l], SKIPS[l] + 80, "up"), (SKIPS[l] + 80, SKIPS[l] + 160, "new")):
+            e = rel_err(got[l][:, lo:hi], want[:, lo:hi])
+            worst = max(worst, e)
+            assert e < tol, f"level {l} {nm} channels [{lo},{hi}) rel err {e:.4f}"
+    want = taps["featureExtractor.bottleneck.bottleneck"]
+    e = rel_err(got[5], want)
+    assert e < tol, f"bottleneck rel err {e:.4f}"
+    return max(worst, e)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("path", GOLDEN, ids=os.path.basename)
+def test_eval_forward_matches_reference_fixture(path):
+    fx = torch.load(path)
+    B, H, W, C = fx["B"], fx["H"], fx["W"], fx["num_cls"]
+    sd = net.init_state_dict(num_cls=C, seed=fx["seed"])
+    # non-trivial running statistics so eval-mode BatchNorm is exercised
+    params, bn = flatten_state_dict(sd, C, "cuda")
+    eng = Engine(B, H, W, C, training=False).bind()
+    eng.pack_weights(params)
+    x = fx["x"].cuda()
+    eng.forward(params, bn, x, train=False)
+    probs = torch.empty(B, C, H, W, device="cuda")
+    mask = torch.empty(B, H, W, dtype=torch.uint8, device="cuda")
+    y = fx["y"].cuda()
+    eng.head(params, y=y, weighted=False, probs=probs, mask=mask)
+    torch.cuda.synchronize()
+    taps = {}
+    feats, _ = net.feature_extractor(sd, fx["x"], taps=taps)
+    worst = _check_levels(eng, taps, 0.03)
+    ref = fx["eval_probs"]
+    # integer work is bit-exact given our own probabilities
+    assert torch.equal(mask.cpu(), probs.cpu().argmax(1).to(torch.uint8))
+    hist, cm, loss, bad = eng.scalars()
+    cm_ref = steps.confusion_matrix(mask.cpu().long(), fx["y"].long(), C)
+    assert torch.equal(cm[:C * C].cpu().view(C, C).long(), cm_ref)
+    assert int(bad.item()) == 0
+    # against the fp32 reference: probabilities close, masks agree except near-ties
+    assert float((probs.cpu() - ref).abs().max()) < 0.12, float((probs.cpu() - ref).abs().max())
+    assert float((probs.cpu() - ref).abs().mean()) < 0.01
+    agree = float((mask.cpu() == fx["eval_mask"]).float().mean())
+    assert agree > 0.97, agree
+    l = float(loss[0] / loss[1])
+    assert abs(l - float(fx["eval_loss"])) < 0.01, (l, float(fx["eval_loss"]))
+    print(f"worst level err {worst:.4f} mask agreement {agree:.4f} loss {l:.5f} vs {float(fx['eval_loss']):.5f}")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("path", [p for p in GOLDEN if "drop" not in p][:2], ids=os.path.basename)
+def test_train_forward_batch_stats(path):
+    fx = torch.load(path)
+    B, H, W, C = fx["B"], fx["H"], fx["W"], fx["num_cls"]
+    sd = net.init_state_dict(num_cls=C, seed=fx["seed"])
+    params, bn = flatten_state_dict(sd, C, "cuda")
+    eng = Engine(B, H, W, C, training=True).bind()
+    eng.pack_weights(params)
+    eng.forward(params, bn, fx["x"].cuda(), train=True)
+    probs = torch.empty(B, C, H, W, device="cuda")
+    eng.head(params, y=fx["y"].cuda(), weighted=True, probs=probs)
+    torch.cuda.synchronize()
+    taps = {}
+    net.feature_extractor(sd, fx["x"], train=True, taps=taps)
+    _check_levels(eng, taps, 0.05)  # bf16 storage noise through ~60 BatchNorm layers with tiny batch statistics
+    assert float((probs.cpu() - fx["train_probs"]).abs().mean()) < 0.01
+    hist, cm, loss, bad = eng.scalars()
+    l = float(loss[0] / loss[1])
+    assert abs(l - float(fx["train_loss"])) < 0.01, (l, float(fx["train_loss"]))
+    # batch statistics of level 0 against torch
+    st = eng.level_stats(0).cpu()
+    want = ref_to_phys(taps["featureExtractor.denseBlocksUp.4"], 128)
+    n = B * H * W
+    mean = st[0] / n
+    torch.testing.assert_close(mean.float(), want.mean(dim=(0, 2, 3)), rtol=0.05, atol=0.02)
