@@ -75,11 +75,13 @@ int rl_forward(rl_plan* p, const float* params, const float* bn_buffers, const f
  * probabilities + argmax + confusion counts (SimpleTrain.py:15-20, TrainingBase.py:84-93, test.py:93-100).
  *   y: labels uint8 or int64 [B,H,W] or NULL; weighted: class weights 1/count as getClassWeight (TrainingBase.py:12-23)
  *   probs (fp32 [B,C,H,W]) / mask (uint8 [B,H,W]) may be NULL.  Loss sums and counts land in the scalars block.
- *   backward: 0 = forward only; 1 = also start the backward pass with the fused CE gradient times grad_scale;
+ *   backward: 0 = forward only; 1 = also start the backward pass with the fused CE gradient times grad_scale
+ *   (times *grad_scale_dev if that device pointer is non-NULL: the loss's grad_output, read without a host sync);
  *   2 = backward from an external d(loss)/d(probs) (dprobs fp32 [B,C,H,W]).  feat_grad_sign = -1 realises
  *   GradReverse (tiramisu.py:7-18).  Classifier gradients are accumulated into grads. */
 int rl_head(rl_plan* p, const float* params, const void* y, int y_is_i64, int weighted, float* probs, uint8_t* mask,
-            int backward, const float* dprobs, float grad_scale, float feat_grad_sign, float* grads, void* stream);
+            int backward, const float* dprobs, float grad_scale, const float* grad_scale_dev, float feat_grad_sign,
+            float* grads, void* stream);
 
 /* loss.backward() for everything below the head (SimpleTrain.py:25 + autograd): accumulates into grads (fp32 arena,
  * same layout as params).  Requires rl_forward(train=1) and rl_head(backward != 0) on the same plan. */
@@ -94,6 +96,14 @@ int rl_adamw_step(float* params, const float* grads, float* exp_avg, float* exp_
 /* torch.optim.SGD(momentum, nesterov=True, weight_decay) step (MMETrainingModule.py:16-19) */
 int rl_sgd_nesterov_step(float* params, const float* grads, float* momentum_buf, long n, float lr, float momentum,
                          float weight_decay, int first_step, float grad_scale, void* stream);
+
+/* launch accounting: number of kernels this library has launched (kernel_class < 0: all classes), and optional
+ * per-class CUDA-event timing for bench.py's roofline (classes: 0 dense_fwd, 1 gemm_px, 2 dgrad_dense, 3 dgrad_td,
+ * 4 wgrad, 5 head, 6 dz_prepare, 7 channel_stats, 8 first_fwd, 9 tu_col2im, 10 pack, 11 optimizer, 12 misc).
+ * rl_profile_end synchronises the device and fills ms[13], launches[13] (host pointers). */
+long rl_launch_count(int kernel_class);
+int rl_profile_begin(void);
+int rl_profile_end(double* ms, long* launches);
 
 /* test hook: one 128 x N x K tcgen05 GEMM through the shared-memory operand conventions of csrc/rl_umma.cuh */
 int rl_selftest_umma(const void* A, int a_rows, int a_cols, int a_mn_major, int a_row_shift, const void* B, int b_rows,

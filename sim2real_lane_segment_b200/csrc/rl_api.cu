@@ -253,7 +253,8 @@ int rl_forward(rl_plan* h, const float* params, const float* bnbuf, const float*
 }
 
 int rl_head(rl_plan* h, const float* params, const void* y, int y_is_i64, int weighted, float* probs, uint8_t* mask,
-            int backward, const float* dprobs, float grad_scale, float feat_grad_sign, float* grads, void* stream) {
+            int backward, const float* dprobs, float grad_scale, const float* grad_scale_dev, float feat_grad_sign,
+            float* grads, void* stream) {
   if (!h || !h->p.ws) return rl_fail(RL_ERR_STATE, "rl_head: plan not bound");
   Plan* p = &h->p;
   cudaStream_t st = (cudaStream_t)stream;
@@ -280,6 +281,7 @@ int rl_head(rl_plan* h, const float* params, const void* y, int y_is_i64, int we
   a.weighted = weighted;
   a.dprobs = backward == 2 ? dprobs : nullptr;
   a.grad_scale = grad_scale;
+  a.grad_scale_dev = grad_scale_dev;
   a.feat_grad_sign = feat_grad_sign;
   a.dact = backward ? dact_of(p, 0) : nullptr;
   a.dl = backward ? (__nv_bfloat16*)(wsb(p) + p->dl_off) : nullptr;

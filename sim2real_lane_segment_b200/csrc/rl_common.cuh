@@ -12,6 +12,19 @@ namespace rl {
 int rl_fail(int code, const char* fmt, ...);
 }
 
+namespace rl {
+// kernel classes for launch counting and the optional per-class CUDA-event timing used by bench.py's roofline
+enum KernelClass { KC_DENSE_FWD = 0, KC_GEMM_PX, KC_DGRAD_DENSE, KC_DGRAD_TD, KC_WGRAD, KC_HEAD, KC_DZ_PREPARE,
+                   KC_STATS, KC_FIRST_FWD, KC_TU_COL2IM, KC_PACK, KC_OPT, KC_MISC, KC_COUNT };
+struct ProfScope {
+  int cls;
+  cudaStream_t st;
+  int slot;
+  ProfScope(int cls, cudaStream_t st);
+  ~ProfScope();
+};
+}  // namespace rl
+
 #define RL_CUDA(expr)                                                                                   \
   do {                                                                                                  \
     cudaError_t _e = (expr);                                                                            \

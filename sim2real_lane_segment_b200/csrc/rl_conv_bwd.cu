@@ -295,10 +295,12 @@ int launch_dgrad(const DgradArgs& a, int grid, cudaStream_t st) {
   if (a.dense) {
     if (a.strip_w + 2 > 165) return rl_fail(RL_ERR_SHAPE, "dgrad: strip too wide");
     size_t smem = 36864 + 2 * kDzRows * 16 + 512;
-    dgrad_dense_kernel<<<grid, 128, smem, st>>>(a);
+    { ProfScope _ps(KC_DGRAD_DENSE, st);
+  dgrad_dense_kernel<<<grid, 128, smem, st>>>(a); }
   } else {
     size_t smem = 2 * 32768 + 512;
-    dgrad_td_kernel<<<grid, 128, smem, st>>>(a);
+    { ProfScope _ps(KC_DGRAD_TD, st);
+  dgrad_td_kernel<<<grid, 128, smem, st>>>(a); }
   }
   RL_CUDA(cudaGetLastError());
   return RL_OK;
@@ -443,7 +445,8 @@ int launch_wgrad(const WgradArgs& a, int nruns, int nmb, int nparts, cudaStream_
   for (int i = 0; i < nparts; ++i) npmax = a.part_np[i] > npmax ? a.part_np[i] : npmax;
   size_t smem = 1024 + 2 * (16384 + (size_t)npmax * 128);
   if (smem > 110 * 1024) return rl_fail(RL_ERR_SHAPE, "wgrad: smem %zu too large", smem);
-  wgrad_kernel<<<dim3(nruns, nmb, nparts), 128, smem, st>>>(a);
+  { ProfScope _ps(KC_WGRAD, st);
+  wgrad_kernel<<<dim3(nruns, nmb, nparts), 128, smem, st>>>(a); }
   RL_CUDA(cudaGetLastError());
   return RL_OK;
 }

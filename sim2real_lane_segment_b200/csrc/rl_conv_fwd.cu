@@ -414,7 +414,8 @@ int launch_dense_fwd(const DenseFwdArgs& a, int grid, cudaStream_t st) {
     configured = 110 * 1024;
   }
   if (smem > 110 * 1024) return rl_fail(RL_ERR_SHAPE, "dense_fwd: smem %zu too large", smem);
-  dense_fwd_kernel<<<grid, 128, smem, st>>>(a);
+  { ProfScope _ps(KC_DENSE_FWD, st);
+  dense_fwd_kernel<<<grid, 128, smem, st>>>(a); }
   RL_CUDA(cudaGetLastError());
   return RL_OK;
 }
@@ -429,7 +430,8 @@ int launch_gemm_px(const GemmPxArgs& a, int grid_x, int nparts, cudaStream_t st)
     configured = true;
   }
   if (smem > 110 * 1024) return rl_fail(RL_ERR_SHAPE, "gemm_px: smem %zu too large (K=%d np=%d)", smem, a.K, npmax);
-  gemm_px_kernel<<<dim3(grid_x, nparts), 128, smem, st>>>(a);
+  { ProfScope _ps(KC_GEMM_PX, st);
+  gemm_px_kernel<<<dim3(grid_x, nparts), 128, smem, st>>>(a); }
   RL_CUDA(cudaGetLastError());
   return RL_OK;
 }

@@ -111,6 +111,7 @@ struct HeadArgs {
   // backward (null dact = forward only)
   const float* dprobs;        // external d(loss)/d(probs) [B][C][H][W] or null -> fused CE gradient
   float grad_scale;           // multiplies the fused CE gradient (grad_output of the loss)
+  const float* grad_scale_dev;  // optional device scalar multiplied in as well
   float feat_grad_sign;       // -1 for GradReverse between extractor and classifier (tiramisu.py:7-18)
   __nv_bfloat16* dact;
   __nv_bfloat16* dl;          // [px][16] bf16: d(logits)/||f||

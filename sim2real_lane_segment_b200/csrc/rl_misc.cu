@@ -90,7 +90,8 @@ __global__ void pack_weights_kernel(const PackEntry* tab, const float* __restric
 
 int launch_pack_weights(const Plan* p, const float* params, cudaStream_t st) {
   const PackEntry* tab = reinterpret_cast<const PackEntry*>((const uint8_t*)p->ws + p->packtab_off);
-  pack_weights_kernel<<<dim3(24, p->n_pack), 256, 0, st>>>(tab, params, (uint8_t*)p->ws);
+  { ProfScope _ps(KC_PACK, st);
+  pack_weights_kernel<<<dim3(24, p->n_pack), 256, 0, st>>>(tab, params, (uint8_t*)p->ws); }
   RL_CUDA(cudaGetLastError());
   return RL_OK;
 }
@@ -149,8 +150,9 @@ int launch_first_fwd(const Plan* p, const float* x, const float* params, cudaStr
   const Layer& L = p->layers[0];
   __nv_bfloat16* act = (__nv_bfloat16*)((uint8_t*)p->ws + p->lv[0].act_off);
   __nv_bfloat16* xcol = p->training ? (__nv_bfloat16*)((uint8_t*)p->ws + p->xcol_off) : nullptr;
+  { ProfScope _ps(KC_FIRST_FWD, st);
   first_fwd_kernel<<<p->sm_count * 4, 256, 0, st>>>(x, params + L.p_w, params + L.p_b, act, p->lv[0].Ct, p->B, p->H, p->W,
-                                                    xcol);
+                                                    xcol); }
   RL_CUDA(cudaGetLastError());
   return RL_OK;
 }
@@ -198,7 +200,8 @@ int launch_channel_stats(const __nv_bfloat16* arena, long npx, int Ct, int c_off
                          cudaStream_t st) {
   int nchunk = nch / 8, ppb = 256 / nchunk;
   int grid = (int)std::min<long>((npx + ppb - 1) / ppb, (long)sm * 4);
-  channel_stats_kernel<<<grid, 256, 256 * 16 * sizeof(float), st>>>(arena, npx, Ct, c_off, nch, stats);
+  { ProfScope _ps(KC_STATS, st);
+  channel_stats_kernel<<<grid, 256, 256 * 16 * sizeof(float), st>>>(arena, npx, Ct, c_off, nch, stats); }
   RL_CUDA(cudaGetLastError());
   return RL_OK;
 }
@@ -244,7 +247,8 @@ int launch_tu_col2im(const __nv_bfloat16* ycol, __nv_bfloat16* out, const float*
                      int W, int Ct, int o_off, cudaStream_t st) {
   long total = (long)B * H * W * 10;
   int grid = (int)std::min<long>((total + 255) / 256, 148L * 16);
-  tu_col2im_kernel<<<grid, 256, 0, st>>>(ycol, out, bias, B, h, w, H, W, Ct, o_off);
+  { ProfScope _ps(KC_TU_COL2IM, st);
+  tu_col2im_kernel<<<grid, 256, 0, st>>>(ycol, out, bias, B, h, w, H, W, Ct, o_off); }
   RL_CUDA(cudaGetLastError());
   return RL_OK;
 }
@@ -276,7 +280,8 @@ __global__ void __launch_bounds__(256) label_hist_kernel(const void* y, int is64
 
 int launch_label_hist(const void* y, int y_is_i64, long n, int num_cls, Scalars* sc, cudaStream_t st) {
   int grid = (int)std::min<long>((n + 255) / 256, 148L * 8);
-  label_hist_kernel<<<grid, 256, 0, st>>>(y, y_is_i64, n, num_cls, sc);
+  { ProfScope _ps(KC_MISC, st);
+  label_hist_kernel<<<grid, 256, 0, st>>>(y, y_is_i64, n, num_cls, sc); }
   RL_CUDA(cudaGetLastError());
   return RL_OK;
 }
@@ -321,6 +326,7 @@ __global__ void __launch_bounds__(256) head_kernel(HeadArgs a) {
 #pragma unroll
   for (int k = 0; k < C; ++k) db[k] = 0.f;
   const float inv_den = 1.0f / s_den;
+  const float gscale = a.grad_scale * (a.grad_scale_dev ? __ldg(a.grad_scale_dev) : 1.0f);
 
   for (long base = ((long)blockIdx.x * 8 + warp) * 8; base < a.npx; base += (long)gridDim.x * 64) {
     const long P = base + pi;
@@ -418,7 +424,7 @@ __global__ void __launch_bounds__(256) head_kernel(HeadArgs a) {
         if (a.dprobs)
           dp[k] = valid ? a.dprobs[((long)b * C + k) * a.HW + hw] : 0.f;
         else
-          dp[k] = (label >= 0) ? a.grad_scale * wl * inv_den * (sm2[k] - (k == label ? 1.f : 0.f)) : 0.f;
+          dp[k] = (label >= 0) ? gscale * wl * inv_den * (sm2[k] - (k == label ? 1.f : 0.f)) : 0.f;
       }
       float dsum = 0.f;
 #pragma unroll
@@ -489,6 +495,7 @@ __global__ void __launch_bounds__(256) head_kernel(HeadArgs a) {
 
 int launch_head(const HeadArgs& a, int sm, cudaStream_t st) {
   int grid = (int)std::min<long>((a.npx + 63) / 64, (long)sm * 4);
+  ProfScope _ps(KC_HEAD, st);
   switch (a.num_cls) {
     case 2: head_kernel<2><<<grid, 256, 0, st>>>(a); break;
     case 3: head_kernel<3><<<grid, 256, 0, st>>>(a); break;
@@ -631,7 +638,8 @@ int launch_dz_prepare(const DzArgs& a, int sm, cudaStream_t st) {
   long blocks = (a.kind == 2) ? (work * nchunk + 255) / 256 : (work + ppb - 1) / ppb;
   int grid = (int)std::min<long>(blocks, (long)sm * 8);
   if (grid < 1) grid = 1;
-  dz_prepare_kernel<<<grid, 256, smem, st>>>(a);
+  { ProfScope _ps(KC_DZ_PREPARE, st);
+  dz_prepare_kernel<<<grid, 256, smem, st>>>(a); }
   RL_CUDA(cudaGetLastError());
   return RL_OK;
 }
@@ -653,7 +661,8 @@ __global__ void bn_running_kernel(const BnTabEntry* tab, const uint8_t* ws, floa
 
 int launch_bn_running(const Plan* p, float* bnbuf, float momentum, cudaStream_t st) {
   const BnTabEntry* tab = reinterpret_cast<const BnTabEntry*>((const uint8_t*)p->ws + p->bntab_off);
-  bn_running_kernel<<<p->n_bn, 256, 0, st>>>(tab, (const uint8_t*)p->ws, bnbuf, momentum);
+  { ProfScope _ps(KC_MISC, st);
+  bn_running_kernel<<<p->n_bn, 256, 0, st>>>(tab, (const uint8_t*)p->ws, bnbuf, momentum); }
   RL_CUDA(cudaGetLastError());
   return RL_OK;
 }
@@ -681,7 +690,8 @@ __global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, const
 int launch_adamw(float* p, const float* g, float* m, float* v, long n, float lr, float b1, float b2, float eps, float wd,
                  float bc1, float bc2, float grad_scale, cudaStream_t st) {
   int grid = (int)std::min<long>((n + 255) / 256, 148L * 8);
-  adamw_kernel<<<grid, 256, 0, st>>>(p, g, m, v, n, lr, b1, b2, eps, wd, bc1, bc2, grad_scale);
+  { ProfScope _ps(KC_OPT, st);
+  adamw_kernel<<<grid, 256, 0, st>>>(p, g, m, v, n, lr, b1, b2, eps, wd, bc1, bc2, grad_scale); }
   RL_CUDA(cudaGetLastError());
   return RL_OK;
 }
@@ -700,7 +710,8 @@ __global__ void __launch_bounds__(256) sgd_nesterov_kernel(float* __restrict__ p
 int launch_sgd_nesterov(float* p, const float* g, float* buf, long n, float lr, float momentum, float wd, int first,
                         float grad_scale, cudaStream_t st) {
   int grid = (int)std::min<long>((n + 255) / 256, 148L * 8);
-  sgd_nesterov_kernel<<<grid, 256, 0, st>>>(p, g, buf, n, lr, momentum, wd, first, grad_scale);
+  { ProfScope _ps(KC_OPT, st);
+  sgd_nesterov_kernel<<<grid, 256, 0, st>>>(p, g, buf, n, lr, momentum, wd, first, grad_scale); }
   RL_CUDA(cudaGetLastError());
   return RL_OK;
 }
@@ -723,7 +734,8 @@ __global__ void fill_masks_kernel(float* masks, long n, float p_drop, unsigned l
 }
 int launch_fill_masks(float* masks, long n, float p_drop, unsigned long long seed, unsigned long long step, cudaStream_t st) {
   int grid = (int)std::min<long>((n + 255) / 256, 148L * 4);
-  fill_masks_kernel<<<grid, 256, 0, st>>>(masks, n, p_drop, seed, step);
+  { ProfScope _ps(KC_MISC, st);
+  fill_masks_kernel<<<grid, 256, 0, st>>>(masks, n, p_drop, seed, step); }
   RL_CUDA(cudaGetLastError());
   return RL_OK;
 }

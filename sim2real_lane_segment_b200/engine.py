@@ -33,7 +33,7 @@ def _sigs(L):
     L.rl_set_dropout.argtypes = [c_void_p, c_float, c_ulonglong, c_ulonglong, c_void_p]
     L.rl_forward.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p]
     L.rl_head.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_float,
-                          c_float, c_void_p, c_void_p]
+                          c_void_p, c_float, c_void_p, c_void_p]
     L.rl_backward.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
     L.rl_bn_running_update.argtypes = [c_void_p, c_void_p, c_float, c_void_p]
     L.rl_adamw_step.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_long, c_float, c_float, c_float, c_float,
@@ -132,15 +132,15 @@ class Engine:
         _lib.check(self.L.rl_forward(self.h, _lib.ptr(params), _lib.ptr(bnbuf), _lib.ptr(x), int(train), _lib.cur_stream()))
 
     def head(self, params, y=None, weighted=False, probs=None, mask=None, backward=0, dprobs=None, grad_scale=1.0,
-             feat_grad_sign=1.0, grads=None):
-        _need_cuda(params, y, probs, mask, dprobs, grads)
+             feat_grad_sign=1.0, grads=None, grad_scale_dev=None):
+        _need_cuda(params, y, probs, mask, dprobs, grads, grad_scale_dev)
         y64 = 0
         if y is not None:
             assert y.is_contiguous() and y.dtype in (torch.uint8, torch.int64)
             y64 = int(y.dtype == torch.int64)
         _lib.check(self.L.rl_head(self.h, _lib.ptr(params), _lib.ptr(y), y64, int(weighted), _lib.ptr(probs), _lib.ptr(mask),
-                                  int(backward), _lib.ptr(dprobs), float(grad_scale), float(feat_grad_sign),
-                                  _lib.ptr(grads), _lib.cur_stream()))
+                                  int(backward), _lib.ptr(dprobs), float(grad_scale), _lib.ptr(grad_scale_dev),
+                                  float(feat_grad_sign), _lib.ptr(grads), _lib.cur_stream()))
 
     def backward(self, params, x, grads):
         _need_cuda(params, x, grads)

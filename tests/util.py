@@ -33,3 +33,24 @@ def ref_to_phys(t, cskip):
 
 def rel_err(a, b):
     return float((a.float() - b.float()).norm() / (b.float().norm() + 1e-30))
+
+
+def layer_names():
+    """state_dict prefixes of the layers in the C plan's forward order (csrc/rl_plan.cu)"""
+    names = ["featureExtractor.firstconv"]
+    for l in range(5):
+        names += [f"featureExtractor.denseBlocksDown.{l}.layers.{j}" for j in range(5)]
+        names.append(f"featureExtractor.transDownBlocks.{l}")
+    names += [f"featureExtractor.bottleneck.bottleneck.layers.{j}" for j in range(5)]
+    for i in range(5):
+        names.append(f"featureExtractor.transUpBlocks.{i}")
+        names += [f"featureExtractor.denseBlocksUp.{i}.layers.{j}" for j in range(5)]
+    return names
+
+
+def install_drop_masks(eng, masks, p_drop=0.2):
+    """write oracle keep masks (dict '<layer prefix>.drop' -> [B, C] of 0/1) into the plan's dropout scale blocks"""
+    for idx, name in enumerate(layer_names()):
+        key = name + ".drop"
+        if key in masks:
+            eng.layer_mask_view(idx).copy_(masks[key].to("cuda") / (1.0 - p_drop))
