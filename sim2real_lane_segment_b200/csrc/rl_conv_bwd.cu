@@ -13,89 +13,167 @@
 
 namespace rl {
 
-constexpr int kDzRows = 464;  // halo tile rows: 128 + 2*(strip+2) + 2 <= 464 for strips up to 165 columns
+constexpr int kDzRows = 464;
+
+__device__ __forceinline__ void unpack8(uint4 v, float* f) {
+  float2 a = unpack_bf16x2(v.x), b = unpack_bf16x2(v.y), c = unpack_bf16x2(v.z), d = unpack_bf16x2(v.w);
+  f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
+}
+__device__ __forceinline__ uint4 pack8(const float* v) {
+  return make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+}
+  // halo tile rows: 128 + 2*(strip+2) + 2 <= 464 for strips up to 165 columns
 
 // ------------------------------------------------------------------------------------------------
-// epilogue shared by both dgrad kernels: thread = channel, 128 accumulator columns = pixels
+// epilogue shared by both dgrad kernels.  Accumulator: rows (TMEM lanes = threads) are PIXELS, columns are the
+// (up to 128) input channels of the current channel block, so every thread streams 32-byte channel groups of its
+// own pixel from the NHWC arenas (x, dX) with 16-byte accesses.  The per-channel BatchNorm-backward sums
+//   S1_c = Σ_p g[p,c]      S2_c = Σ_p g[p,c]·(x[p,c] - mean_c)          (g = relu-masked input gradient)
+// are reduced across the 32 pixels of a warp with a transposing butterfly (16 shuffles per quantity per 16 channels)
+// and kept in registers across tiles.
 // ------------------------------------------------------------------------------------------------
-struct DgradChan {
-  bool active;
-  int c;
-  float s, t, mean, rstd, gr;  // gr = gamma * rstd
-  float S1, S2;
+struct DgradConsts {  // per channel of the current block, in shared memory
+  float s[128], t[128], gr[128], mean[128];
 };
 
-__device__ __forceinline__ void dgrad_epilogue(uint32_t tmem_acc, int warp, const int* P_s, const DgradArgs& a,
-                                               DgradChan& ch) {
-  const unsigned short* actu = reinterpret_cast<const unsigned short*>(a.act);
-  unsigned short* dactu = reinterpret_cast<unsigned short*>(a.dact);
-  const bool rmw = ch.c >= a.rmw_from;
-#pragma unroll 1
-  for (int n0 = 0; n0 < 128; n0 += 16) {
-    float g[16];
-    tmem_ld16(tmem_acc + ((uint32_t)(warp * 32) << 16) + n0, g);
-    if (ch.active) {
-      unsigned short xs[16], ds[16];
-      long idx[16];
+// Σ over the 32 lanes of v[k] for k = 0..15; lane l ends up holding the total of k = (l >> 1) & 15
+__device__ __forceinline__ float warp_reduce16(float* v, int lane) {
+  {
+    const bool hi = lane & 16;
 #pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        const int P = P_s[n0 + i];
-        idx[i] = P >= 0 ? (long)P * a.Ct + ch.c : -1;
-        xs[i] = idx[i] >= 0 ? __ldg(actu + idx[i]) : (unsigned short)0;
-        ds[i] = (idx[i] >= 0 && rmw) ? dactu[idx[i]] : (unsigned short)0;
-      }
+    for (int i = 0; i < 8; ++i) {
+      const float send = hi ? v[i] : v[i + 8], keep = hi ? v[i + 8] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    }
+  }
+  {
+    const bool hi = lane & 8;
 #pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        if (idx[i] >= 0) {
-          const float x = __uint_as_float((uint32_t)xs[i] << 16);
-          const float gi = (fmaf(x, ch.s, ch.t) > 0.f) ? g[i] : 0.f;
-          const float xh = (x - ch.mean) * ch.rstd;
-          ch.S1 += gi;
-          ch.S2 = fmaf(gi, xh, ch.S2);
-          const float old = __uint_as_float((uint32_t)ds[i] << 16);
-          dactu[idx[i]] = __bfloat16_as_ushort(__float2bfloat16_rn(fmaf(ch.gr, gi, old)));
+    for (int i = 0; i < 4; ++i) {
+      const float send = hi ? v[i] : v[i + 4], keep = hi ? v[i + 4] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+    }
+  }
+  {
+    const bool hi = lane & 4;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const float send = hi ? v[i] : v[i + 2], keep = hi ? v[i + 2] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+    }
+  }
+  {
+    const bool hi = lane & 2;
+    const float send = hi ? v[0] : v[1], keep = hi ? v[1] : v[0];
+    v[0] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+  }
+  return v[0] + __shfl_xor_sync(0xffffffffu, v[0], 1);
+}
+
+// one 128-pixel tile x one channel block; P = this thread's pixel (or -1); S1/S2: per-thread running totals, index =
+// channel group (16 channels), the lane's channel inside the group is (lane >> 1) & 15
+__device__ __forceinline__ void dgrad_epilogue(uint32_t tmem_acc, int warp, int lane, int P, int cbase, int nvalid,
+                                               const DgradConsts* k, const DgradArgs& a, float* S1, float* S2) {
+  const __nv_bfloat16* xrow = P >= 0 ? a.act + (size_t)P * a.Ct + cbase : nullptr;
+  __nv_bfloat16* drow = P >= 0 ? a.dact + (size_t)P * a.Ct + cbase : nullptr;
+#pragma unroll
+  for (int gi = 0; gi < 8; ++gi) {
+    const int c0 = gi * 16;
+    if (c0 < nvalid) {  // warp-uniform
+      float g[16];
+      tmem_ld16(tmem_acc + ((uint32_t)(warp * 32) << 16) + c0, g);
+      float gs[16], gx[16];
+      if (P >= 0) {
+        const bool rmw = (cbase + c0) >= a.rmw_from;
+        float x[16], d[16];
+        unpack8(ldg128(xrow + c0), x);
+        unpack8(ldg128(xrow + c0 + 8), x + 8);
+        if (rmw) {
+          unpack8(*reinterpret_cast<const uint4*>(drow + c0), d);
+          unpack8(*reinterpret_cast<const uint4*>(drow + c0 + 8), d + 8);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) d[i] = 0.f;
         }
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const float gv = (fmaf(x[i], k->s[c0 + i], k->t[c0 + i]) > 0.f) ? g[i] : 0.f;
+          gs[i] = gv;
+          gx[i] = gv * (x[i] - k->mean[c0 + i]);
+          d[i] = fmaf(k->gr[c0 + i], gv, d[i]);
+        }
+        *reinterpret_cast<uint4*>(drow + c0) = pack8(d);
+        *reinterpret_cast<uint4*>(drow + c0 + 8) = pack8(d + 8);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) gs[i] = gx[i] = 0.f;
       }
+      S1[gi] += warp_reduce16(gs, lane);
+      S2[gi] += warp_reduce16(gx, lane);
     }
   }
 }
 
-__device__ __forceinline__ void dgrad_chan_init(DgradChan& ch, const DgradArgs& a, int mb) {
-  ch.c = mb * 128 + threadIdx.x;
-  ch.active = ch.c < a.Cin;
-  ch.S1 = ch.S2 = 0.f;
-  if (ch.active) {
-    BnCoef k = bn_coef(a.bn, ch.c);
-    ch.s = k.s;
-    ch.t = k.t;
-    ch.mean = k.mean;
-    ch.rstd = k.rstd;
-    ch.gr = k.gamma * k.rstd;
-  } else {
-    ch.s = ch.t = ch.mean = ch.rstd = ch.gr = 0.f;
+__device__ __forceinline__ void dgrad_consts_init(DgradConsts* k, float* s_rstd, const DgradArgs& a, int mb) {
+  const int c = mb * 128 + threadIdx.x;
+  float s = 0.f, t = 0.f, gr = 0.f, mean = 0.f, rstd = 0.f;
+  if (c < a.Cin) {
+    BnCoef b = bn_coef(a.bn, c);
+    s = b.s;
+    t = b.t;
+    gr = b.gamma * b.rstd;
+    mean = b.mean;
+    rstd = b.rstd;
   }
+  k->s[threadIdx.x] = s;
+  k->t[threadIdx.x] = t;
+  k->gr[threadIdx.x] = gr;
+  k->mean[threadIdx.x] = mean;
+  s_rstd[threadIdx.x] = rstd;
 }
 
-__device__ __forceinline__ void dgrad_chan_flush(const DgradChan& ch, const DgradArgs& a) {
-  if (!ch.active) return;
-  const int rc = ref_channel(ch.c, a.bn.cs_perm);
-  atomicAdd(a.g_beta + rc, ch.S1);
-  atomicAdd(a.g_gamma + rc, ch.S2);
-  atomicAdd(a.acc + ch.c, (double)(ch.gr * ch.S1));
-  atomicAdd(a.acc + a.Ct + ch.c, (double)(ch.gr * ch.S2));
+// block totals -> gradient slots: dβ = S1, dγ = rstd·S2, and the deferred mean terms A += γ·rstd·S1, B += γ·rstd·(rstd·S2)
+__device__ __forceinline__ void dgrad_flush(float* s_sum /*[2][128]*/, const float* S1, const float* S2, int warp, int lane,
+                                            const DgradConsts* k, const float* s_rstd, const DgradArgs& a, int mb,
+                                            int nvalid) {
+  for (int i = threadIdx.x; i < 256; i += 128) s_sum[i] = 0.f;
+  __syncthreads();
+  if ((lane & 1) == 0) {
+    const int cl = (lane >> 1) & 15;
+#pragma unroll
+    for (int gi = 0; gi < 8; ++gi)
+      if (gi * 16 < nvalid) {
+        atomicAdd(&s_sum[gi * 16 + cl], S1[gi]);
+        atomicAdd(&s_sum[128 + gi * 16 + cl], S2[gi]);
+      }
+  }
+  __syncthreads();
+  const int cl = threadIdx.x;
+  if (cl < nvalid) {
+    const int c = mb * 128 + cl;
+    const float s1 = s_sum[cl], s2 = s_rstd[cl] * s_sum[128 + cl];
+    const int rc = ref_channel(c, a.bn.cs_perm);
+    atomicAdd(a.g_beta + rc, s1);
+    atomicAdd(a.g_gamma + rc, s2);
+    atomicAdd(a.acc + c, (double)(k->gr[cl] * s1));
+    atomicAdd(a.acc + a.Ct + c, (double)(k->gr[cl] * s2));
+  }
+  (void)warp;
 }
 
 // ================================================================================================
-// dgrad_dense_kernel
+// dgrad_dense_kernel:  G[p, c] = Σ_tap dz[p - tap, 0:16] · W[tap][0:16, c]   (M = 128 pixels, N = channel block, K = 16/tap)
 // ================================================================================================
 __global__ void __launch_bounds__(128, 3) dgrad_dense_kernel(DgradArgs a) {
   extern __shared__ __align__(128) uint8_t smem[];
-  uint8_t* sW = smem;                 // W^T of one M-block: [18][128][8] bf16 = 36864 B
-  uint8_t* sDz = smem + 36864;        // halo tile [2][kDzRows][8] bf16 = 14848 B
-  int* P_s = reinterpret_cast<int*>(smem + 36864 + 2 * kDzRows * 16);
+  uint8_t* sW = smem;                 // W of one channel block: [18][128][8] bf16 = 36864 B   (B operand, rows = channels)
+  uint8_t* sDz = smem + 36864;        // halo tile [2][kDzRows][8] bf16 = 14848 B              (A operand, rows = pixels)
+  DgradConsts* kc = reinterpret_cast<DgradConsts*>(smem + 36864 + 2 * kDzRows * 16);
+  float* s_rstd = reinterpret_cast<float*>(kc + 1);
+  float* s_sum = s_rstd + 128;
   __shared__ uint64_t bar_w, bar_mma;
   __shared__ uint32_t tmem_base_s;
-  const int tid = threadIdx.x, warp = tid >> 5;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   const int VH = a.H + 1;
   const int vrows_total = a.B * VH;
@@ -117,13 +195,16 @@ __global__ void __launch_bounds__(128, 3) dgrad_dense_kernel(DgradArgs a) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_base_s;
-  const uint32_t idesc = umma_idesc_bf16(128, 0, 0);
   uint32_t n_w = 0, n_mma = 0;
 
   for (int mb = 0; mb < nmb; ++mb) {
-    DgradChan ch;
-    dgrad_chan_init(ch, a, mb);
-    __syncthreads();  // every MMA of the previous M-block has been waited for: sW may be overwritten
+    const int nvalid = min(128, a.Cin - mb * 128);
+    const uint32_t idesc = umma_idesc_bf16((uint32_t)nvalid, 0, 0);
+    float S1[8], S2[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) S1[i] = S2[i] = 0.f;
+    __syncthreads();  // every MMA of the previous block has been waited for: sW / constants may be overwritten
+    dgrad_consts_init(kc, s_rstd, a, mb);
     if (tid == 0) {
       mbar_arrive_expect_tx(&bar_w, 36864);
       bulk_g2s(sW, a.wpk + (size_t)mb * 36864, 36864, &bar_w);
@@ -150,43 +231,40 @@ __global__ void __launch_bounds__(128, 3) dgrad_dense_kernel(DgradArgs a) {
         *reinterpret_cast<uint4*>(sDz + (size_t)rr * 16) = v0;
         *reinterpret_cast<uint4*>(sDz + ((size_t)kDzRows + rr) * 16) = v1;
       }
-      {  // accumulator column -> pixel
+      int P = -1;  // accumulator row -> pixel
+      {
         const int t = t0 + tid;
-        int P = -1;
         if (t < t_end) {
           const int rrow = t / SW, cc = t - rrow * SW;
           const int vr = V0 - 1 + rrow, xc = x0 - 1 + cc;
           const int img = vr / VH, ri = vr - img * VH;
           if (ri < a.H && xc >= x0 && xc < x1) P = (img * a.H + ri) * a.W + xc;
         }
-        P_s[tid] = P;
       }
       fence_proxy_async();
       __syncthreads();
       if (tid == 0) {
-        if (tile == 0) {
-          mbar_wait(&bar_w, n_w & 1);
-        }
+        if (tile == 0) mbar_wait(&bar_w, n_w & 1);
         tc_fence_after();
         const uint32_t wa = smem_u32(sW), da = smem_u32(sDz);
 #pragma unroll
         for (int tap = 0; tap < 9; ++tap) {
           const int dy = tap / 3 - 1, dx = tap % 3 - 1;
           const uint32_t roff = (uint32_t)((1 - dy) * SW + (1 - dx));
-          umma_ss(tmem, desc_kmajor(wa + tap * 2 * 16 * 128, 128), desc_kmajor(da + roff * 16, kDzRows), idesc, tap != 0);
+          umma_ss(tmem, desc_kmajor(da + roff * 16, kDzRows), desc_kmajor(wa + tap * 2 * 16 * 128, 128), idesc, tap != 0);
         }
         umma_commit(&bar_mma);
       }
       mbar_wait(&bar_mma, n_mma & 1);
       ++n_mma;
       tc_fence_after();
-      dgrad_epilogue(tmem, warp, P_s, a, ch);
+      dgrad_epilogue(tmem, warp, lane, P, mb * 128, nvalid, kc, a, S1, S2);
       tc_fence_before();
       __syncthreads();
     }
-    if (ntiles > 0) ++n_w;
-    else if (tid == 0) { mbar_wait(&bar_w, n_w & 1); ++n_w; }
-    dgrad_chan_flush(ch, a);
+    if (ntiles == 0 && tid == 0) mbar_wait(&bar_w, n_w & 1);
+    ++n_w;
+    dgrad_flush(s_sum, S1, S2, warp, lane, kc, s_rstd, a, mb, nvalid);
   }
   tc_fence_before();
   __syncthreads();
@@ -194,15 +272,17 @@ __global__ void __launch_bounds__(128, 3) dgrad_dense_kernel(DgradArgs a) {
 }
 
 // ================================================================================================
-// dgrad_td_kernel
+// dgrad_td_kernel:  G[p, c] = Σ_co dz[p, co] · W[co, c]   (M = 128 pixels, N = channel block, K = C streamed in chunks of 64)
 // ================================================================================================
 __global__ void __launch_bounds__(128, 3) dgrad_td_kernel(DgradArgs a) {
   extern __shared__ __align__(128) uint8_t smem[];
-  uint8_t* stage_base = smem;  // 2 x (W^T chunk 16 KB + dz chunk 16 KB)
-  int* P_s = reinterpret_cast<int*>(smem + 2 * 32768);
+  uint8_t* stage_base = smem;  // 2 x (W chunk 16 KB + dz chunk 16 KB)
+  DgradConsts* kcs = reinterpret_cast<DgradConsts*>(smem + 2 * 32768);
+  float* s_rstd = reinterpret_cast<float*>(kcs + 1);
+  float* s_sum = s_rstd + 128;
   __shared__ uint64_t bar_full[2], bar_done[2];
   __shared__ uint32_t tmem_base_s;
-  const int tid = threadIdx.x, warp = tid >> 5;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int nmb = (a.Cin + 127) / 128;
   const int nkc = (a.Kdz + 63) / 64;
   const long npx = (long)a.B * a.H * a.W;
@@ -219,24 +299,27 @@ __global__ void __launch_bounds__(128, 3) dgrad_td_kernel(DgradArgs a) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_base_s;
-  const uint32_t idesc = umma_idesc_bf16(128, 0, 0);
   uint32_t g = 0;
   TileLoader<128> ld;
   const __nv_bfloat16* rowptr[4];
 
   for (int mb = 0; mb < nmb; ++mb) {
-    DgradChan ch;
-    dgrad_chan_init(ch, a, mb);
+    const int nvalid = min(128, a.Cin - mb * 128);
+    const uint32_t idesc = umma_idesc_bf16((uint32_t)nvalid, 0, 0);
+    float S1[8], S2[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) S1[i] = S2[i] = 0.f;
+    __syncthreads();
+    dgrad_consts_init(kcs, s_rstd, a, mb);
+    __syncthreads();
     for (long tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        const long P = tile * 128 + TileLoader<128>::row_of(i);
-        rowptr[i] = P < npx ? a.dz + (size_t)P * a.Kdz : nullptr;
+        const long Pr = tile * 128 + TileLoader<128>::row_of(i);
+        rowptr[i] = Pr < npx ? a.dz + (size_t)Pr * a.Kdz : nullptr;
       }
-      {
-        const long P = tile * 128 + tid;
-        P_s[tid] = P < npx ? (int)P : -1;
-      }
+      const long Pl = tile * 128 + tid;
+      const int P = Pl < npx ? (int)Pl : -1;
       ld.load(rowptr, min(8, a.Kdz / 8));
       for (int kc = 0; kc < nkc; ++kc) {
         const int ck = min(64, a.Kdz - kc * 64);
@@ -263,7 +346,7 @@ __global__ void __launch_bounds__(128, 3) dgrad_td_kernel(DgradArgs a) {
           tc_fence_after();
           const uint32_t wa = smem_u32(sW), ba = smem_u32(sB);
           for (int kk = 0; kk < ck / 16; ++kk)
-            umma_ss(tmem, desc_kmajor(wa + kk * 2 * 16 * 128, 128), desc_kmajor(ba + kk * 2 * 16 * 128, 128), idesc,
+            umma_ss(tmem, desc_kmajor(ba + kk * 2 * 16 * 128, 128), desc_kmajor(wa + kk * 2 * 16 * 128, 128), idesc,
                     (kc | kk) != 0);
           umma_commit(&bar_done[s]);
         }
@@ -274,11 +357,11 @@ __global__ void __launch_bounds__(128, 3) dgrad_td_kernel(DgradArgs a) {
         mbar_wait(&bar_done[s], u & 1);
         tc_fence_after();
       }
-      dgrad_epilogue(tmem, warp, P_s, a, ch);
+      dgrad_epilogue(tmem, warp, lane, P, mb * 128, nvalid, kcs, a, S1, S2);
       tc_fence_before();
       __syncthreads();
     }
-    dgrad_chan_flush(ch, a);
+    dgrad_flush(s_sum, S1, S2, warp, lane, kcs, s_rstd, a, mb, nvalid);
   }
   tc_fence_before();
   __syncthreads();
@@ -294,11 +377,11 @@ int launch_dgrad(const DgradArgs& a, int grid, cudaStream_t st) {
   }
   if (a.dense) {
     if (a.strip_w + 2 > 165) return rl_fail(RL_ERR_SHAPE, "dgrad: strip too wide");
-    size_t smem = 36864 + 2 * kDzRows * 16 + 512;
+    size_t smem = 36864 + 2 * kDzRows * 16 + sizeof(DgradConsts) + 384 * sizeof(float);
     { ProfScope _ps(KC_DGRAD_DENSE, st);
   dgrad_dense_kernel<<<grid, 128, smem, st>>>(a); }
   } else {
-    size_t smem = 2 * 32768 + 512;
+    size_t smem = 2 * 32768 + sizeof(DgradConsts) + 384 * sizeof(float);
     { ProfScope _ps(KC_DGRAD_TD, st);
   dgrad_td_kernel<<<grid, 128, smem, st>>>(a); }
   }
@@ -361,24 +444,23 @@ __global__ void __launch_bounds__(128, 2) wgrad_kernel(WgradArgs a) {
   TileLoader<64> ld;
   const __nv_bfloat16* rowptr[2];
   const long HW = (long)a.H * a.W;
+  const int nj = (a.kind == WG_DENSE) ? 18 : np / 8;   // 16-byte column chunks of the B tile
+  const int nitems = nj / 2;                            // per thread: 64 rows * nj / 128 threads
+  uint4 bv[16];
 
-  for (int kc = 0; kc < nchunks; ++kc) {
+  // global -> registers for one K chunk (64 pixels) of both operands; consumed one iteration later
+  auto load_chunk = [&](int kc) {
     const long Pc = P0 + (long)kc * 64;
-    const uint32_t s = kc & 1, u = kc >> 1;
-    uint8_t* sA = stage_base + s * kStageBytes;
-    uint8_t* sB = sA + 16384;
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
       const long P = Pc + TileLoader<64>::row_of(i);
       rowptr[i] = P < P1 ? a.A + (size_t)P * a.lda + a.a_off + mb * 128 : nullptr;
     }
     ld.load(rowptr, a_nchunk);
-    if (u > 0) mbar_wait(&bar_done[s], (u - 1) & 1);
-    ld.store(sA, rowptr, a_nchunk, a.transform ? s_s : nullptr, s_t);
-    // zero-fill the channel chunks beyond Ca once per stage use is unnecessary: those accumulator rows are ignored
-    // ---- B tile
     if (a.kind == WG_DENSE) {
-      for (int it = tid; it < 64 * 18; it += 128) {
+#pragma unroll
+      for (int q = 0; q < 9; ++q) {
+        const int it = q * 128 + tid;
         const int row = it & 63, j = it >> 6;
         const int tap = j >> 1, half = j & 1;
         const long P = Pc + row;
@@ -390,18 +472,37 @@ __global__ void __launch_bounds__(128, 2) wgrad_kernel(WgradArgs a) {
           const int qy = y - dy, qx = x - dx;
           if (qy >= 0 && qy < a.H && qx >= 0 && qx < a.W) v = ldg128(a.Bm + ((b * a.H + qy) * a.W + qx) * 16 + half * 8);
         }
-        *reinterpret_cast<uint4*>(sB + ((size_t)j * 64 + row) * 16) = v;
+        bv[q] = v;
       }
     } else {
-      const int nj = np / 8;
-      for (int it = tid; it < 64 * nj; it += 128) {
-        const int row = it & 63, j = it >> 6;
-        const long P = Pc + row;
+#pragma unroll
+      for (int q = 0; q < 16; ++q) {
         uint4 v = make_uint4(0, 0, 0, 0);
-        if (P < P1) v = ldg128(a.Bm + (size_t)P * a.ldb + n0 + j * 8);
-        *reinterpret_cast<uint4*>(sB + ((size_t)j * 64 + row) * 16) = v;
+        if (q < nitems) {
+          const int it = q * 128 + tid;
+          const int row = it & 63, j = it >> 6;
+          const long P = Pc + row;
+          if (P < P1) v = ldg128(a.Bm + (size_t)P * a.ldb + n0 + j * 8);
+        }
+        bv[q] = v;
       }
     }
+  };
+
+  if (nchunks > 0) load_chunk(0);
+  for (int kc = 0; kc < nchunks; ++kc) {
+    const uint32_t s = kc & 1, u = kc >> 1;
+    uint8_t* sA = stage_base + s * kStageBytes;
+    uint8_t* sB = sA + 16384;
+    if (u > 0) mbar_wait(&bar_done[s], (u - 1) & 1);
+    ld.store(sA, rowptr, a_nchunk, a.transform ? s_s : nullptr, s_t);
+#pragma unroll
+    for (int q = 0; q < 16; ++q)
+      if (q < nitems) {
+        const int it = q * 128 + tid;
+        *reinterpret_cast<uint4*>(sB + ((size_t)(it >> 6) * 64 + (it & 63)) * 16) = bv[q];
+      }
+    if (kc + 1 < nchunks) load_chunk(kc + 1);  // in flight while this chunk's MMAs run
     fence_proxy_async();
     __syncthreads();
     if (tid == 0) {

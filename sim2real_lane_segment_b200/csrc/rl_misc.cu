@@ -593,29 +593,33 @@ __global__ void __launch_bounds__(256) dz_prepare_kernel(DzArgs a) {
         *reinterpret_cast<uint4*>(a.dz + P * a.nch + j * 8) = pack8(o);
       }
   } else {
-    // TU: column matrix row (b,i,j) holds dz at output pixels (2i+ky, 2j+kx) for the 9 taps
-    const int items = 9 * nchunk;  // per input pixel
-    const long npx_in = (long)a.B * a.Hp * a.Wp;
-    for (long it = blockIdx.x * (long)blockDim.x + threadIdx.x; it < npx_in * items; it += (long)gridDim.x * blockDim.x) {
-      const long Pin = it / items;
-      const int r = (int)(it % items), tap = r / nchunk, j = r % nchunk;
-      const int jj = (int)(Pin % a.Wp), ii = (int)((Pin / a.Wp) % a.Hp), b = (int)(Pin / ((long)a.Wp * a.Hp));
-      const int ky = tap / 3, kx = tap % 3, Y = 2 * ii + ky, X = 2 * jj + kx;
-      float o[8];
+    // TU: column matrix row (b,i,j) holds dz at output pixels (2i+ky, 2j+kx) for the 9 taps.
+    // thread <-> fixed channel chunk j; loops over (input pixel, tap) pairs, so the bias sum stays in registers
+    const int ppb = blockDim.x / nchunk;
+    const int j = threadIdx.x % nchunk, pl = threadIdx.x / nchunk;
+    const long nitems = (long)a.B * a.Hp * a.Wp * 9;
+    if (pl < ppb)
+      for (long it = (long)blockIdx.x * ppb + pl; it < nitems; it += (long)gridDim.x * ppb) {
+        const long Pin = it / 9;
+        const int tap = (int)(it - Pin * 9);
+        const int jj = (int)(Pin % a.Wp), ii = (int)((Pin / a.Wp) % a.Hp), b = (int)(Pin / ((long)a.Wp * a.Hp));
+        const int ky = tap / 3, kx = tap % 3, Y = 2 * ii + ky, X = 2 * jj + kx;
+        float o[8];
 #pragma unroll
-      for (int k = 0; k < 8; ++k) o[k] = 0.f;
-      if (Y < a.H && X < a.W) {
-        corrected(((long)b * a.H + Y) * a.W + X, j, b, o);
-        const bool count = (ky < 2 || ii == a.Hp - 1) && (kx < 2 || jj == a.Wp - 1);
-        if (count && a.g_bias) {
+        for (int k = 0; k < 8; ++k) o[k] = 0.f;
+        if (Y < a.H && X < a.W) {
+          corrected(((long)b * a.H + Y) * a.W + X, j, b, o);
+          // every output pixel appears in 1, 2 or 4 (pixel, tap) slots: count it once for the bias gradient
+          const bool count = (ky < 2 || ii == a.Hp - 1) && (kx < 2 || jj == a.Wp - 1);
+          if (count) {
 #pragma unroll
-          for (int k = 0; k < 8; ++k) atomicAdd(a.g_bias + j * 8 + k, o[k]);
+            for (int k = 0; k < 8; ++k) bsum[k] += o[k];
+          }
         }
+        *reinterpret_cast<uint4*>(a.dz + Pin * 720 + tap * a.nch + j * 8) = pack8(o);
       }
-      *reinterpret_cast<uint4*>(a.dz + Pin * 720 + tap * a.nch + j * 8) = pack8(o);
-    }
   }
-  if (a.kind != 2 && a.g_bias != nullptr) {
+  if (a.g_bias != nullptr) {
     __syncthreads();
 #pragma unroll
     for (int k = 0; k < 8; ++k) s_red[threadIdx.x * 8 + k] = bsum[k];
@@ -635,7 +639,7 @@ int launch_dz_prepare(const DzArgs& a, int sm, cudaStream_t st) {
   long work = (a.kind == 0) ? a.npx_out : (a.kind == 1 ? (long)a.B * a.H * a.W : (long)a.B * a.Hp * a.Wp * 9);
   int nchunk = a.nch / 8;
   int ppb = 256 / nchunk;
-  long blocks = (a.kind == 2) ? (work * nchunk + 255) / 256 : (work + ppb - 1) / ppb;
+  long blocks = (work + ppb - 1) / ppb;
   int grid = (int)std::min<long>(blocks, (long)sm * 8);
   if (grid < 1) grid = 1;
   { ProfScope _ps(KC_DZ_PREPARE, st);
