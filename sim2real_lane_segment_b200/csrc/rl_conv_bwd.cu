@@ -32,8 +32,8 @@ __device__ __forceinline__ uint4 pack8(const float* v) {
 // are reduced across the 32 pixels of a warp with a transposing butterfly (16 shuffles per quantity per 16 channels)
 // and kept in registers across tiles.
 // ------------------------------------------------------------------------------------------------
-struct DgradConsts {  // per channel of the current block, in shared memory
-  float s[128], t[128], gr[128], mean[128];
+struct DgradConsts {  // per channel of the current block, in shared memory: {s, t, gamma*rstd, mean}
+  float4 k[128];
 };
 
 // Σ over the 32 lanes of v[k] for k = 0..15; lane l ends up holding the total of k = (l >> 1) & 15
@@ -70,37 +70,51 @@ __device__ __forceinline__ float warp_reduce16(float* v, int lane) {
   return v[0] + __shfl_xor_sync(0xffffffffu, v[0], 1);
 }
 
+// x / dX of one 16-channel group of this thread's pixel, fetched two groups ahead of their use
+struct DgradPre {
+  uint4 x0, x1, d0, d1;
+};
+__device__ __forceinline__ void dgrad_prefetch(DgradPre& p, const __nv_bfloat16* xrow, const __nv_bfloat16* drow, int c0,
+                                               int nvalid, bool rmw) {
+  if (xrow != nullptr && c0 < nvalid) {
+    p.x0 = ldg128(xrow + c0);
+    p.x1 = ldg128(xrow + c0 + 8);
+    if (rmw) {
+      p.d0 = *reinterpret_cast<const uint4*>(drow + c0);
+      p.d1 = *reinterpret_cast<const uint4*>(drow + c0 + 8);
+    } else {
+      p.d0 = p.d1 = make_uint4(0, 0, 0, 0);
+    }
+  }
+}
+
 // one 128-pixel tile x one channel block; P = this thread's pixel (or -1); S1/S2: per-thread running totals, index =
-// channel group (16 channels), the lane's channel inside the group is (lane >> 1) & 15
-__device__ __forceinline__ void dgrad_epilogue(uint32_t tmem_acc, int warp, int lane, int P, int cbase, int nvalid,
-                                               const DgradConsts* k, const DgradArgs& a, float* S1, float* S2) {
-  const __nv_bfloat16* xrow = P >= 0 ? a.act + (size_t)P * a.Ct + cbase : nullptr;
-  __nv_bfloat16* drow = P >= 0 ? a.dact + (size_t)P * a.Ct + cbase : nullptr;
+// channel group (16 channels), the lane's channel inside the group is (lane >> 1) & 15.  pre[0..1] hold groups 0 and 1.
+__device__ __forceinline__ void dgrad_epilogue(uint32_t tmem_acc, int warp, int lane, const __nv_bfloat16* xrow,
+                                               __nv_bfloat16* drow, int cbase, int nvalid, const DgradConsts* k,
+                                               const DgradArgs& a, float* S1, float* S2, DgradPre* pre) {
 #pragma unroll
   for (int gi = 0; gi < 8; ++gi) {
     const int c0 = gi * 16;
     if (c0 < nvalid) {  // warp-uniform
       float g[16];
       tmem_ld16(tmem_acc + ((uint32_t)(warp * 32) << 16) + c0, g);
+      const DgradPre cur = pre[gi & 1];
+      if (gi + 2 < 8) dgrad_prefetch(pre[gi & 1], xrow, drow, c0 + 32, nvalid, (cbase + c0 + 32) >= a.rmw_from);
       float gs[16], gx[16];
-      if (P >= 0) {
-        const bool rmw = (cbase + c0) >= a.rmw_from;
+      if (xrow != nullptr) {
         float x[16], d[16];
-        unpack8(ldg128(xrow + c0), x);
-        unpack8(ldg128(xrow + c0 + 8), x + 8);
-        if (rmw) {
-          unpack8(*reinterpret_cast<const uint4*>(drow + c0), d);
-          unpack8(*reinterpret_cast<const uint4*>(drow + c0 + 8), d + 8);
-        } else {
-#pragma unroll
-          for (int i = 0; i < 16; ++i) d[i] = 0.f;
-        }
+        unpack8(cur.x0, x);
+        unpack8(cur.x1, x + 8);
+        unpack8(cur.d0, d);
+        unpack8(cur.d1, d + 8);
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
-          const float gv = (fmaf(x[i], k->s[c0 + i], k->t[c0 + i]) > 0.f) ? g[i] : 0.f;
+          const float4 kk = k->k[c0 + i];
+          const float gv = (fmaf(x[i], kk.x, kk.y) > 0.f) ? g[i] : 0.f;
           gs[i] = gv;
-          gx[i] = gv * (x[i] - k->mean[c0 + i]);
-          d[i] = fmaf(k->gr[c0 + i], gv, d[i]);
+          gx[i] = gv * (x[i] - kk.w);
+          d[i] = fmaf(kk.z, gv, d[i]);
         }
         *reinterpret_cast<uint4*>(drow + c0) = pack8(d);
         *reinterpret_cast<uint4*>(drow + c0 + 8) = pack8(d + 8);
@@ -125,10 +139,7 @@ __device__ __forceinline__ void dgrad_consts_init(DgradConsts* k, float* s_rstd,
     mean = b.mean;
     rstd = b.rstd;
   }
-  k->s[threadIdx.x] = s;
-  k->t[threadIdx.x] = t;
-  k->gr[threadIdx.x] = gr;
-  k->mean[threadIdx.x] = mean;
+  k->k[threadIdx.x] = make_float4(s, t, gr, mean);
   s_rstd[threadIdx.x] = rstd;
 }
 
@@ -155,8 +166,8 @@ __device__ __forceinline__ void dgrad_flush(float* s_sum /*[2][128]*/, const flo
     const int rc = ref_channel(c, a.bn.cs_perm);
     atomicAdd(a.g_beta + rc, s1);
     atomicAdd(a.g_gamma + rc, s2);
-    atomicAdd(a.acc + c, (double)(k->gr[cl] * s1));
-    atomicAdd(a.acc + a.Ct + c, (double)(k->gr[cl] * s2));
+    atomicAdd(a.acc + c, (double)(k->k[cl].z * s1));
+    atomicAdd(a.acc + a.Ct + c, (double)(k->k[cl].z * s2));
   }
   (void)warp;
 }
@@ -211,6 +222,21 @@ __global__ void __launch_bounds__(128, 3) dgrad_dense_kernel(DgradArgs a) {
     }
     for (int tile = 0; tile < ntiles; ++tile) {
       const int t0 = t_begin + tile * 128;
+      int P = -1;  // accumulator row -> pixel
+      {
+        const int t = t0 + tid;
+        if (t < t_end) {
+          const int rrow = t / SW, cc = t - rrow * SW;
+          const int vr = V0 - 1 + rrow, xc = x0 - 1 + cc;
+          const int img = vr / VH, ri = vr - img * VH;
+          if (ri < a.H && xc >= x0 && xc < x1) P = (img * a.H + ri) * a.W + xc;
+        }
+      }
+      const __nv_bfloat16* xrow = P >= 0 ? a.act + (size_t)P * a.Ct + mb * 128 : nullptr;
+      __nv_bfloat16* drow = P >= 0 ? a.dact + (size_t)P * a.Ct + mb * 128 : nullptr;
+      DgradPre pre[2];
+      dgrad_prefetch(pre[0], xrow, drow, 0, nvalid, (mb * 128) >= a.rmw_from);
+      dgrad_prefetch(pre[1], xrow, drow, 16, nvalid, (mb * 128 + 16) >= a.rmw_from);
       // ---- halo tile of dz: smem row rr <-> region position t0 - SW - 1 + rr
       const int nrows = 128 + 2 * SW + 2;
       for (int rr = tid; rr < nrows; rr += 128) {
@@ -231,16 +257,6 @@ __global__ void __launch_bounds__(128, 3) dgrad_dense_kernel(DgradArgs a) {
         *reinterpret_cast<uint4*>(sDz + (size_t)rr * 16) = v0;
         *reinterpret_cast<uint4*>(sDz + ((size_t)kDzRows + rr) * 16) = v1;
       }
-      int P = -1;  // accumulator row -> pixel
-      {
-        const int t = t0 + tid;
-        if (t < t_end) {
-          const int rrow = t / SW, cc = t - rrow * SW;
-          const int vr = V0 - 1 + rrow, xc = x0 - 1 + cc;
-          const int img = vr / VH, ri = vr - img * VH;
-          if (ri < a.H && xc >= x0 && xc < x1) P = (img * a.H + ri) * a.W + xc;
-        }
-      }
       fence_proxy_async();
       __syncthreads();
       if (tid == 0) {
@@ -258,7 +274,7 @@ __global__ void __launch_bounds__(128, 3) dgrad_dense_kernel(DgradArgs a) {
       mbar_wait(&bar_mma, n_mma & 1);
       ++n_mma;
       tc_fence_after();
-      dgrad_epilogue(tmem, warp, lane, P, mb * 128, nvalid, kc, a, S1, S2);
+      dgrad_epilogue(tmem, warp, lane, xrow, drow, mb * 128, nvalid, kc, a, S1, S2, pre);
       tc_fence_before();
       __syncthreads();
     }
@@ -320,6 +336,11 @@ __global__ void __launch_bounds__(128, 3) dgrad_td_kernel(DgradArgs a) {
       }
       const long Pl = tile * 128 + tid;
       const int P = Pl < npx ? (int)Pl : -1;
+      const __nv_bfloat16* xrow = P >= 0 ? a.act + (size_t)P * a.Ct + mb * 128 : nullptr;
+      __nv_bfloat16* drow = P >= 0 ? a.dact + (size_t)P * a.Ct + mb * 128 : nullptr;
+      DgradPre pre[2];
+      dgrad_prefetch(pre[0], xrow, drow, 0, nvalid, (mb * 128) >= a.rmw_from);
+      dgrad_prefetch(pre[1], xrow, drow, 16, nvalid, (mb * 128 + 16) >= a.rmw_from);
       ld.load(rowptr, min(8, a.Kdz / 8));
       for (int kc = 0; kc < nkc; ++kc) {
         const int ck = min(64, a.Kdz - kc * 64);
@@ -357,7 +378,7 @@ __global__ void __launch_bounds__(128, 3) dgrad_td_kernel(DgradArgs a) {
         mbar_wait(&bar_done[s], u & 1);
         tc_fence_after();
       }
-      dgrad_epilogue(tmem, warp, lane, P, mb * 128, nvalid, kcs, a, S1, S2);
+      dgrad_epilogue(tmem, warp, lane, xrow, drow, mb * 128, nvalid, kcs, a, S1, S2, pre);
       tc_fence_before();
       __syncthreads();
     }
@@ -402,7 +423,9 @@ __device__ __forceinline__ long wgrad_index(const WgradArgs& a, int c, int ng) {
   }
 }
 
-__global__ void __launch_bounds__(128, 2) wgrad_kernel(WgradArgs a) {
+constexpr int kWgThreads = 256;
+
+__global__ void __launch_bounds__(kWgThreads, 2) wgrad_kernel(WgradArgs a) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int mb = blockIdx.y, part = blockIdx.z;
   const int n0 = a.part_n0[part], np = a.part_np[part];
@@ -414,7 +437,7 @@ __global__ void __launch_bounds__(128, 2) wgrad_kernel(WgradArgs a) {
   const int kStageBytes = 16384 + stageB;
   __shared__ uint64_t bar_done[2];
   __shared__ uint32_t tmem_base_s;
-  const int tid = threadIdx.x, warp = tid >> 5;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   if (tid == 0) {
     mbar_init(&bar_done[0], 1);
@@ -422,7 +445,7 @@ __global__ void __launch_bounds__(128, 2) wgrad_kernel(WgradArgs a) {
     fence_mbar_init();
   }
   if (warp == 0) tmem_alloc(&tmem_base_s, 256);
-  {
+  if (tid < 128) {
     float s = 0.f, t = 0.f;
     if (a.transform && tid < ca) {
       BnCoef k = bn_coef(a.bn, mb * 128 + tid);
@@ -441,50 +464,53 @@ __global__ void __launch_bounds__(128, 2) wgrad_kernel(WgradArgs a) {
   const long P0 = (long)blockIdx.x * a.px_per_cta, P1 = min(P0 + a.px_per_cta, a.npx);
   const int nchunks = (int)((P1 - P0 + 63) / 64);
   const int a_nchunk = (ca + 7) / 8;
-  TileLoader<64> ld;
-  const __nv_bfloat16* rowptr[2];
   const long HW = (long)a.H * a.W;
-  const int nj = (a.kind == WG_DENSE) ? 18 : np / 8;   // 16-byte column chunks of the B tile
-  const int nitems = nj / 2;                            // per thread: 64 rows * nj / 128 threads
-  uint4 bv[16];
+  const int nj = (a.kind == WG_DENSE) ? 18 : np / 8;  // 16-byte column chunks of the B tile
+  // A tile: 64 pixel rows x 16 channel chunks -> 4 items per thread: row = 8*warp + (lane&7), chunk = (lane>>3) + 4h
+  const int a_row = warp * 8 + (lane & 7), a_j0 = lane >> 3;
+  // B tile: row = tid & 63, column chunks j = (tid >> 6) + 4q
+  const int b_row = tid & 63, b_j0 = tid >> 6;
+  uint4 av[4], bv[8];
+  bool a_valid = false;
 
-  // global -> registers for one K chunk (64 pixels) of both operands; consumed one iteration later
   auto load_chunk = [&](int kc) {
     const long Pc = P0 + (long)kc * 64;
+    {
+      const long P = Pc + a_row;
+      a_valid = P < P1;
+      const __nv_bfloat16* src = a.A + (size_t)P * a.lda + a.a_off + mb * 128;
 #pragma unroll
-    for (int i = 0; i < 2; ++i) {
-      const long P = Pc + TileLoader<64>::row_of(i);
-      rowptr[i] = P < P1 ? a.A + (size_t)P * a.lda + a.a_off + mb * 128 : nullptr;
+      for (int h = 0; h < 4; ++h) {
+        const int j = a_j0 + 4 * h;
+        av[h] = (a_valid && j < a_nchunk) ? ldg128(src + j * 8) : make_uint4(0, 0, 0, 0);
+      }
     }
-    ld.load(rowptr, a_nchunk);
+    const long P = Pc + b_row;
     if (a.kind == WG_DENSE) {
+      int y = 0, x = 0;
+      long b = 0;
+      if (P < P1) {
+        b = P / HW;
+        const int hw = (int)(P - b * HW);
+        y = hw / a.W;
+        x = hw - y * a.W;
+      }
 #pragma unroll
-      for (int q = 0; q < 9; ++q) {
-        const int it = q * 128 + tid;
-        const int row = it & 63, j = it >> 6;
-        const int tap = j >> 1, half = j & 1;
-        const long P = Pc + row;
+      for (int q = 0; q < 5; ++q) {
+        const int j = b_j0 + 4 * q;
         uint4 v = make_uint4(0, 0, 0, 0);
-        if (P < P1) {
-          const int dy = tap / 3 - 1, dx = tap % 3 - 1;
-          const long b = P / HW;
-          const int hw = (int)(P - b * HW), y = hw / a.W, x = hw - y * a.W;
-          const int qy = y - dy, qx = x - dx;
+        if (j < 18 && P < P1) {
+          const int tap = j >> 1, half = j & 1;
+          const int qy = y - (tap / 3 - 1), qx = x - (tap % 3 - 1);
           if (qy >= 0 && qy < a.H && qx >= 0 && qx < a.W) v = ldg128(a.Bm + ((b * a.H + qy) * a.W + qx) * 16 + half * 8);
         }
         bv[q] = v;
       }
     } else {
 #pragma unroll
-      for (int q = 0; q < 16; ++q) {
-        uint4 v = make_uint4(0, 0, 0, 0);
-        if (q < nitems) {
-          const int it = q * 128 + tid;
-          const int row = it & 63, j = it >> 6;
-          const long P = Pc + row;
-          if (P < P1) v = ldg128(a.Bm + (size_t)P * a.ldb + n0 + j * 8);
-        }
-        bv[q] = v;
+      for (int q = 0; q < 8; ++q) {
+        const int j = b_j0 + 4 * q;
+        bv[q] = (j < nj && P < P1) ? ldg128(a.Bm + (size_t)P * a.ldb + n0 + j * 8) : make_uint4(0, 0, 0, 0);
       }
     }
   };
@@ -495,13 +521,20 @@ __global__ void __launch_bounds__(128, 2) wgrad_kernel(WgradArgs a) {
     uint8_t* sA = stage_base + s * kStageBytes;
     uint8_t* sB = sA + 16384;
     if (u > 0) mbar_wait(&bar_done[s], (u - 1) & 1);
-    ld.store(sA, rowptr, a_nchunk, a.transform ? s_s : nullptr, s_t);
 #pragma unroll
-    for (int q = 0; q < 16; ++q)
-      if (q < nitems) {
-        const int it = q * 128 + tid;
-        *reinterpret_cast<uint4*>(sB + ((size_t)(it >> 6) * 64 + (it & 63)) * 16) = bv[q];
+    for (int h = 0; h < 4; ++h) {
+      const int j = a_j0 + 4 * h;
+      if (j < a_nchunk) {
+        uint4 o = av[h];
+        if (a.transform && a_valid) o = bn_relu8(o, s_s + j * 8, s_t + j * 8);
+        *reinterpret_cast<uint4*>(sA + ((size_t)j * 64 + a_row) * 16) = o;
       }
+    }
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const int j = b_j0 + 4 * q;
+      if (j < nj && (a.kind != WG_DENSE || q < 5)) *reinterpret_cast<uint4*>(sB + ((size_t)j * 64 + b_row) * 16) = bv[q];
+    }
     if (kc + 1 < nchunks) load_chunk(kc + 1);  // in flight while this chunk's MMAs run
     fence_proxy_async();
     __syncthreads();
@@ -514,7 +547,7 @@ __global__ void __launch_bounds__(128, 2) wgrad_kernel(WgradArgs a) {
       umma_commit(&bar_done[s]);
     }
   }
-  if (nchunks > 0) {
+  if (nchunks > 0 && warp < 4) {
     const uint32_t s = (nchunks - 1) & 1, u = (nchunks - 1) >> 1;
     mbar_wait(&bar_done[s], u & 1);
     tc_fence_after();
@@ -547,7 +580,7 @@ int launch_wgrad(const WgradArgs& a, int nruns, int nmb, int nparts, cudaStream_
   size_t smem = 1024 + 2 * (16384 + (size_t)npmax * 128);
   if (smem > 110 * 1024) return rl_fail(RL_ERR_SHAPE, "wgrad: smem %zu too large", smem);
   { ProfScope _ps(KC_WGRAD, st);
-  wgrad_kernel<<<dim3(nruns, nmb, nparts), 128, smem, st>>>(a); }
+  wgrad_kernel<<<dim3(nruns, nmb, nparts), kWgThreads, smem, st>>>(a); }
   RL_CUDA(cudaGetLastError());
   return RL_OK;
 }
