@@ -140,6 +140,7 @@ int rl_plan_bind(rl_plan* h, void* workspace, void* stream) {
   }
   p.n_bn = (int)bt.size();
   RL_CUDA(cudaMemcpyAsync(wsb(&p) + p.bntab_off, bt.data(), bt.size() * sizeof(BnTabEntry), cudaMemcpyHostToDevice, st));
+  if (p.training && p.dzp_bytes) RL_CUDA(cudaMemsetAsync(wsb(&p) + p.dzp_off_all, 0, p.dzp_bytes, st));
   RL_CUDA(cudaStreamSynchronize(st));  // host vectors go out of scope
   // dropout scales default to 1 (no dropout)
   return rl_set_dropout(h, 0.f, 0, 0, stream);
@@ -377,11 +378,19 @@ extern "C" int rl_backward(rl_plan* h, const float* params, const float* x, floa
     if (L.type == L_DENSE) {
       z.kind = 0;
       z.mask = (const float*)(wsb(p) + L.mask_off);
+      z.planes = 1;
+      z.dz = (__nv_bfloat16*)(wsb(p) + lin.dzp_off);
+      z.dz_npos = lin.dzp_npos;
+      z.dz_guard = lin.dzp_guard;
+      z.H = lin.H;
+      z.W = lin.W;
       if ((rc = launch_dz_prepare(z, sm, st))) return rc;
       DgradArgs d;
       memset(&d, 0, sizeof(d));
       d.dense = 1;
-      d.dz = tmp;
+      d.dz = z.dz;
+      d.dz_npos = lin.dzp_npos;
+      d.dz_guard = lin.dzp_guard;
       d.Kdz = 16;
       d.wpk = wsb(p) + L.wpk_bwd;
       d.act = act_of(p, L.lvl_in);
@@ -411,7 +420,9 @@ extern "C" int rl_backward(rl_plan* h, const float* params, const float* x, floa
       w.Ca = L.cin;
       w.transform = 1;
       w.bn = d.bn;
-      w.Bm = tmp;
+      w.Bm = z.dz;
+      w.dz_npos = lin.dzp_npos;
+      w.dz_guard = lin.dzp_guard;
       w.ldb = 16;
       w.N = 144;
       w.part_n0[0] = 0;

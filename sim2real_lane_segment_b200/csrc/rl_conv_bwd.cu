@@ -7,6 +7,8 @@
 // (TMEM lane = thread) is a *channel*: the per-channel BatchNorm-backward sums Σg and Σg·x̂ are then plain
 // per-thread accumulations, and every thread streams one channel column of the NHWC arenas.
 // The 3x3 taps are 9 row-shifted views of one 16-channel halo tile in shared memory (start-address offsets).
+#include <stdlib.h>
+
 #include "rl_common.cuh"
 #include "rl_dev.cuh"
 #include "rl_kernels.h"
@@ -75,13 +77,25 @@ struct DgradPre {
   uint4 x0, x1, d0, d1;
 };
 __device__ __forceinline__ void dgrad_prefetch(DgradPre& p, const __nv_bfloat16* xrow, const __nv_bfloat16* drow, int c0,
-                                               int nvalid, bool rmw) {
+                                               int nvalid, bool rmw, int variant = 3) {
   if (xrow != nullptr && c0 < nvalid) {
-    p.x0 = ldg128(xrow + c0);
-    p.x1 = ldg128(xrow + c0 + 8);
+    if (variant & 2) {
+      const u32x8 xv = (variant & 1) ? ldg256_nc(xrow + c0) : ldg256_nc_nohint(xrow + c0);
+      p.x0 = xv.lo;
+      p.x1 = xv.hi;
+    } else {
+      p.x0 = ldg128(xrow + c0);
+      p.x1 = ldg128(xrow + c0 + 8);
+    }
     if (rmw) {
-      p.d0 = *reinterpret_cast<const uint4*>(drow + c0);
-      p.d1 = *reinterpret_cast<const uint4*>(drow + c0 + 8);
+      if (variant & 2) {
+        const u32x8 dv = (variant & 1) ? ld256(drow + c0) : ld256_nohint(drow + c0);
+        p.d0 = dv.lo;
+        p.d1 = dv.hi;
+      } else {
+        p.d0 = *reinterpret_cast<const uint4*>(drow + c0);
+        p.d1 = *reinterpret_cast<const uint4*>(drow + c0 + 8);
+      }
     } else {
       p.d0 = p.d1 = make_uint4(0, 0, 0, 0);
     }
@@ -100,7 +114,7 @@ __device__ __forceinline__ void dgrad_epilogue(uint32_t tmem_acc, int warp, int 
       float g[16];
       tmem_ld16(tmem_acc + ((uint32_t)(warp * 32) << 16) + c0, g);
       const DgradPre cur = pre[gi & 1];
-      if (gi + 2 < 8) dgrad_prefetch(pre[gi & 1], xrow, drow, c0 + 32, nvalid, (cbase + c0 + 32) >= a.rmw_from);
+      if (gi + 2 < 8) dgrad_prefetch(pre[gi & 1], xrow, drow, c0 + 32, nvalid, (cbase + c0 + 32) >= a.rmw_from, a.variant);
       float gs[16], gx[16];
       if (xrow != nullptr) {
         float x[16], d[16];
@@ -116,8 +130,12 @@ __device__ __forceinline__ void dgrad_epilogue(uint32_t tmem_acc, int warp, int 
           gx[i] = gv * (x[i] - kk.w);
           d[i] = fmaf(kk.z, gv, d[i]);
         }
-        *reinterpret_cast<uint4*>(drow + c0) = pack8(d);
-        *reinterpret_cast<uint4*>(drow + c0 + 8) = pack8(d + 8);
+        if (a.variant & 2) {
+          st256(drow + c0, pack8(d), pack8(d + 8));
+        } else {
+          *reinterpret_cast<uint4*>(drow + c0) = pack8(d);
+          *reinterpret_cast<uint4*>(drow + c0 + 8) = pack8(d + 8);
+        }
       } else {
 #pragma unroll
         for (int i = 0; i < 16; ++i) gs[i] = gx[i] = 0.f;
@@ -179,10 +197,11 @@ __global__ void __launch_bounds__(128, 3) dgrad_dense_kernel(DgradArgs a) {
   extern __shared__ __align__(128) uint8_t smem[];
   uint8_t* sW = smem;                 // W of one channel block: [18][128][8] bf16 = 36864 B   (B operand, rows = channels)
   uint8_t* sDz = smem + 36864;        // halo tile [2][kDzRows][8] bf16 = 14848 B              (A operand, rows = pixels)
-  DgradConsts* kc = reinterpret_cast<DgradConsts*>(smem + 36864 + 2 * kDzRows * 16);
+  constexpr int kDzBytes = 2 * kDzRows * 16;
+  DgradConsts* kc = reinterpret_cast<DgradConsts*>(smem + 36864 + kDzBytes);
   float* s_rstd = reinterpret_cast<float*>(kc + 1);
   float* s_sum = s_rstd + 128;
-  __shared__ uint64_t bar_w, bar_mma;
+  __shared__ uint64_t bar_w, bar_mma, bar_dz[2];
   __shared__ uint32_t tmem_base_s;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
@@ -195,10 +214,13 @@ __global__ void __launch_bounds__(128, 3) dgrad_dense_kernel(DgradArgs a) {
   const int t_begin = SW, t_end = (V1 - V0 + 1) * SW;  // rows V0..V1-1 of the region (region row 0 is V0-1)
   const int ntiles = (t_end - t_begin + 127) / 128;
   const int nmb = (a.Cin + 127) / 128;
+  const int nrows = 128 + 2 * SW + 2;
 
   if (tid == 0) {
     mbar_init(&bar_w, 1);
     mbar_init(&bar_mma, 1);
+    mbar_init(&bar_dz[0], 1);
+    mbar_init(&bar_dz[1], 1);
     fence_mbar_init();
   }
   if (warp == 0) tmem_alloc(&tmem_base_s, 128);
@@ -208,13 +230,42 @@ __global__ void __launch_bounds__(128, 3) dgrad_dense_kernel(DgradArgs a) {
   const uint32_t tmem = tmem_base_s;
   uint32_t n_w = 0, n_mma = 0;
 
+  // Halo tile of dz for the tile starting at region position t0: smem row rr <-> region position t0 - SW - 1 + rr.
+  // dz lives in global memory as two zero-padded planes whose position index is linear in (virtual row, column+1), so
+  // for un-stripped levels the whole tile is one contiguous range per plane: a plain coalesced copy, no bounds checks
+  // (pads and guards supply the zeros).
+  const long PW = a.W + 2;  // padded row pitch (positions)
+  const uint4* plane0 = reinterpret_cast<const uint4*>(a.dz);
+  const uint4* plane1 = plane0 + a.dz_npos;
+  auto load_dz = [&](int tile) {
+    const int t0 = t_begin + tile * 128;
+    uint4* d0 = reinterpret_cast<uint4*>(sDz);
+    uint4* d1 = d0 + kDzRows;
+    if (SW == PW) {
+      const long pos0 = a.dz_guard + (long)(V0 - 1) * PW + (t0 - SW - 1);
+      for (int rr = tid; rr < nrows; rr += 128) {
+        d0[rr] = __ldg(plane0 + pos0 + rr);
+        d1[rr] = __ldg(plane1 + pos0 + rr);
+      }
+    } else {
+      for (int rr = tid; rr < nrows; rr += 128) {
+        const int t = t0 - SW - 1 + rr;
+        const int rrow = (t >= 0) ? t / SW : -1;
+        const int cc = t - rrow * SW;
+        const long pos = a.dz_guard + (long)(V0 - 1 + rrow) * PW + (x0 - 1 + cc) + 1;
+        d0[rr] = __ldg(plane0 + pos);
+        d1[rr] = __ldg(plane1 + pos);
+      }
+    }
+  };
+
   for (int mb = 0; mb < nmb; ++mb) {
     const int nvalid = min(128, a.Cin - mb * 128);
     const uint32_t idesc = umma_idesc_bf16((uint32_t)nvalid, 0, 0);
     float S1[8], S2[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) S1[i] = S2[i] = 0.f;
-    __syncthreads();  // every MMA of the previous block has been waited for: sW / constants may be overwritten
+    __syncthreads();  // every MMA of the previous block has been waited for: sW / constants / dz buffers may be overwritten
     dgrad_consts_init(kc, s_rstd, a, mb);
     if (tid == 0) {
       mbar_arrive_expect_tx(&bar_w, 36864);
@@ -235,30 +286,11 @@ __global__ void __launch_bounds__(128, 3) dgrad_dense_kernel(DgradArgs a) {
       const __nv_bfloat16* xrow = P >= 0 ? a.act + (size_t)P * a.Ct + mb * 128 : nullptr;
       __nv_bfloat16* drow = P >= 0 ? a.dact + (size_t)P * a.Ct + mb * 128 : nullptr;
       DgradPre pre[2];
-      dgrad_prefetch(pre[0], xrow, drow, 0, nvalid, (mb * 128) >= a.rmw_from);
-      dgrad_prefetch(pre[1], xrow, drow, 16, nvalid, (mb * 128 + 16) >= a.rmw_from);
-      // ---- halo tile of dz: smem row rr <-> region position t0 - SW - 1 + rr
-      const int nrows = 128 + 2 * SW + 2;
-      for (int rr = tid; rr < nrows; rr += 128) {
-        const int t = t0 - SW - 1 + rr;
-        uint4 v0 = make_uint4(0, 0, 0, 0), v1 = v0;
-        if (t >= 0) {
-          const int rrow = t / SW, cc = t - rrow * SW;
-          const int vr = V0 - 1 + rrow, xc = x0 - 1 + cc;
-          if (vr >= 0 && vr < vrows_total && xc >= 0 && xc < a.W) {
-            const int img = vr / VH, ri = vr - img * VH;
-            if (ri < a.H) {
-              const __nv_bfloat16* src = a.dz + (((size_t)img * a.H + ri) * a.W + xc) * 16;
-              v0 = ldg128(src);
-              v1 = ldg128(src + 8);
-            }
-          }
-        }
-        *reinterpret_cast<uint4*>(sDz + (size_t)rr * 16) = v0;
-        *reinterpret_cast<uint4*>(sDz + ((size_t)kDzRows + rr) * 16) = v1;
-      }
+      dgrad_prefetch(pre[0], xrow, drow, 0, nvalid, (mb * 128) >= a.rmw_from, a.variant);
+      dgrad_prefetch(pre[1], xrow, drow, 16, nvalid, (mb * 128 + 16) >= a.rmw_from, a.variant);
+      load_dz(tile);           // previous tile's MMAs were waited for before its epilogue: the buffer is free
       fence_proxy_async();
-      __syncthreads();
+      __syncthreads();         // also: every thread is past the epilogue of tile-1 -> TMEM reusable
       if (tid == 0) {
         if (tile == 0) mbar_wait(&bar_w, n_w & 1);
         tc_fence_after();
@@ -276,7 +308,6 @@ __global__ void __launch_bounds__(128, 3) dgrad_dense_kernel(DgradArgs a) {
       tc_fence_after();
       dgrad_epilogue(tmem, warp, lane, xrow, drow, mb * 128, nvalid, kc, a, S1, S2, pre);
       tc_fence_before();
-      __syncthreads();
     }
     if (ntiles == 0 && tid == 0) mbar_wait(&bar_w, n_w & 1);
     ++n_w;
@@ -339,8 +370,8 @@ __global__ void __launch_bounds__(128, 3) dgrad_td_kernel(DgradArgs a) {
       const __nv_bfloat16* xrow = P >= 0 ? a.act + (size_t)P * a.Ct + mb * 128 : nullptr;
       __nv_bfloat16* drow = P >= 0 ? a.dact + (size_t)P * a.Ct + mb * 128 : nullptr;
       DgradPre pre[2];
-      dgrad_prefetch(pre[0], xrow, drow, 0, nvalid, (mb * 128) >= a.rmw_from);
-      dgrad_prefetch(pre[1], xrow, drow, 16, nvalid, (mb * 128 + 16) >= a.rmw_from);
+      dgrad_prefetch(pre[0], xrow, drow, 0, nvalid, (mb * 128) >= a.rmw_from, a.variant);
+      dgrad_prefetch(pre[1], xrow, drow, 16, nvalid, (mb * 128 + 16) >= a.rmw_from, a.variant);
       ld.load(rowptr, min(8, a.Kdz / 8));
       for (int kc = 0; kc < nkc; ++kc) {
         const int ck = min(64, a.Kdz - kc * 64);
@@ -389,7 +420,14 @@ __global__ void __launch_bounds__(128, 3) dgrad_td_kernel(DgradArgs a) {
   if (warp == 0) tmem_dealloc(tmem, 128);
 }
 
-int launch_dgrad(const DgradArgs& a, int grid, cudaStream_t st) {
+int launch_dgrad(const DgradArgs& a_in, int grid, cudaStream_t st) {
+  static int variant = -1;
+  if (variant < 0) {
+    const char* e = getenv("RL_VARIANT");
+    variant = e ? atoi(e) : 3;
+  }
+  DgradArgs a = a_in;
+  a.variant = variant;
   static bool configured = false;
   if (!configured) {
     RL_CUDA(cudaFuncSetAttribute(dgrad_dense_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
@@ -435,13 +473,14 @@ __global__ void __launch_bounds__(kWgThreads, 2) wgrad_kernel(WgradArgs a) {
   uint8_t* stage_base = smem + 1024;
   const int stageB = np * 128;  // np/8 chunks x 64 rows x 16 B
   const int kStageBytes = 16384 + stageB;
-  __shared__ uint64_t bar_done[2];
+  __shared__ uint64_t bar_done[3];
   __shared__ uint32_t tmem_base_s;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   if (tid == 0) {
     mbar_init(&bar_done[0], 1);
     mbar_init(&bar_done[1], 1);
+    mbar_init(&bar_done[2], 1);
     fence_mbar_init();
   }
   if (warp == 0) tmem_alloc(&tmem_base_s, 256);
@@ -470,85 +509,95 @@ __global__ void __launch_bounds__(kWgThreads, 2) wgrad_kernel(WgradArgs a) {
   const int a_row = warp * 8 + (lane & 7), a_j0 = lane >> 3;
   // B tile: row = tid & 63, column chunks j = (tid >> 6) + 4q
   const int b_row = tid & 63, b_j0 = tid >> 6;
-  uint4 av[4], bv[8];
-  bool a_valid = false;
-
-  auto load_chunk = [&](int kc) {
-    const long Pc = P0 + (long)kc * 64;
-    {
-      const long P = Pc + a_row;
-      a_valid = P < P1;
-      const __nv_bfloat16* src = a.A + (size_t)P * a.lda + a.a_off + mb * 128;
-#pragma unroll
-      for (int h = 0; h < 4; ++h) {
-        const int j = a_j0 + 4 * h;
-        av[h] = (a_valid && j < a_nchunk) ? ldg128(src + j * 8) : make_uint4(0, 0, 0, 0);
-      }
-    }
-    const long P = Pc + b_row;
-    if (a.kind == WG_DENSE) {
-      int y = 0, x = 0;
-      long b = 0;
-      if (P < P1) {
-        b = P / HW;
-        const int hw = (int)(P - b * HW);
-        y = hw / a.W;
-        x = hw - y * a.W;
-      }
-#pragma unroll
-      for (int q = 0; q < 5; ++q) {
-        const int j = b_j0 + 4 * q;
-        uint4 v = make_uint4(0, 0, 0, 0);
-        if (j < 18 && P < P1) {
-          const int tap = j >> 1, half = j & 1;
-          const int qy = y - (tap / 3 - 1), qx = x - (tap % 3 - 1);
-          if (qy >= 0 && qy < a.H && qx >= 0 && qx < a.W) v = ldg128(a.Bm + ((b * a.H + qy) * a.W + qx) * 16 + half * 8);
-        }
-        bv[q] = v;
-      }
-    } else {
-#pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        const int j = b_j0 + 4 * q;
-        bv[q] = (j < nj && P < P1) ? ldg128(a.Bm + (size_t)P * a.ldb + n0 + j * 8) : make_uint4(0, 0, 0, 0);
-      }
-    }
+  struct ARegs {
+    uint4 v[4];
+    bool valid;
   };
 
-  if (nchunks > 0) load_chunk(0);
-  for (int kc = 0; kc < nchunks; ++kc) {
-    const uint32_t s = kc & 1, u = kc >> 1;
+  // 3-stage pipeline, prefetch distance 2 chunks: A through registers (it needs the BN+ReLU transform),
+  // B by cp.async straight into its operand layout
+  auto load_a = [&](int kc, ARegs& r) {
+    const long P = P0 + (long)kc * 64 + a_row;
+    r.valid = kc < nchunks && P < P1;
+    const __nv_bfloat16* src = a.A + (size_t)(r.valid ? P : P0) * a.lda + a.a_off + mb * 128;
+#pragma unroll
+    for (int h = 0; h < 4; ++h) {
+      const int j = a_j0 + 4 * h;
+      r.v[h] = (r.valid && j < a_nchunk) ? ldg128(src + j * 8) : make_uint4(0, 0, 0, 0);
+    }
+  };
+  auto issue_b = [&](int kc, uint8_t* sB) {
+    if (kc < nchunks) {
+      const long P = P0 + (long)kc * 64 + b_row;
+      const bool pv = P < P1;
+      if (a.kind == WG_DENSE) {
+        // zero-padded planes: the tap at (dy,dx) of pixel (b,y,x) sits at position pos - dy*(W+2) - dx, always in range
+        long pos = a.dz_guard;
+        if (pv) {
+          const long b = P / HW;
+          const int hw = (int)(P - b * HW), y = hw / a.W, x = hw - y * a.W;
+          pos += (b * (a.H + 1) + y) * (a.W + 2) + x + 1;
+        }
+#pragma unroll
+        for (int q = 0; q < 5; ++q) {
+          const int j = b_j0 + 4 * q;
+          if (j < 18) {
+            const int tap = j >> 1, half = j & 1;
+            const long tp = pos - (long)(tap / 3 - 1) * (a.W + 2) - (tap % 3 - 1);
+            cp_async16(sB + ((size_t)j * 64 + b_row) * 16, a.Bm + ((long)half * a.dz_npos + tp) * 8, pv);
+          }
+        }
+      } else {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const int j = b_j0 + 4 * q;
+          if (j < nj) cp_async16(sB + ((size_t)j * 64 + b_row) * 16, pv ? a.Bm + (size_t)P * a.ldb + n0 + j * 8 : a.Bm, pv);
+        }
+      }
+    }
+    cp_async_commit();  // always: keeps the group count uniform
+  };
+  auto step = [&](int k, ARegs& r) {
+    const int s = k % 3;
     uint8_t* sA = stage_base + s * kStageBytes;
-    uint8_t* sB = sA + 16384;
-    if (u > 0) mbar_wait(&bar_done[s], (u - 1) & 1);
 #pragma unroll
     for (int h = 0; h < 4; ++h) {
       const int j = a_j0 + 4 * h;
       if (j < a_nchunk) {
-        uint4 o = av[h];
-        if (a.transform && a_valid) o = bn_relu8(o, s_s + j * 8, s_t + j * 8);
+        uint4 o = r.v[h];
+        if (a.transform && r.valid) o = bn_relu8(o, s_s + j * 8, s_t + j * 8);
         *reinterpret_cast<uint4*>(sA + ((size_t)j * 64 + a_row) * 16) = o;
       }
     }
-#pragma unroll
-    for (int q = 0; q < 8; ++q) {
-      const int j = b_j0 + 4 * q;
-      if (j < nj && (a.kind != WG_DENSE || q < 5)) *reinterpret_cast<uint4*>(sB + ((size_t)j * 64 + b_row) * 16) = bv[q];
-    }
-    if (kc + 1 < nchunks) load_chunk(kc + 1);  // in flight while this chunk's MMAs run
+    // stage (k+2)%3 == (k-1)%3 is recycled for chunk k+2 once the MMAs of chunk k-1 have retired
+    if (k >= 1) mbar_wait(&bar_done[(k - 1) % 3], ((k - 1) / 3) & 1);
+    load_a(k + 2, r);
+    issue_b(k + 2, stage_base + ((k + 2) % 3) * kStageBytes + 16384);
+    cp_async_wait<2>();  // B(k) has landed (B(k+1), B(k+2) may still be in flight)
     fence_proxy_async();
     __syncthreads();
     if (tid == 0) {
       tc_fence_after();
-      const uint32_t aa = smem_u32(sA), ba = smem_u32(sB);
+      const uint32_t aa = smem_u32(sA), ba = smem_u32(sA + 16384);
 #pragma unroll
       for (int kk = 0; kk < 4; ++kk)
-        umma_ss(tmem, desc_mnmajor(aa + kk * 256, 64), desc_mnmajor(ba + kk * 256, 64), idesc, (kc | kk) != 0);
+        umma_ss(tmem, desc_mnmajor(aa + kk * 256, 64), desc_mnmajor(ba + kk * 256, 64), idesc, (k | kk) != 0);
       umma_commit(&bar_done[s]);
     }
+  };
+
+  ARegs r0, r1;
+  load_a(0, r0);
+  issue_b(0, stage_base + 16384);
+  load_a(1, r1);
+  issue_b(1, stage_base + kStageBytes + 16384);
+  for (int kc = 0; kc < nchunks; kc += 2) {
+    step(kc, r0);
+    if (kc + 1 < nchunks) step(kc + 1, r1);
   }
+  cp_async_wait<0>();
   if (nchunks > 0 && warp < 4) {
-    const uint32_t s = (nchunks - 1) & 1, u = (nchunks - 1) >> 1;
+    const uint32_t s = (nchunks - 1) % 3, u = (nchunks - 1) / 3;
     mbar_wait(&bar_done[s], u & 1);
     tc_fence_after();
     const int c = mb * 128 + tid;
@@ -572,13 +621,13 @@ __global__ void __launch_bounds__(kWgThreads, 2) wgrad_kernel(WgradArgs a) {
 int launch_wgrad(const WgradArgs& a, int nruns, int nmb, int nparts, cudaStream_t st) {
   static bool configured = false;
   if (!configured) {
-    RL_CUDA(cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
+    RL_CUDA(cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
     configured = true;
   }
   int npmax = 0;
   for (int i = 0; i < nparts; ++i) npmax = a.part_np[i] > npmax ? a.part_np[i] : npmax;
-  size_t smem = 1024 + 2 * (16384 + (size_t)npmax * 128);
-  if (smem > 110 * 1024) return rl_fail(RL_ERR_SHAPE, "wgrad: smem %zu too large", smem);
+  size_t smem = 1024 + 3 * (16384 + (size_t)npmax * 128);
+  if (smem > 160 * 1024) return rl_fail(RL_ERR_SHAPE, "wgrad: smem %zu too large", smem);
   { ProfScope _ps(KC_WGRAD, st);
   wgrad_kernel<<<dim3(nruns, nmb, nparts), kWgThreads, smem, st>>>(a); }
   RL_CUDA(cudaGetLastError());

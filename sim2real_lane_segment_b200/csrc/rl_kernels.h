@@ -47,7 +47,8 @@ int launch_gemm_px(const GemmPxArgs& a, int grid_x, int nparts, cudaStream_t st)
 struct DgradArgs {
   // G^T[c, p] = Σ_k W^T[c, k] · dz[p(-tap shift), k]; epilogue: ReLU mask, BN-backward sums, accumulate into dX
   int dense;                 // 1: 3x3 growth-16 layer (9 taps, halo tile); 0: 1x1 TransitionDown (K = Kdz, streamed)
-  const __nv_bfloat16* dz;   // dense: [px][16]; td: [px][Kdz]
+  const __nv_bfloat16* dz;   // td: [px][Kdz]; dense: zero-padded planes (see Level::dzp_off)
+  long dz_npos, dz_guard;    // dense: positions per plane, front guard
   int Kdz;
   const uint8_t* wpk;        // dense: per M-block [18][128][8]; td: per M-block, per K chunk [8][128][8]
   const __nv_bfloat16* act;  // level arena
@@ -60,6 +61,7 @@ struct DgradArgs {
   double* acc;               // level accumulators: A at [c], B at [Ct+c]
   int vrows_per_cta, nstrips, strip_w;  // dense work decomposition (virtual rows: H+1 per image)
   long ntiles;                           // td: 128-pixel tiles
+  int variant;                           // tuning switches (env RL_VARIANT): bit0 L2::128B hint, bit1 256-bit accesses
 };
 int launch_dgrad(const DgradArgs& a, int grid, cudaStream_t st);
 
@@ -71,7 +73,8 @@ struct WgradArgs {
   int lda, a_off, Ca;        // Ca = valid A channels
   int transform;
   BnSrc bn;
-  const __nv_bfloat16* Bm;   // dense: dz16 [px][16]; else row-major [px][ldb]
+  const __nv_bfloat16* Bm;   // dense: zero-padded dz16 planes; else row-major [px][ldb]
+  long dz_npos, dz_guard;
   int ldb;
   int N;                     // total B columns (dense: 144)
   int part_n0[3], part_np[3];
@@ -131,6 +134,8 @@ struct DzArgs {
   const float* mask;          // [B][nch] or null
   int HW_out;                 // pixels per image of the output arena
   __nv_bfloat16* dz;          // result
+  int planes;                 // kind 0, nch = 16: write the zero-padded two-plane layout (H, W = level geometry)
+  long dz_npos, dz_guard;
   float* g_bias;              // Σ dz per channel -> conv bias gradient (fp32 atomics)
   // TD: output arena is the pooled level; dz is written at the input resolution [px_in][nch]
   const uint8_t* amax;

@@ -558,8 +558,15 @@ __global__ void __launch_bounds__(256) dz_prepare_kernel(DzArgs a) {
     if (pl < ppb)
       for (long P = (long)blockIdx.x * ppb + pl; P < a.npx_out; P += (long)gridDim.x * ppb) {
         float o[8];
-        corrected(P, j, (int)(P / a.HW_out), o);
-        *reinterpret_cast<uint4*>(a.dz + P * a.nch + j * 8) = pack8(o);
+        const int img = (int)(P / a.HW_out);
+        corrected(P, j, img, o);
+        if (a.planes) {
+          const int hw = (int)(P - (long)img * a.HW_out), y = hw / a.W, x = hw - y * a.W;
+          const long pos = a.dz_guard + ((long)img * (a.H + 1) + y) * (a.W + 2) + x + 1;
+          *reinterpret_cast<uint4*>(a.dz + ((long)j * a.dz_npos + pos) * 8) = pack8(o);
+        } else {
+          *reinterpret_cast<uint4*>(a.dz + P * a.nch + j * 8) = pack8(o);
+        }
 #pragma unroll
         for (int k = 0; k < 8; ++k) bsum[k] += o[k];
       }

@@ -187,6 +187,14 @@ int build_plan(Plan* p, int B, int H, int W, int num_cls, int training) {
   p->tmp_bytes = tmp;
   p->tmp_off = carve(tmp);
   p->xcol_off = training ? carve((size_t)p->lv[0].px * 32 * 2) : 0;
+  p->dzp_off_all = ws;
+  for (int l = 0; l < kLevels; ++l) {
+    Level& L = p->lv[l];
+    L.dzp_guard = L.W + 3;
+    L.dzp_npos = L.dzp_guard + (long)B * (L.H + 1) * (L.W + 2) + 128 + 2 * (L.W + 2) + 8;
+    L.dzp_off = training ? carve((size_t)L.dzp_npos * 32) : 0;
+  }
+  p->dzp_bytes = ws - p->dzp_off_all;
   p->dl_bytes = training ? (size_t)p->lv[0].px * 16 * 2 : 0;
   p->dl_off = carve(p->dl_bytes);
   p->ws_bytes = ws;

@@ -37,6 +37,10 @@ struct Level {
   size_t act_off, dact_off;      // bytes into workspace
   size_t stats_off, acc_off;     // bytes into workspace: double[2][Ct] each
   long px;                       // B*H*W
+  // zero-padded planes of the 16-channel output gradient of a DenseLayer (training):
+  // two planes [npos][8] bf16; position(b,y,x) = guard + (b*(H+1)+y)*(W+2) + x+1; pads are never written
+  size_t dzp_off;
+  long dzp_npos, dzp_guard;
 };
 
 struct Layer {
@@ -76,6 +80,7 @@ struct Plan {
   size_t acc_off_all, acc_bytes;      // A_c, B_c for all levels (zeroed every backward)
   size_t tmp_off, tmp_bytes;          // shared scratch: dz buffers, convT column matrices
   size_t dl_off, dl_bytes;            // head: d(logits)/n as bf16 [px0][16]
+  size_t dzp_off_all, dzp_bytes;      // all levels' padded dz16 planes (zeroed once at bind)
   size_t scal_off;                    // small scalars: hist[8] int, loss sums, counters (256 B)
   size_t bntab_off;                   // device copy of the per-BN table for rl_bn_running_update
   size_t packtab_off;                 // device copy of the weight-packing table

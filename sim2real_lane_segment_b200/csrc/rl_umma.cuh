@@ -64,6 +64,16 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint3
                "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
 }
+// Ampere-style 16-byte async copy global -> shared (LDGSTS); !valid zero-fills the destination (src-size 0)
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, bool valid) {
+  const uint32_t sz = valid ? 16u : 0u;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
 // generic-proxy smem writes → visible to the async proxy (tcgen05.mma / TMA reads of smem)
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
@@ -158,6 +168,49 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
   for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// ----------------------------------------------------------------------------------------------
+// 32-byte (one full sector) global accesses: LDG.E.ENL2.256 / STG.E.ENL2.256 on sm_100.  The loads carry an
+// L2::128B prefetch hint so a DRAM access always fetches whole 128-byte lines of the NHWC rows we stream.
+// ----------------------------------------------------------------------------------------------
+struct __align__(32) u32x8 {
+  uint4 lo, hi;
+};
+__device__ __forceinline__ u32x8 ldg256_nc(const void* p) {
+  u32x8 r;
+  asm volatile("ld.global.nc.L2::128B.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r.lo.x), "=r"(r.lo.y), "=r"(r.lo.z), "=r"(r.lo.w), "=r"(r.hi.x), "=r"(r.hi.y), "=r"(r.hi.z), "=r"(r.hi.w)
+               : "l"(p));
+  return r;
+}
+__device__ __forceinline__ u32x8 ld256(const void* p) {
+  u32x8 r;
+  asm volatile("ld.global.L2::128B.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r.lo.x), "=r"(r.lo.y), "=r"(r.lo.z), "=r"(r.lo.w), "=r"(r.hi.x), "=r"(r.hi.y), "=r"(r.hi.z), "=r"(r.hi.w)
+               : "l"(p)
+               : "memory");
+  return r;
+}
+__device__ __forceinline__ u32x8 ldg256_nc_nohint(const void* p) {
+  u32x8 r;
+  asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r.lo.x), "=r"(r.lo.y), "=r"(r.lo.z), "=r"(r.lo.w), "=r"(r.hi.x), "=r"(r.hi.y), "=r"(r.hi.z), "=r"(r.hi.w)
+               : "l"(p));
+  return r;
+}
+__device__ __forceinline__ u32x8 ld256_nohint(const void* p) {
+  u32x8 r;
+  asm volatile("ld.global.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r.lo.x), "=r"(r.lo.y), "=r"(r.lo.z), "=r"(r.lo.w), "=r"(r.hi.x), "=r"(r.hi.y), "=r"(r.hi.z), "=r"(r.hi.w)
+               : "l"(p)
+               : "memory");
+  return r;
+}
+__device__ __forceinline__ void st256(void* p, const uint4& lo, const uint4& hi) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(lo.x), "r"(lo.y), "r"(lo.z), "r"(lo.w),
+               "r"(hi.x), "r"(hi.y), "r"(hi.z), "r"(hi.w)
+               : "memory");
 }
 
 // ----------------------------------------------------------------------------------------------
