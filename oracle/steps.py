@@ -111,6 +111,26 @@ def summarize_evaluation_results(outputs):
             "dice": sum(o["dice"] for o in outputs) / tw, "iou": sum(o["iou"] for o in outputs) / tw * 100.0}
 
 
+class _GradReverse(torch.autograd.Function):
+    """models/FCDenseNet/tiramisu.py:7-18: identity forward, negated gradient"""
+
+    @staticmethod
+    def forward(ctx, x):
+        return x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g.neg()
+
+
+def mme_unlabelled_loss(sd, x_unl, cfg=net.FCDENSENET67, drop_masks=None):
+    """MMETrainingModule.training_step, optimizer_idx 0 (MMETrainingModule.py:28-32): entropy maximisation on the
+    unlabelled stream with the gradient reversed between extractor and classifier"""
+    feats, new_running = net.feature_extractor(sd, x_unl, cfg, train=True, drop_masks=drop_masks, update_running=True)
+    probs = net.classifier(sd, _GradReverse.apply(feats))
+    return adentropy(probs, lamda=0.1), new_running
+
+
 def adentropy(probs, lamda=1.0):
     return lamda * torch.mean(torch.sum(probs * torch.log(probs + 1e-5), 1))
 

@@ -70,6 +70,7 @@ __global__ void __launch_bounds__(128, 2) dense_fwd_kernel(DenseFwdArgs a) {
   for (int i = 0; i < 16; ++i) st_sum[i] = st_sq[i] = 0.f;
 
   uint32_t g = 0;  // running chunk counter: stage = g & 1, use index = g >> 1
+  bool w_issued = false;  // weights of chunk g already requested by thread 0 during the previous iteration
   int emit_pos = 0;
   TileLoader<128> ld;
   const __nv_bfloat16* rowptr[4];
@@ -107,7 +108,7 @@ __global__ void __launch_bounds__(128, 2) dense_fwd_kernel(DenseFwdArgs a) {
       uint8_t* sA = stage_base + s * kStageBytes;
       uint8_t* sW = sA + 16384;
       if (u > 0) mbar_wait(&bar_done[s], (u - 1) & 1);  // MMAs that read this stage have retired
-      if (tid == 0) {
+      if (tid == 0 && !w_issued) {  // (normally issued one iteration ahead, see below)
         const uint32_t wbytes = (uint32_t)(ck / 8) * 144 * 16;
         mbar_arrive_expect_tx(&bar_full[s], wbytes);
         bulk_g2s(sW, a.wpk + (size_t)kc * 18432, wbytes, &bar_full[s]);
@@ -129,7 +130,20 @@ __global__ void __launch_bounds__(128, 2) dense_fwd_kernel(DenseFwdArgs a) {
           umma_ss(tmem, desc_kmajor(aaddr + kk * 2 * 16 * 128, 128), desc_kmajor(waddr + kk * 2 * 16 * 144, 144), idesc,
                   (kc | kk) != 0);
         umma_commit(&bar_done[s]);
+        // weights of the NEXT chunk (this tile's kc+1, or the next tile's chunk 0) go out now, one iteration ahead of
+        // their use, into the other stage as soon as the MMAs that last read it (issued one iteration ago) retire
+        const bool more = (kc + 1 < nkc) || (tile + 1 < ntiles);
+        if (more) {
+          const int nk = (kc + 1 < nkc) ? kc + 1 : 0;
+          const int nck = min(64, a.Cin - nk * 64);
+          const uint32_t ns = (g + 1) & 1, nu = (g + 1) >> 1;
+          if (nu > 0) mbar_wait(&bar_done[ns], (nu - 1) & 1);
+          const uint32_t wbytes = (uint32_t)(nck / 8) * 144 * 16;
+          mbar_arrive_expect_tx(&bar_full[ns], wbytes);
+          bulk_g2s(stage_base + ns * kStageBytes + 16384, a.wpk + (size_t)nk * 18432, wbytes, &bar_full[ns]);
+        }
       }
+      w_issued = true;
       ++g;
     }
     // ---------------- accumulator ready: the commit of the last chunk covers every MMA of this tile
@@ -277,6 +291,7 @@ __global__ void __launch_bounds__(128, 2) gemm_px_kernel(GemmPxArgs a) {
   const uint32_t idesc = umma_idesc_bf16((uint32_t)np, 0, 0);
 
   uint32_t g = 0;
+  bool w_issued = false;
   TileLoader<128> ld;
   const __nv_bfloat16* rowptr[4];
 
@@ -311,7 +326,7 @@ __global__ void __launch_bounds__(128, 2) gemm_px_kernel(GemmPxArgs a) {
       uint8_t* sA = stage_base + s * kStageBytes;
       uint8_t* sW = sA + 16384;
       if (u > 0) mbar_wait(&bar_done[s], (u - 1) & 1);
-      if (tid == 0) {
+      if (tid == 0 && !w_issued) {
         const uint32_t wbytes = (uint32_t)(ck / 8) * np * 16;
         mbar_arrive_expect_tx(&bar_full[s], wbytes);
         bulk_g2s(sW, wpart + (size_t)kc * stageB, wbytes, &bar_full[s]);
@@ -333,7 +348,18 @@ __global__ void __launch_bounds__(128, 2) gemm_px_kernel(GemmPxArgs a) {
           umma_ss(tmem, desc_kmajor(aaddr + kk * 2 * 16 * 128, 128), desc_kmajor(waddr + kk * 2 * 16 * np, np), idesc,
                   (kc | kk) != 0);
         umma_commit(&bar_done[s]);
+        const bool more = (kc + 1 < nkc) || (tile + gridDim.x < a.ntiles);
+        if (more) {  // next chunk's weights, one iteration ahead
+          const int nk = (kc + 1 < nkc) ? kc + 1 : 0;
+          const int nck = min(64, a.K - nk * 64);
+          const uint32_t ns = (g + 1) & 1, nu = (g + 1) >> 1;
+          if (nu > 0) mbar_wait(&bar_done[ns], (nu - 1) & 1);
+          const uint32_t wbytes = (uint32_t)(nck / 8) * np * 16;
+          mbar_arrive_expect_tx(&bar_full[ns], wbytes);
+          bulk_g2s(stage_base + ns * kStageBytes + 16384, wpart + (size_t)nk * stageB, wbytes, &bar_full[ns]);
+        }
       }
+      w_issued = true;
       ++g;
     }
     {

@@ -60,50 +60,49 @@ __device__ __forceinline__ uint4 bn_relu8(uint4 v, const float* s8, const float*
 }
 
 // ------------------------------------------------------------------------------------------------
-// Tile loader, 128 threads: ROWS rows x up to 64 channels (8 chunks) of an NHWC arena -> chunk layout
-// T[j][row][8] with ROWS rows.  Lane mapping: 8 consecutive lanes cover 8 consecutive rows of one chunk
-// (conflict-free 128 B shared stores); the 4 lane groups cover 4 consecutive chunks (64 B per row per
-// request: whole 32 B sectors).  ROWS = 128: 4 row groups x 2 chunk halves; ROWS = 64: 2 x 4.
+// Tile loader, 128 threads: 128 rows x up to 64 channels (8 chunks) of an NHWC arena -> chunk layout T[j][row][8].
+// Lane mapping: lane = (r8 = lane & 7, q = lane >> 3).  A lane moves 32 contiguous bytes (chunks 2q, 2q+1) of row
+// 32*warp + 8*i + r8 with one 256-bit load, so 4 lanes cover a whole 128-byte line of a row and 8 consecutive lanes
+// store 8 consecutive rows of one chunk plane (conflict-free 128 B shared stores).  nchunk is always even here
+// (channel counts are multiples of 16).
 // ------------------------------------------------------------------------------------------------
 template <int ROWS>
 struct TileLoader {
-  static constexpr int RG = ROWS / 32;       // row groups per thread
-  static constexpr int CH = 8 / RG;          // chunk slots per thread (RG*CH = 8 loads)
-  static constexpr int CSTEP = 4;            // chunk stride between slots
-  uint4 v[8];
+  static_assert(ROWS == 128, "only the 128-row tile is used");
+  u32x8 v[4];
 
   __device__ __forceinline__ static int row_of(int i) {
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    return w * (ROWS / 4) + 8 * i + (lane & 7);
+    return w * 32 + 8 * i + (lane & 7);
   }
-  __device__ __forceinline__ static int chunk_of(int h) { return ((threadIdx.x & 31) >> 3) + CSTEP * h; }
-
   // rowptr[i]: pointer to channel 0 of the chunk window for row row_of(i), or nullptr (row is zero)
   __device__ __forceinline__ void load(const __nv_bfloat16* const* rowptr, int nchunk) {
+    const int q = (threadIdx.x & 31) >> 3;
 #pragma unroll
-    for (int i = 0; i < RG; ++i)
-#pragma unroll
-      for (int h = 0; h < CH; ++h) {
-        const int j = chunk_of(h);
-        uint4 z = make_uint4(0, 0, 0, 0);
-        if (rowptr[i] != nullptr && j < nchunk) z = ldg128(rowptr[i] + j * 8);
-        v[i * CH + h] = z;
+    for (int i = 0; i < 4; ++i) {
+      if (rowptr[i] != nullptr && 2 * q < nchunk) {
+        v[i] = ldg256_nc_nohint(rowptr[i] + 16 * q);
+      } else {
+        v[i].lo = v[i].hi = make_uint4(0, 0, 0, 0);
       }
+    }
   }
-  // st: per-channel s / t arrays (shared memory) already offset to the first channel of this window; null = raw copy
+  // s / t: per-channel arrays (shared memory) already offset to the first channel of this window; null = raw copy
   __device__ __forceinline__ void store(uint8_t* smem, const __nv_bfloat16* const* rowptr, int nchunk, const float* s,
                                         const float* t) const {
+    const int q = (threadIdx.x & 31) >> 3;
+    if (2 * q >= nchunk) return;
 #pragma unroll
-    for (int i = 0; i < RG; ++i)
-#pragma unroll
-      for (int h = 0; h < CH; ++h) {
-        const int j = chunk_of(h);
-        if (j < nchunk) {
-          uint4 o = v[i * CH + h];
-          if (s != nullptr && rowptr[i] != nullptr) o = bn_relu8(o, s + j * 8, t + j * 8);
-          *reinterpret_cast<uint4*>(smem + ((size_t)j * ROWS + row_of(i)) * 16) = o;
-        }
+    for (int i = 0; i < 4; ++i) {
+      uint4 lo = v[i].lo, hi = v[i].hi;
+      if (s != nullptr && rowptr[i] != nullptr) {
+        lo = bn_relu8(lo, s + 16 * q, t + 16 * q);
+        hi = bn_relu8(hi, s + 16 * q + 8, t + 16 * q + 8);
       }
+      const int row = row_of(i);
+      *reinterpret_cast<uint4*>(smem + ((size_t)(2 * q) * ROWS + row) * 16) = lo;
+      *reinterpret_cast<uint4*>(smem + ((size_t)(2 * q + 1) * ROWS + row) * 16) = hi;
+    }
   }
 };
 

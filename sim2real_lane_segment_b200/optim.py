@@ -42,6 +42,7 @@ class _FlatOptimizer(torch.optim.Optimizer):
         self.rt = _runtime_of([p for g in self.param_groups for p in g["params"]])
         self._ranges = None
         self._steps = 0
+        self.grad_scale = 1.0   # multiplies the gradients inside the kernel (1/world_size after a summed all-reduce)
 
     def _ensure(self):
         self.rt.flatten()
@@ -73,7 +74,7 @@ class FusedAdamW(_FlatOptimizer):
         self._steps += 1
         for g, (lo, hi) in zip(self.param_groups, self._ranges):
             engine.adamw_step(self.rt.params[lo:hi], self.rt.grads[lo:hi], self.exp_avg[lo:hi], self.exp_avg_sq[lo:hi],
-                              g["lr"], g["betas"][0], g["betas"][1], g["eps"], g["weight_decay"], self._steps)
+                              g["lr"], g["betas"][0], g["betas"][1], g["eps"], g["weight_decay"], self._steps, self.grad_scale)
         self.rt.mark_weights_changed()
         return loss
 
@@ -95,6 +96,6 @@ class FusedSGD(_FlatOptimizer):
         self._steps += 1
         for g, (lo, hi) in zip(self.param_groups, self._ranges):
             engine.sgd_nesterov_step(self.rt.params[lo:hi], self.rt.grads[lo:hi], self.momentum_buf[lo:hi], g["lr"],
-                                     g["momentum"], g["weight_decay"], first)
+                                     g["momentum"], g["weight_decay"], first, self.grad_scale)
         self.rt.mark_weights_changed()
         return loss
