@@ -18,20 +18,26 @@ def _arena_taps(eng):
     return {l: eng.level_view(l).float().permute(0, 3, 1, 2).cpu() for l in range(6)}
 
 
-def _check_levels(eng, taps, tol):
-    """compare every concat arena with the oracle's intermediate activations; returns worst relative error"""
+def _check_levels(eng, taps, tol, small_sample_tol=None):
+    """compare every concat arena with the oracle's intermediate activations; returns worst relative error.
+    small_sample_tol: looser bound for levels whose BatchNorm batch statistics are taken over < 1000 samples per
+    channel (train mode on the tiny reference fixtures: 2..300 samples, where bf16 rounding is amplified by 1/sigma)"""
     got = _arena_taps(eng)
     worst = 0.0
-    for l in range(5):
-        want = ref_to_phys(taps[f"featureExtractor.denseBlocksUp.{4 - l}"], SKIPS[l])
-        for lo, hi, nm in ((0, SKIPS[l], "skip"), (SKIPS[l], SKIPS[l] + 80, "up"), (SKIPS[l] + 80, SKIPS[l] + 160, "new")):
+    for l in range(6):
+        n = got[l].shape[0] * got[l].shape[2] * got[l].shape[3]
+        t = tol if (small_sample_tol is None or n >= 1000) else small_sample_tol
+        if l < 5:
+            want = ref_to_phys(taps[f"featureExtractor.denseBlocksUp.{4 - l}"], SKIPS[l])
+            parts = ((0, SKIPS[l], "skip"), (SKIPS[l], SKIPS[l] + 80, "up"), (SKIPS[l] + 80, SKIPS[l] + 160, "new"))
+        else:
+            want = taps["featureExtractor.bottleneck.bottleneck"]
+            parts = ((0, 448, "in"), (448, 528, "new"))
+        for lo, hi, nm in parts:
             e = rel_err(got[l][:, lo:hi], want[:, lo:hi])
             worst = max(worst, e)
-            assert e < tol, f"level {l} {nm} channels [{lo},{hi}) rel err {e:.4f}"
-    want = taps["featureExtractor.bottleneck.bottleneck"]
-    e = rel_err(got[5], want)
-    assert e < tol, f"bottleneck rel err {e:.4f}"
-    return max(worst, e)
+            assert e < t, f"level {l} ({n} samples/channel) {nm} channels [{lo},{hi}) rel err {e:.4f}"
+    return worst
 
 
 @pytest.mark.gpu
@@ -86,7 +92,7 @@ def test_train_forward_batch_stats(path):
     torch.cuda.synchronize()
     taps = {}
     net.feature_extractor(sd, fx["x"], train=True, taps=taps)
-    _check_levels(eng, taps, 0.05)  # bf16 storage noise through ~60 BatchNorm layers with tiny batch statistics
+    _check_levels(eng, taps, 0.05, small_sample_tol=0.25)
     assert float((probs.cpu() - fx["train_probs"]).abs().mean()) < 0.01
     hist, cm, loss, bad = eng.scalars()
     l = float(loss[0] / loss[1])
@@ -97,3 +103,33 @@ def test_train_forward_batch_stats(path):
     n = B * H * W
     mean = st[0] / n
     torch.testing.assert_close(mean.float(), want.mean(dim=(0, 2, 3)), rtol=0.05, atol=0.02)
+
+
+@pytest.mark.gpu
+def test_train_forward_realistic_batch():
+    """every arena within 5 % of the fp32 oracle in training mode (eval mode: < 1 %).  Training mode is noisier because
+    the 3x5 / 7x10 levels normalise with batch statistics over only a few hundred samples and their bf16 rounding is
+    carried up through the transposed convolutions."""
+    B, H, W, C = 8, 128, 192, 4
+    sd = net.init_state_dict(num_cls=C, seed=77)
+    x, y = steps.synthetic_batch(B, H, W, C, seed=77)
+    params, bn = flatten_state_dict(sd, C, "cuda")
+    eng = Engine(B, H, W, C, training=True).bind()
+    eng.pack_weights(params)
+    eng.forward(params, bn, x.cuda(), train=True)
+    torch.cuda.synchronize()
+    taps = {}
+    sdc = {k: v.cuda() for k, v in sd.items()}
+    with torch.no_grad():
+        net.feature_extractor(sdc, x.cuda(), train=True, taps=taps)
+    taps = {k: v.cpu() for k, v in taps.items()}
+    worst = _check_levels(eng, taps, 0.05)
+    print("worst level error", worst)
+    # shared batch statistics of every level against torch (mean and variance of all concat channels)
+    for l in range(5):
+        want = ref_to_phys(taps[f"featureExtractor.denseBlocksUp.{4 - l}"], SKIPS[l])
+        st = eng.level_stats(l).cpu()
+        n = want.shape[0] * want.shape[2] * want.shape[3]
+        mean, var = st[0] / n, st[1] / n - (st[0] / n) ** 2
+        torch.testing.assert_close(mean.float(), want.mean(dim=(0, 2, 3)), rtol=0.05, atol=0.02)
+        torch.testing.assert_close(var.float(), want.var(dim=(0, 2, 3), unbiased=False), rtol=0.08, atol=0.01)
