@@ -31,8 +31,10 @@ __global__ void __launch_bounds__(128, 2) dense_fwd_kernel(DenseFwdArgs a) {
   __shared__ uint64_t bar_full[2], bar_done[2];
   __shared__ uint32_t tmem_base_s;
   __shared__ float red[4][32];
+  __shared__ __align__(16) float s_bias16[16];
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid < 16) s_bias16[tid] = a.bias[tid];
 
   // ---- work item: rows [R0,R1) of the level (all images stacked), columns [x0,x1)
   const int run = blockIdx.x / a.nstrips, strip = blockIdx.x % a.nstrips;
@@ -206,10 +208,24 @@ __global__ void __launch_bounds__(128, 2) dense_fwd_kernel(DenseFwdArgs a) {
             o[q * 4 + 3] = z.w;
           }
           uint32_t pk[8];
+          float mk[16];
+          if (a.mask != nullptr) {
+            const float4* mp = reinterpret_cast<const float4*>(a.mask + (size_t)img * 16);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const float4 m4 = __ldg(mp + q);
+              mk[4 * q] = m4.x;
+              mk[4 * q + 1] = m4.y;
+              mk[4 * q + 2] = m4.z;
+              mk[4 * q + 3] = m4.w;
+            }
+          } else {
+#pragma unroll
+            for (int c = 0; c < 16; ++c) mk[c] = 1.f;
+          }
 #pragma unroll
           for (int c = 0; c < 16; c += 2) {
-            float m0 = a.mask ? a.mask[img * 16 + c] : 1.f, m1 = a.mask ? a.mask[img * 16 + c + 1] : 1.f;
-            float y0 = (o[c] + a.bias[c]) * m0, y1 = (o[c + 1] + a.bias[c + 1]) * m1;
+            float y0 = (o[c] + s_bias16[c]) * mk[c], y1 = (o[c + 1] + s_bias16[c + 1]) * mk[c + 1];
             pk[c >> 1] = pack_bf16x2(y0, y1);
             float2 rb = unpack_bf16x2(pk[c >> 1]);
             st_sum[c] += rb.x;
@@ -217,9 +233,8 @@ __global__ void __launch_bounds__(128, 2) dense_fwd_kernel(DenseFwdArgs a) {
             st_sum[c + 1] += rb.y;
             st_sq[c + 1] += rb.y * rb.y;
           }
-          uint4* dst = reinterpret_cast<uint4*>(a.act_out + ((size_t)orow * a.W + ox) * a.Ct + a.Cin);
-          dst[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-          dst[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+          st256(a.act_out + ((size_t)orow * a.W + ox) * a.Ct + a.Cin, make_uint4(pk[0], pk[1], pk[2], pk[3]),
+                make_uint4(pk[4], pk[5], pk[6], pk[7]));
         }
       }
     }
@@ -258,7 +273,9 @@ __global__ void __launch_bounds__(128, 2) gemm_px_kernel(GemmPxArgs a) {
   extern __shared__ __align__(128) uint8_t smem[];
   float* s_s = reinterpret_cast<float*>(smem);
   float* s_t = s_s + a.K;
-  uint8_t* stage_base = smem + (((size_t)a.K * 8 + 127) & ~(size_t)127);
+  float* s_bias = reinterpret_cast<float*>(smem + (((size_t)a.K * 8 + 127) & ~(size_t)127));  // [256] this part's bias
+  float* s_mask = s_bias + 256;                                                               // [256] dropout scale of the tile's image
+  uint8_t* stage_base = reinterpret_cast<uint8_t*>(s_mask + 256);
   const int part = blockIdx.y;
   const int n0 = a.part_n0[part], np = a.part_np[part];
   const int stageB = 8 * np * 16;           // bytes of one packed weight chunk slot for this part
@@ -284,6 +301,10 @@ __global__ void __launch_bounds__(128, 2) gemm_px_kernel(GemmPxArgs a) {
       s_s[c] = k.s;
       s_t[c] = k.t;
     }
+  for (int c = tid; c < 256; c += 128) {
+    s_bias[c] = (a.bias != nullptr && c < np) ? a.bias[n0 + c] : 0.f;
+    s_mask[c] = 1.f;
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -292,6 +313,7 @@ __global__ void __launch_bounds__(128, 2) gemm_px_kernel(GemmPxArgs a) {
 
   uint32_t g = 0;
   bool w_issued = false;
+  int mask_img = -1;
   TileLoader<128> ld;
   const __nv_bfloat16* rowptr[4];
 
@@ -301,6 +323,11 @@ __global__ void __launch_bounds__(128, 2) gemm_px_kernel(GemmPxArgs a) {
     if (a.mode == GEMM_POOL) {
       pr = (int)(tile / a.wblocks);
       wb = (int)(tile % a.wblocks);
+      const int img = pr / a.Hp;
+      if (a.mask != nullptr && img != mask_img) {  // visible to the epilogue through the main loop's barriers
+        for (int c = tid; c < np; c += 128) s_mask[c] = a.mask[(size_t)img * a.N + n0 + c];
+        mask_img = img;
+      }
     }
     auto pixel_of_row = [&](int m) -> long {
       if (a.mode == GEMM_POOL) {
@@ -381,20 +408,13 @@ __global__ void __launch_bounds__(128, 2) gemm_px_kernel(GemmPxArgs a) {
         uint32_t am[4] = {0, 0, 0, 0};
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
-          const int n = n0 + c0 + i;
-          float m = a.mask ? a.mask[img * a.N + n] : 1.f;
-          float y = (v[i] + a.bias[n]) * m;
-          int bq = q;
-#pragma unroll
-          for (int o = 1; o <= 2; o <<= 1) {
-            float oy = __shfl_xor_sync(0xffffffffu, y, o);
-            int oq = __shfl_xor_sync(0xffffffffu, bq, o);
-            if (oy > y || (oy == y && oq < bq)) {
-              y = oy;
-              bq = oq;
-            }
-          }
-          v[i] = y;
+          const float y = (v[i] + s_bias[c0 + i]) * s_mask[c0 + i];
+          float m = fmaxf(y, __shfl_xor_sync(0xffffffffu, y, 1));
+          m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 2));
+          // arg-max inside the 2x2 window = first lane of the quad holding the maximum (torch scans row-major)
+          const unsigned bal = __ballot_sync(0xffffffffu, y == m);
+          const int bq = __ffs((bal >> (lane & 28)) & 0xFu) - 1;
+          v[i] = m;
           am[i >> 2] |= (uint32_t)bq << (8 * (i & 3));
         }
         if (valid && q == 0) {
@@ -423,13 +443,12 @@ __global__ void __launch_bounds__(128, 2) gemm_px_kernel(GemmPxArgs a) {
     tc_fence_before();
     __syncthreads();
   }
-  (void)lane;
   tc_fence_before();
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem, 256);
 }
 
-size_t gemm_px_smem(int K, int np_max) { return (((size_t)K * 8 + 127) & ~(size_t)127) + 2 * (16384 + (size_t)8 * np_max * 16); }
+size_t gemm_px_smem(int K, int np_max) { return (((size_t)K * 8 + 127) & ~(size_t)127) + 2048 + 2 * (16384 + (size_t)8 * np_max * 16); }
 
 // ------------------------------------------------------------------------------------------------ launchers
 int launch_dense_fwd(const DenseFwdArgs& a, int grid, cudaStream_t st) {

@@ -123,7 +123,7 @@ def test_train_forward_realistic_batch():
     with torch.no_grad():
         net.feature_extractor(sdc, x.cuda(), train=True, taps=taps)
     taps = {k: v.cpu() for k, v in taps.items()}
-    worst = _check_levels(eng, taps, 0.05)
+    worst = _check_levels(eng, taps, 0.05, small_sample_tol=0.15)
     print("worst level error", worst)
     # shared batch statistics of every level against torch (mean and variance of all concat channels)
     for l in range(5):
