@@ -72,6 +72,33 @@ __device__ __forceinline__ float warp_reduce16(float* v, int lane) {
   return v[0] + __shfl_xor_sync(0xffffffffu, v[0], 1);
 }
 
+// Σ over the 32 lanes of v[k], k = 0..7; every lane ends up with the total of k = (lane >> 2) & 7
+__device__ __forceinline__ float warp_reduce8(float* v, int lane) {
+  {
+    const bool hi = lane & 16;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float send = hi ? v[i] : v[i + 4], keep = hi ? v[i + 4] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    }
+  }
+  {
+    const bool hi = lane & 8;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const float send = hi ? v[i] : v[i + 2], keep = hi ? v[i + 2] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+    }
+  }
+  {
+    const bool hi = lane & 4;
+    const float send = hi ? v[0] : v[1], keep = hi ? v[1] : v[0];
+    v[0] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+  }
+  float r = v[0] + __shfl_xor_sync(0xffffffffu, v[0], 2);
+  return r + __shfl_xor_sync(0xffffffffu, r, 1);
+}
+
 // x / dX of one 16-channel group of this thread's pixel, fetched two groups ahead of their use
 struct DgradPre {
   uint4 x0, x1, d0, d1;
@@ -79,7 +106,9 @@ struct DgradPre {
 __device__ __forceinline__ void dgrad_prefetch(DgradPre& p, const __nv_bfloat16* xrow, const __nv_bfloat16* drow, int c0,
                                                int nvalid, bool rmw, int variant = 3) {
   if (xrow != nullptr && c0 < nvalid) {
-    if (variant & 2) {
+    if (variant & 32) {
+      p.x0 = p.x1 = make_uint4(0x3f803f80u, 0x3f803f80u, 0x3f803f80u, 0x3f803f80u);
+    } else if (variant & 2) {
       const u32x8 xv = (variant & 1) ? ldg256_nc(xrow + c0) : ldg256_nc_nohint(xrow + c0);
       p.x0 = xv.lo;
       p.x1 = xv.hi;
@@ -87,7 +116,7 @@ __device__ __forceinline__ void dgrad_prefetch(DgradPre& p, const __nv_bfloat16*
       p.x0 = ldg128(xrow + c0);
       p.x1 = ldg128(xrow + c0 + 8);
     }
-    if (rmw) {
+    if (rmw && !(variant & 16)) {
       if (variant & 2) {
         const u32x8 dv = (variant & 1) ? ld256(drow + c0) : ld256_nohint(drow + c0);
         p.d0 = dv.lo;
@@ -115,33 +144,49 @@ __device__ __forceinline__ void dgrad_epilogue(uint32_t tmem_acc, int warp, int 
       tmem_ld16(tmem_acc + ((uint32_t)(warp * 32) << 16) + c0, g);
       const DgradPre cur = pre[gi & 1];
       if (gi + 2 < 8) dgrad_prefetch(pre[gi & 1], xrow, drow, c0 + 32, nvalid, (cbase + c0 + 32) >= a.rmw_from, a.variant);
-      float gs[16], gx[16];
-      if (xrow != nullptr) {
-        float x[16], d[16];
-        unpack8(cur.x0, x);
-        unpack8(cur.x1, x + 8);
-        unpack8(cur.d0, d);
-        unpack8(cur.d1, d + 8);
+      // two halves of 8 channels keep the fp32 temporaries small (register budget: 4 CTAs per SM)
+      uint4 dpk[2];
+      float r1[2], r2[2];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const float4 kk = k->k[c0 + i];
-          const float gv = (fmaf(x[i], kk.x, kk.y) > 0.f) ? g[i] : 0.f;
-          gs[i] = gv;
-          gx[i] = gv * (x[i] - kk.w);
-          d[i] = fmaf(kk.z, gv, d[i]);
-        }
-        if (a.variant & 2) {
-          st256(drow + c0, pack8(d), pack8(d + 8));
+      for (int h = 0; h < 2; ++h) {
+        float gs[8], gx[8];
+        if (xrow != nullptr) {
+          float x[8], d[8];
+          unpack8(h ? cur.x1 : cur.x0, x);
+          unpack8(h ? cur.d1 : cur.d0, d);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float4 kk = k->k[c0 + 8 * h + i];
+            const float gv = (fmaf(x[i], kk.x, kk.y) > 0.f) ? g[8 * h + i] : 0.f;
+            gs[i] = gv;
+            gx[i] = gv * (x[i] - kk.w);
+            d[i] = fmaf(kk.z, gv, d[i]);
+          }
+          dpk[h] = pack8(d);
         } else {
-          *reinterpret_cast<uint4*>(drow + c0) = pack8(d);
-          *reinterpret_cast<uint4*>(drow + c0 + 8) = pack8(d + 8);
-        }
-      } else {
 #pragma unroll
-        for (int i = 0; i < 16; ++i) gs[i] = gx[i] = 0.f;
+          for (int i = 0; i < 8; ++i) gs[i] = gx[i] = 0.f;
+          dpk[h] = make_uint4(0, 0, 0, 0);
+        }
+        if (a.variant & 4) {  // triage switch: skip the BN-sum butterflies
+          r1[h] = gs[0];
+          r2[h] = gx[0];
+        } else {
+          r1[h] = warp_reduce8(gs, lane);
+          r2[h] = warp_reduce8(gx, lane);
+        }
       }
-      S1[gi] += warp_reduce16(gs, lane);
-      S2[gi] += warp_reduce16(gx, lane);
+      if (xrow != nullptr && !(a.variant & 8)) {
+        if (a.variant & 2) {
+          st256(drow + c0, dpk[0], dpk[1]);
+        } else {
+          *reinterpret_cast<uint4*>(drow + c0) = dpk[0];
+          *reinterpret_cast<uint4*>(drow + c0 + 8) = dpk[1];
+        }
+      }
+      // lane keeps channel (lane&2 ? 8 : 0) + ((lane >> 2) & 7) of this group
+      S1[gi] += (lane & 2) ? r1[1] : r1[0];
+      S2[gi] += (lane & 2) ? r2[1] : r2[0];
     }
   }
 }
@@ -168,7 +213,7 @@ __device__ __forceinline__ void dgrad_flush(float* s_sum /*[2][128]*/, const flo
   for (int i = threadIdx.x; i < 256; i += 128) s_sum[i] = 0.f;
   __syncthreads();
   if ((lane & 1) == 0) {
-    const int cl = (lane >> 1) & 15;
+    const int cl = ((lane >> 1) & 1) * 8 + ((lane >> 2) & 7);
 #pragma unroll
     for (int gi = 0; gi < 8; ++gi)
       if (gi * 16 < nvalid) {

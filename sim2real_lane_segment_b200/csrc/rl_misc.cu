@@ -516,38 +516,46 @@ __device__ __forceinline__ void unpack8(uint4 v, float* f) {
 }
 
 __global__ void __launch_bounds__(256) dz_prepare_kernel(DzArgs a) {
-  extern __shared__ float sm[];  // mean[nch], rstd[nch], A[nch], Bc[nch], then reduction scratch [256][8]
-  float* s_mean = sm;
-  float* s_rstd = sm + a.nch;
-  float* s_A = sm + 2 * a.nch;
-  float* s_B = sm + 3 * a.nch;
-  float* s_red = sm + 4 * a.nch;
-  for (int c = threadIdx.x; c < a.nch; c += blockDim.x) {
-    const int gc = a.c_off + c;
+  extern __shared__ float sm[];  // reduction scratch [256][8]
+  float* s_red = sm;
+  const int nchunk = a.nch / 8;
+  // every thread owns one fixed chunk of 8 channels: its BatchNorm constants and deferred-correction coefficients
+  // live in registers for the whole kernel
+  const int jown = threadIdx.x % nchunk;
+  float c_mean[8], c_rstd[8], c_A[8], c_B[8], mk[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int gc = a.c_off + jown * 8 + k;
     double m = a.stats[gc] * a.inv_n_out, v = a.stats[a.Ct + gc] * a.inv_n_out - m * m;
     if (v < 0) v = 0;
-    s_mean[c] = (float)m;
-    s_rstd[c] = (float)(1.0 / sqrt(v + (double)kBnEps));
-    s_A[c] = (float)(a.acc[gc] * a.inv_n_out);
-    s_B[c] = (float)(a.acc[a.Ct + gc] * a.inv_n_out);
+    c_mean[k] = (float)m;
+    c_rstd[k] = (float)(1.0 / sqrt(v + (double)kBnEps));
+    c_A[k] = (float)(a.acc[gc] * a.inv_n_out);
+    c_B[k] = (float)(a.acc[a.Ct + gc] * a.inv_n_out);
+    mk[k] = 1.f;
   }
-  __syncthreads();
-  const int nchunk = a.nch / 8;
+  int mk_img = -1;
   float bsum[8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) bsum[k] = 0.f;
   int jfix = -1;
 
+  // j is always this thread's own chunk (jown)
   auto corrected = [&](long Pout, int j, int img, float* o) {
     float dx[8], xv[8];
     unpack8(ldg128(a.dact + Pout * a.Ct + a.c_off + j * 8), dx);
     unpack8(ldg128(a.act + Pout * a.Ct + a.c_off + j * 8), xv);
+    if (a.mask != nullptr && img != mk_img) {
+      const float4* mp = reinterpret_cast<const float4*>(a.mask + (long)img * a.nch + j * 8);
+      const float4 m0 = __ldg(mp), m1 = __ldg(mp + 1);
+      mk[0] = m0.x; mk[1] = m0.y; mk[2] = m0.z; mk[3] = m0.w;
+      mk[4] = m1.x; mk[5] = m1.y; mk[6] = m1.z; mk[7] = m1.w;
+      mk_img = img;
+    }
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-      const int c = j * 8 + k;
-      const float xh = (xv[k] - s_mean[c]) * s_rstd[c];
-      const float m = a.mask ? a.mask[(long)img * a.nch + c] : 1.f;
-      o[k] = m * (dx[k] - s_A[c] - xh * s_B[c]);
+      const float xh = (xv[k] - c_mean[k]) * c_rstd[k];
+      o[k] = mk[k] * (dx[k] - c_A[k] - xh * c_B[k]);
     }
   };
 
@@ -642,7 +650,7 @@ __global__ void __launch_bounds__(256) dz_prepare_kernel(DzArgs a) {
 }
 
 int launch_dz_prepare(const DzArgs& a, int sm, cudaStream_t st) {
-  size_t smem = (size_t)(4 * a.nch + 256 * 8) * sizeof(float);
+  size_t smem = (size_t)(256 * 8) * sizeof(float);
   long work = (a.kind == 0) ? a.npx_out : (a.kind == 1 ? (long)a.B * a.H * a.W : (long)a.B * a.Hp * a.Wp * 9);
   int nchunk = a.nch / 8;
   int ppb = 256 / nchunk;
