@@ -20,7 +20,11 @@ constexpr int kRing = 512;  // col2im ring, pixels
 // ================================================================================================
 // dense_fwd_kernel
 // ================================================================================================
-__global__ void __launch_bounds__(128, 2) dense_fwd_kernel(DenseFwdArgs a) {
+constexpr int kFwdThreads = 160;  // warps 0-3: operand producers + epilogue; warp 4: weight TMA + MMA issue
+
+__device__ __forceinline__ void producers_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+__global__ void __launch_bounds__(kFwdThreads, 2) dense_fwd_kernel(DenseFwdArgs a) {
   extern __shared__ __align__(128) uint8_t smem[];
   // smem carve-up: s[Cin], t[Cin] floats | zs ring [4][kRing][4] floats | 2 stages x (A 16 KB + W 18 KB)
   float* s_s = reinterpret_cast<float*>(smem);
@@ -28,7 +32,9 @@ __global__ void __launch_bounds__(128, 2) dense_fwd_kernel(DenseFwdArgs a) {
   float* zs = reinterpret_cast<float*>(smem + (((size_t)a.Cin * 8 + 127) & ~(size_t)127));
   uint8_t* stage_base = reinterpret_cast<uint8_t*>(zs) + 4 * kRing * 16;
   constexpr int kStageBytes = 16384 + 18432;
-  __shared__ uint64_t bar_full[2], bar_done[2];
+  // ready: 128 producers stored + fenced their part of A[s];  wfull: weight chunk landed (TMA tx bytes);
+  // done: the MMAs that read stage s retired;  acc_full: a tile's accumulator is complete;  acc_empty: 128 readers drained it
+  __shared__ uint64_t bar_ready[2], bar_wfull[2], bar_done[2], bar_acc_full, bar_acc_empty;
   __shared__ uint32_t tmem_base_s;
   __shared__ float red[4][32];
   __shared__ __align__(16) float s_bias16[16];
@@ -48,215 +54,220 @@ __global__ void __launch_bounds__(128, 2) dense_fwd_kernel(DenseFwdArgs a) {
   const int nkc = (a.Cin + 63) / 64;
 
   if (tid == 0) {
-    mbar_init(&bar_full[0], 1);
-    mbar_init(&bar_full[1], 1);
-    mbar_init(&bar_done[0], 1);
-    mbar_init(&bar_done[1], 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&bar_ready[i], 128);
+      mbar_init(&bar_wfull[i], 1);
+      mbar_init(&bar_done[i], 1);
+    }
+    mbar_init(&bar_acc_full, 1);
+    mbar_init(&bar_acc_empty, 128);
     fence_mbar_init();
   }
   if (warp == 0) tmem_alloc(&tmem_base_s, 256);
-  for (int c = tid; c < a.Cin; c += 128) {
+  for (int c = tid; c < a.Cin; c += kFwdThreads) {
     BnCoef k = bn_coef(a.bn, c);
     s_s[c] = k.s;
     s_t[c] = k.t;
   }
-  for (int i = tid; i < 4 * kRing * 4; i += 128) zs[i] = 0.f;
+  for (int i = tid; i < 4 * kRing * 4; i += kFwdThreads) zs[i] = 0.f;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_base_s;
-  const uint32_t idesc = umma_idesc_bf16(144, 0, 0);
 
-  float st_sum[16], st_sq[16];
-#pragma unroll
-  for (int i = 0; i < 16; ++i) st_sum[i] = st_sq[i] = 0.f;
-
-  uint32_t g = 0;  // running chunk counter: stage = g & 1, use index = g >> 1
-  bool w_issued = false;  // weights of chunk g already requested by thread 0 during the previous iteration
-  int emit_pos = 0;
-  TileLoader<128> ld;
-  const __nv_bfloat16* rowptr[4];
-
-  auto set_rowptrs = [&](int t0) {
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int t = t0 + TileLoader<128>::row_of(i);
-      if (t < n_in) {
-        const int rr = t / SW, cc = t - rr * SW;
-        rowptr[i] = a.act + ((size_t)(rin0 + rr) * a.W + (xi0 + cc)) * a.Ct;
-      } else {
-        rowptr[i] = nullptr;
-      }
-    }
-  };
-  auto shifted = [&](int kc) {
-    // row pointers advanced to the K-chunk (pointer arithmetic on nullptr avoided)
-  };
-  (void)shifted;
-
-  for (int tile = 0; tile < ntiles; ++tile) {
-    const int t0 = tile * 128;
-    set_rowptrs(t0);
-    // ---------------- main loop over K chunks of 64 channels
-    {
-      const __nv_bfloat16* rp[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) rp[i] = rowptr[i];
-      ld.load(rp, min(8, a.Cin / 8));
-    }
-    for (int kc = 0; kc < nkc; ++kc) {
-      const int ck = min(64, a.Cin - kc * 64);
-      const uint32_t s = g & 1, u = g >> 1;
-      uint8_t* sA = stage_base + s * kStageBytes;
-      uint8_t* sW = sA + 16384;
-      if (u > 0) mbar_wait(&bar_done[s], (u - 1) & 1);  // MMAs that read this stage have retired
-      if (tid == 0 && !w_issued) {  // (normally issued one iteration ahead, see below)
+  if (warp == 4) {
+    // =============================================================== weight TMA + MMA issue (one elected lane)
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_bf16(144, 0, 0);
+      auto issue_w = [&](uint32_t gg, int kc) {
+        const uint32_t s = gg & 1, u = gg >> 1;
+        if (u > 0) mbar_wait(&bar_done[s], (u - 1) & 1);  // MMAs that last read this stage have retired
+        const int ck = min(64, a.Cin - kc * 64);
         const uint32_t wbytes = (uint32_t)(ck / 8) * 144 * 16;
-        mbar_arrive_expect_tx(&bar_full[s], wbytes);
-        bulk_g2s(sW, a.wpk + (size_t)kc * 18432, wbytes, &bar_full[s]);
-      }
-      ld.store(sA, rowptr, ck / 8, s_s + kc * 64, s_t + kc * 64);
-      if (kc + 1 < nkc) {  // prefetch next chunk while this one is consumed
-        const __nv_bfloat16* rp[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) rp[i] = rowptr[i] ? rowptr[i] + (kc + 1) * 64 : nullptr;
-        ld.load(rp, min(8, (a.Cin - (kc + 1) * 64) / 8));
-      }
-      fence_proxy_async();
-      __syncthreads();
-      if (tid == 0) {
-        mbar_wait(&bar_full[s], u & 1);
-        tc_fence_after();
-        const uint32_t aaddr = smem_u32(sA), waddr = smem_u32(sW);
-        for (int kk = 0; kk < ck / 16; ++kk)
-          umma_ss(tmem, desc_kmajor(aaddr + kk * 2 * 16 * 128, 128), desc_kmajor(waddr + kk * 2 * 16 * 144, 144), idesc,
-                  (kc | kk) != 0);
-        umma_commit(&bar_done[s]);
-        // weights of the NEXT chunk (this tile's kc+1, or the next tile's chunk 0) go out now, one iteration ahead of
-        // their use, into the other stage as soon as the MMAs that last read it (issued one iteration ago) retire
-        const bool more = (kc + 1 < nkc) || (tile + 1 < ntiles);
-        if (more) {
-          const int nk = (kc + 1 < nkc) ? kc + 1 : 0;
-          const int nck = min(64, a.Cin - nk * 64);
-          const uint32_t ns = (g + 1) & 1, nu = (g + 1) >> 1;
-          if (nu > 0) mbar_wait(&bar_done[ns], (nu - 1) & 1);
-          const uint32_t wbytes = (uint32_t)(nck / 8) * 144 * 16;
-          mbar_arrive_expect_tx(&bar_full[ns], wbytes);
-          bulk_g2s(stage_base + ns * kStageBytes + 16384, a.wpk + (size_t)nk * 18432, wbytes, &bar_full[ns]);
+        mbar_arrive_expect_tx(&bar_wfull[s], wbytes);
+        bulk_g2s(stage_base + s * kStageBytes + 16384, a.wpk + (size_t)kc * 18432, wbytes, &bar_wfull[s]);
+      };
+      uint32_t g = 0;
+      if (ntiles > 0) issue_w(0, 0);
+      for (int tile = 0; tile < ntiles; ++tile) {
+        if (tile > 0) {
+          mbar_wait(&bar_acc_empty, (tile - 1) & 1);  // previous tile's accumulator has been read out
+          tc_fence_after();
+        }
+        for (int kc = 0; kc < nkc; ++kc, ++g) {
+          const uint32_t s = g & 1, u = g >> 1;
+          const int ck = min(64, a.Cin - kc * 64);
+          // next chunk's weights go out one step ahead (this tile's kc+1, or the next tile's chunk 0)
+          if (kc + 1 < nkc) issue_w(g + 1, kc + 1);
+          else if (tile + 1 < ntiles) issue_w(g + 1, 0);
+          mbar_wait(&bar_ready[s], u & 1);
+          mbar_wait(&bar_wfull[s], u & 1);
+          tc_fence_after();
+          const uint32_t aaddr = smem_u32(stage_base + s * kStageBytes), waddr = aaddr + 16384;
+          for (int kk = 0; kk < ck / 16; ++kk)
+            umma_ss(tmem, desc_kmajor(aaddr + kk * 2 * 16 * 128, 128), desc_kmajor(waddr + kk * 2 * 16 * 144, 144), idesc,
+                    (kc | kk) != 0);
+          umma_commit(&bar_done[s]);
+          if (kc == nkc - 1) umma_commit(&bar_acc_full);
         }
       }
-      w_issued = true;
-      ++g;
     }
-    // ---------------- accumulator ready: the commit of the last chunk covers every MMA of this tile
-    {
-      const uint32_t s = (g - 1) & 1, u = (g - 1) >> 1;
-      mbar_wait(&bar_done[s], u & 1);
+  } else {
+    // =============================================================== producers (BN+ReLU -> smem A) and epilogue
+    float st_sum[16], st_sq[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) st_sum[i] = st_sq[i] = 0.f;
+    uint32_t g = 0;
+    int emit_pos = 0;
+    TileLoader<128> ld;
+    const __nv_bfloat16* rowptr[4];
+    auto set_rowptrs = [&](int t0) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int t = t0 + TileLoader<128>::row_of(i);
+        if (t < n_in) {
+          const int rr = t / SW, cc = t - rr * SW;
+          rowptr[i] = a.act + ((size_t)(rin0 + rr) * a.W + (xi0 + cc)) * a.Ct;
+        } else {
+          rowptr[i] = nullptr;
+        }
+      }
+    };
+    if (ntiles > 0) {
+      set_rowptrs(0);
+      ld.load(rowptr, min(8, a.Cin / 8));
+    }
+    for (int tile = 0; tile < ntiles; ++tile) {
+      const int t0 = tile * 128;
+      // ---------------- K chunks of 64 channels: registers -> BN+ReLU -> smem A[s]; no block-wide barrier
+      for (int kc = 0; kc < nkc; ++kc, ++g) {
+        const int ck = min(64, a.Cin - kc * 64);
+        const uint32_t s = g & 1, u = g >> 1;
+        if (u > 0) mbar_wait(&bar_done[s], (u - 1) & 1);
+        ld.store(stage_base + s * kStageBytes, rowptr, ck / 8, s_s + kc * 64, s_t + kc * 64);
+        if (kc + 1 < nkc) {  // prefetch the next chunk while this one is consumed
+          const __nv_bfloat16* rp[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) rp[i] = rowptr[i] ? rowptr[i] + (kc + 1) * 64 : nullptr;
+          ld.load(rp, min(8, (a.Cin - (kc + 1) * 64) / 8));
+        }
+        fence_proxy_async();
+        mbar_arrive(&bar_ready[s]);
+      }
+      // first chunk of the next tile streams in behind this tile's epilogue
+      if (tile + 1 < ntiles) {
+        set_rowptrs(t0 + 128);
+        ld.load(rowptr, min(8, a.Cin / 8));
+      }
+      mbar_wait(&bar_acc_full, tile & 1);
       tc_fence_after();
-    }
-    // ---------------- col2im scatter of the 9 tap planes
-    const int t = t0 + tid;
-    const bool in_valid = t < n_in;
-    int rr = 0, cc = 0;
-    if (in_valid) {
-      rr = t / SW;
-      cc = t - rr * SW;
-    }
-    const int r = rin0 + rr, xx = xi0 + cc;
-    const int ri = r % a.H;
-#pragma unroll 1
-    for (int tap = 0; tap < 9; ++tap) {
-      const int dy = tap / 3 - 1, dx = tap % 3 - 1;
-      float v[16];
-      tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16) + tap * 16, v);
-      const int qr = r - dy, qx = xx - dx, qi = ri - dy;
-      if (in_valid && qi >= 0 && qi < a.H && qr >= R0 && qr < R1 && qx >= x0 && qx < x1) {
-        const int uidx = (t - dy * SW - dx + SW + 1) & (kRing - 1);
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          float4* p = reinterpret_cast<float4*>(zs + ((size_t)q * kRing + uidx) * 4);
-          float4 o = *p;
-          o.x += v[q * 4 + 0];
-          o.y += v[q * 4 + 1];
-          o.z += v[q * 4 + 2];
-          o.w += v[q * 4 + 3];
-          *p = o;
-        }
+      // ---------------- col2im scatter of the 9 tap planes
+      const int t = t0 + tid;
+      const bool in_valid = t < n_in;
+      int rr = 0, cc = 0;
+      if (in_valid) {
+        rr = t / SW;
+        cc = t - rr * SW;
       }
-      tc_fence_before();
-      __syncthreads();
-    }
-    // ---------------- emit finished output pixels
-    const int lim = (tile == ntiles - 1) ? n_in : max(0, min(t0 + 128 - SW - 1, n_in));
-    for (int e0 = emit_pos; e0 < lim; e0 += 128) {
-      const int e = e0 + tid;
-      if (e < lim) {
-        const int er = e / SW, ec = e - er * SW;
-        const int orow = rin0 + er, ox = xi0 + ec;
-        if (orow >= R0 && orow < R1 && ox >= x0 && ox < x1) {
-          const int uidx = (e + SW + 1) & (kRing - 1);
-          const int img = orow / a.H;
-          float o[16];
+      const int r = rin0 + rr, xx = xi0 + cc;
+      const int ri = r % a.H;
+#pragma unroll 1
+      for (int tap = 0; tap < 9; ++tap) {
+        const int dy = tap / 3 - 1, dx = tap % 3 - 1;
+        float v[16];
+        tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16) + tap * 16, v);
+        if (tap == 8) {  // accumulator fully read by this thread: the next tile's MMAs may overwrite it
+          tc_fence_before();
+          mbar_arrive(&bar_acc_empty);
+        }
+        const int qr = r - dy, qx = xx - dx, qi = ri - dy;
+        if (in_valid && qi >= 0 && qi < a.H && qr >= R0 && qr < R1 && qx >= x0 && qx < x1) {
+          const int uidx = (t - dy * SW - dx + SW + 1) & (kRing - 1);
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             float4* p = reinterpret_cast<float4*>(zs + ((size_t)q * kRing + uidx) * 4);
-            float4 z = *p;
-            *p = make_float4(0.f, 0.f, 0.f, 0.f);
-            o[q * 4 + 0] = z.x;
-            o[q * 4 + 1] = z.y;
-            o[q * 4 + 2] = z.z;
-            o[q * 4 + 3] = z.w;
+            float4 o = *p;
+            o.x += v[q * 4 + 0];
+            o.y += v[q * 4 + 1];
+            o.z += v[q * 4 + 2];
+            o.w += v[q * 4 + 3];
+            *p = o;
           }
-          uint32_t pk[8];
-          float mk[16];
-          if (a.mask != nullptr) {
-            const float4* mp = reinterpret_cast<const float4*>(a.mask + (size_t)img * 16);
+        }
+        producers_sync();
+      }
+      // ---------------- emit finished output pixels
+      const int lim = (tile == ntiles - 1) ? n_in : max(0, min(t0 + 128 - SW - 1, n_in));
+      for (int e0 = emit_pos; e0 < lim; e0 += 128) {
+        const int e = e0 + tid;
+        if (e < lim) {
+          const int er = e / SW, ec = e - er * SW;
+          const int orow = rin0 + er, ox = xi0 + ec;
+          if (orow >= R0 && orow < R1 && ox >= x0 && ox < x1) {
+            const int uidx = (e + SW + 1) & (kRing - 1);
+            const int img = orow / a.H;
+            float o[16];
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-              const float4 m4 = __ldg(mp + q);
-              mk[4 * q] = m4.x;
-              mk[4 * q + 1] = m4.y;
-              mk[4 * q + 2] = m4.z;
-              mk[4 * q + 3] = m4.w;
+              float4* p = reinterpret_cast<float4*>(zs + ((size_t)q * kRing + uidx) * 4);
+              float4 z = *p;
+              *p = make_float4(0.f, 0.f, 0.f, 0.f);
+              o[q * 4 + 0] = z.x;
+              o[q * 4 + 1] = z.y;
+              o[q * 4 + 2] = z.z;
+              o[q * 4 + 3] = z.w;
             }
-          } else {
+            uint32_t pk[8];
+            float mk[16];
+            if (a.mask != nullptr) {
+              const float4* mp = reinterpret_cast<const float4*>(a.mask + (size_t)img * 16);
 #pragma unroll
-            for (int c = 0; c < 16; ++c) mk[c] = 1.f;
-          }
+              for (int q = 0; q < 4; ++q) {
+                const float4 m4 = __ldg(mp + q);
+                mk[4 * q] = m4.x;
+                mk[4 * q + 1] = m4.y;
+                mk[4 * q + 2] = m4.z;
+                mk[4 * q + 3] = m4.w;
+              }
+            } else {
 #pragma unroll
-          for (int c = 0; c < 16; c += 2) {
-            float y0 = (o[c] + s_bias16[c]) * mk[c], y1 = (o[c + 1] + s_bias16[c + 1]) * mk[c + 1];
-            pk[c >> 1] = pack_bf16x2(y0, y1);
-            float2 rb = unpack_bf16x2(pk[c >> 1]);
-            st_sum[c] += rb.x;
-            st_sq[c] += rb.x * rb.x;
-            st_sum[c + 1] += rb.y;
-            st_sq[c + 1] += rb.y * rb.y;
+              for (int c = 0; c < 16; ++c) mk[c] = 1.f;
+            }
+#pragma unroll
+            for (int c = 0; c < 16; c += 2) {
+              float y0 = (o[c] + s_bias16[c]) * mk[c], y1 = (o[c + 1] + s_bias16[c + 1]) * mk[c + 1];
+              pk[c >> 1] = pack_bf16x2(y0, y1);
+              float2 rb = unpack_bf16x2(pk[c >> 1]);
+              st_sum[c] += rb.x;
+              st_sq[c] += rb.x * rb.x;
+              st_sum[c + 1] += rb.y;
+              st_sq[c + 1] += rb.y * rb.y;
+            }
+            st256(a.act_out + ((size_t)orow * a.W + ox) * a.Ct + a.Cin, make_uint4(pk[0], pk[1], pk[2], pk[3]),
+                  make_uint4(pk[4], pk[5], pk[6], pk[7]));
           }
-          st256(a.act_out + ((size_t)orow * a.W + ox) * a.Ct + a.Cin, make_uint4(pk[0], pk[1], pk[2], pk[3]),
-                make_uint4(pk[4], pk[5], pk[6], pk[7]));
         }
       }
+      emit_pos = max(emit_pos, lim);
+      producers_sync();
     }
-    emit_pos = max(emit_pos, lim);
-    __syncthreads();
-  }
 
-  // ---------------- per-channel Σx, Σx² of the 16 new channels (fp32 per thread -> fp64 atomics)
-  if (a.stats_out != nullptr) {
+    // ---------------- per-channel Σx, Σx² of the 16 new channels (fp32 per thread -> fp64 atomics)
+    if (a.stats_out != nullptr) {
 #pragma unroll
-    for (int c = 0; c < 16; ++c) {
-      float s1 = warp_sum(st_sum[c]), s2 = warp_sum(st_sq[c]);
-      if (lane == 0) {
-        red[warp][c] = s1;
-        red[warp][16 + c] = s2;
+      for (int c = 0; c < 16; ++c) {
+        float s1 = warp_sum(st_sum[c]), s2 = warp_sum(st_sq[c]);
+        if (lane == 0) {
+          red[warp][c] = s1;
+          red[warp][16 + c] = s2;
+        }
       }
-    }
-    __syncthreads();
-    if (tid < 32) {
-      float v = red[0][tid] + red[1][tid] + red[2][tid] + red[3][tid];
-      const int c = tid & 15;
-      atomicAdd(a.stats_out + (tid < 16 ? 0 : a.Ct) + a.Cin + c, (double)v);
+      producers_sync();
+      if (tid < 32) {
+        float v = red[0][tid] + red[1][tid] + red[2][tid] + red[3][tid];
+        const int c = tid & 15;
+        atomicAdd(a.stats_out + (tid < 16 ? 0 : a.Ct) + a.Cin + c, (double)v);
+      }
     }
   }
   tc_fence_before();
@@ -460,7 +471,7 @@ int launch_dense_fwd(const DenseFwdArgs& a, int grid, cudaStream_t st) {
   }
   if (smem > 110 * 1024) return rl_fail(RL_ERR_SHAPE, "dense_fwd: smem %zu too large", smem);
   { ProfScope _ps(KC_DENSE_FWD, st);
-  dense_fwd_kernel<<<grid, 128, smem, st>>>(a); }
+  dense_fwd_kernel<<<grid, kFwdThreads, smem, st>>>(a); }
   RL_CUDA(cudaGetLastError());
   return RL_OK;
 }

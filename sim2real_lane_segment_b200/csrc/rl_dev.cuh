@@ -52,10 +52,10 @@ __device__ __forceinline__ uint4 bn_relu8(uint4 v, const float* s8, const float*
   const float4 t0 = *reinterpret_cast<const float4*>(t8), t1 = *reinterpret_cast<const float4*>(t8 + 4);
   float2 a = unpack_bf16x2(v.x), b = unpack_bf16x2(v.y), c = unpack_bf16x2(v.z), d = unpack_bf16x2(v.w);
   uint4 o;
-  o.x = pack_bf16x2(fmaxf(fmaf(a.x, s0.x, t0.x), 0.f), fmaxf(fmaf(a.y, s0.y, t0.y), 0.f));
-  o.y = pack_bf16x2(fmaxf(fmaf(b.x, s0.z, t0.z), 0.f), fmaxf(fmaf(b.y, s0.w, t0.w), 0.f));
-  o.z = pack_bf16x2(fmaxf(fmaf(c.x, s1.x, t1.x), 0.f), fmaxf(fmaf(c.y, s1.y, t1.y), 0.f));
-  o.w = pack_bf16x2(fmaxf(fmaf(d.x, s1.z, t1.z), 0.f), fmaxf(fmaf(d.y, s1.w, t1.w), 0.f));
+  o.x = pack_bf16x2_relu(fmaf(a.x, s0.x, t0.x), fmaf(a.y, s0.y, t0.y));
+  o.y = pack_bf16x2_relu(fmaf(b.x, s0.z, t0.z), fmaf(b.y, s0.w, t0.w));
+  o.z = pack_bf16x2_relu(fmaf(c.x, s1.x, t1.x), fmaf(c.y, s1.y, t1.y));
+  o.w = pack_bf16x2_relu(fmaf(d.x, s1.z, t1.z), fmaf(d.y, s1.w, t1.w));
   return o;
 }
 
