@@ -289,7 +289,9 @@ def run_b200(args, rank, world, local_rank):
         ncu_traffic = os.path.join(ROOT, "profiles", "r01_traffic.json")
         if os.path.exists(ncu_traffic):
             try:
-                roof["traffic"] = json.load(open(ncu_traffic)).get(top)
+                tj = json.load(open(ncu_traffic))
+                roof["traffic"] = tj.get(top)
+                roof["traffic_note"] = tj.get("note")
             except Exception:
                 pass
 
