@@ -104,6 +104,7 @@ int rl_sgd_nesterov_step(float* params, const float* grads, float* momentum_buf,
 long rl_launch_count(int kernel_class);
 int rl_profile_begin(void);
 int rl_profile_end(double* ms, long* launches);
+int rl_profile_launches(float* ms, int* kernel_class, int max); /* per-launch times of the last profiled region */
 
 /* test hook: one 128 x N x K tcgen05 GEMM through the shared-memory operand conventions of csrc/rl_umma.cuh */
 int rl_selftest_umma(const void* A, int a_rows, int a_cols, int a_mn_major, int a_row_shift, const void* B, int b_rows,

@@ -408,7 +408,10 @@ extern "C" int rl_backward(rl_plan* h, const float* params, const float* x, floa
       d.strip_w = 160;
       d.nstrips = (lin.W + d.strip_w - 1) / d.strip_w;
       const int vrows = p->B * (lin.H + 1);
-      int nruns = std::max(1, std::min(vrows, (3 * sm) / d.nstrips));
+      // small levels run their channel blocks in parallel CTAs (launch_dgrad splits over grid.y): keep one wave in total
+      const int nmb_d = (L.cin + 127) / 128;
+      const bool split = nmb_d > 1 && (long)vrows * (lin.W + 2) <= 40000;
+      int nruns = std::max(1, std::min(vrows, (3 * sm) / (d.nstrips * (split ? nmb_d : 1))));
       d.vrows_per_cta = (vrows + nruns - 1) / nruns;
       nruns = (vrows + d.vrows_per_cta - 1) / d.vrows_per_cta;
       if ((rc = launch_dgrad(d, nruns * d.nstrips, st))) return rc;

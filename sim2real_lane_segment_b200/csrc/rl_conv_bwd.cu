@@ -223,7 +223,7 @@ __device__ __forceinline__ void dgrad_flush(float* s_sum /*[2][128]*/, const flo
   }
   __syncthreads();
   const int cl = threadIdx.x;
-  if (cl < nvalid) {
+  if (cl < nvalid && !(a.variant & 64)) {  // (bit 6: triage switch, skip the global accumulation)
     const int c = mb * 128 + cl;
     const float s1 = s_sum[cl], s2 = s_rstd[cl] * s_sum[128 + cl];
     const int rc = ref_channel(c, a.bn.cs_perm);
@@ -304,7 +304,10 @@ __global__ void __launch_bounds__(128, 3) dgrad_dense_kernel(DgradArgs a) {
     }
   };
 
-  for (int mb = 0; mb < nmb; ++mb) {
+  // channel blocks: all of them in this CTA (large levels: W^T is reused across the CTA's tiles), or one per
+  // blockIdx.y (small levels, where the chain over blocks would be pure latency)
+  const int mb_lo = gridDim.y > 1 ? blockIdx.y : 0, mb_hi = gridDim.y > 1 ? blockIdx.y + 1 : nmb;
+  for (int mb = mb_lo; mb < mb_hi; ++mb) {
     const int nvalid = min(128, a.Cin - mb * 128);
     const uint32_t idesc = umma_idesc_bf16((uint32_t)nvalid, 0, 0);
     float S1[8], S2[8];

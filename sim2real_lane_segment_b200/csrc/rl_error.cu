@@ -73,5 +73,17 @@ extern "C" int rl_profile_end(double* ms, long* launches) {
   return 0;
 }
 
+// per-launch times of the last profiled region (call after rl_profile_end): fills up to max entries, returns the count
+extern "C" int rl_profile_launches(float* ms, int* cls, int max) {
+  int n = rl::g_ev_used < max ? rl::g_ev_used : max;
+  for (int i = 0; i < n; ++i) {
+    float t = 0.f;
+    cudaEventElapsedTime(&t, rl::g_ev[i].a, rl::g_ev[i].b);
+    ms[i] = t;
+    cls[i] = rl::g_ev[i].cls;
+  }
+  return n;
+}
+
 extern "C" const char* rl_last_error(void) { return rl::g_err; }
 extern "C" int rl_abi_version(void) { return 1; }

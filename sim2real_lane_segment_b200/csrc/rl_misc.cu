@@ -293,7 +293,7 @@ int launch_label_hist(const void* y, int y_is_i64, long n, int num_cls, Scalars*
 //   -> confusion counts.  One warp handles 8 pixels: a quad of lanes per pixel, 9 chunks of 8 channels per lane.
 // ================================================================================================
 template <int C>
-__global__ void __launch_bounds__(256) head_kernel(HeadArgs a) {
+__global__ void __launch_bounds__(256, 2) head_kernel(HeadArgs a) {
   __shared__ float sw[C * 288];  // physical channel order
   __shared__ float sb[C], scw[C];
   __shared__ int scm[C * C];
@@ -494,7 +494,7 @@ __global__ void __launch_bounds__(256) head_kernel(HeadArgs a) {
 }
 
 int launch_head(const HeadArgs& a, int sm, cudaStream_t st) {
-  int grid = (int)std::min<long>((a.npx + 63) / 64, (long)sm * 4);
+  int grid = (int)std::min<long>((a.npx + 63) / 64, (long)sm * 8);
   ProfScope _ps(KC_HEAD, st);
   switch (a.num_cls) {
     case 2: head_kernel<2><<<grid, 256, 0, st>>>(a); break;
@@ -649,7 +649,251 @@ __global__ void __launch_bounds__(256) dz_prepare_kernel(DzArgs a) {
   (void)jfix;
 }
 
+// ---- specialised variants (one pass per producing layer; all index math hoisted, one `corrected` per value) ----
+struct DzConst {  // per-channel constants of `corrected`: mean, rstd, A_c, B_c
+  float mean, rstd, A, B;
+};
+__device__ __forceinline__ DzConst dz_const(const DzArgs& a, int c) {
+  const int gc = a.c_off + c;
+  double m = a.stats[gc] * a.inv_n_out, v = a.stats[a.Ct + gc] * a.inv_n_out - m * m;
+  if (v < 0) v = 0;
+  DzConst k;
+  k.mean = (float)m;
+  k.rstd = rsqrtf((float)v + kBnEps);
+  k.A = (float)(a.acc[gc] * a.inv_n_out);
+  k.B = (float)(a.acc[a.Ct + gc] * a.inv_n_out);
+  return k;
+}
+
+// DenseLayer output (16 channels): one thread per pixel, 32-byte accesses, zero-padded two-plane result
+__global__ void __launch_bounds__(256) dz_dense16_kernel(DzArgs a) {
+  __shared__ float s_red[8][16];
+  __shared__ DzConst s_k[16];
+  if (threadIdx.x < 16) s_k[threadIdx.x] = dz_const(a, threadIdx.x);
+  __syncthreads();
+  DzConst k[16];
+#pragma unroll
+  for (int c = 0; c < 16; ++c) k[c] = s_k[c];
+  float bsum[16];
+#pragma unroll
+  for (int c = 0; c < 16; ++c) bsum[c] = 0.f;
+  for (long P = blockIdx.x * (long)blockDim.x + threadIdx.x; P < a.npx_out; P += (long)gridDim.x * blockDim.x) {
+    const int img = (int)(P / a.HW_out);
+    const int hw = (int)(P - (long)img * a.HW_out), y = hw / a.W, x = hw - y * a.W;
+    const u32x8 dv = ld256_nohint(a.dact + P * a.Ct + a.c_off);
+    const u32x8 xv = ldg256_nc_nohint(a.act + P * a.Ct + a.c_off);
+    float dx[16], xx[16], mk[16], o[16];
+    unpack8(dv.lo, dx);
+    unpack8(dv.hi, dx + 8);
+    unpack8(xv.lo, xx);
+    unpack8(xv.hi, xx + 8);
+    if (a.mask != nullptr) {
+      const float4* mp = reinterpret_cast<const float4*>(a.mask + (long)img * 16);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float4 m4 = __ldg(mp + q);
+        mk[4 * q] = m4.x; mk[4 * q + 1] = m4.y; mk[4 * q + 2] = m4.z; mk[4 * q + 3] = m4.w;
+      }
+    } else {
+#pragma unroll
+      for (int c = 0; c < 16; ++c) mk[c] = 1.f;
+    }
+#pragma unroll
+    for (int c = 0; c < 16; ++c) {
+      const float xh = (xx[c] - k[c].mean) * k[c].rstd;
+      o[c] = mk[c] * (dx[c] - k[c].A - xh * k[c].B);
+      bsum[c] += o[c];
+    }
+    const long pos = a.dz_guard + ((long)img * (a.H + 1) + y) * (a.W + 2) + x + 1;
+    *reinterpret_cast<uint4*>(a.dz + pos * 8) = pack8(o);
+    *reinterpret_cast<uint4*>(a.dz + (a.dz_npos + pos) * 8) = pack8(o + 8);
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int c = 0; c < 16; ++c) {
+    const float v = warp_sum(bsum[c]);
+    if (lane == 0) s_red[warp][c] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < 16 && a.g_bias != nullptr) {
+    float v = 0.f;
+    for (int w = 0; w < 8; ++w) v += s_red[w][threadIdx.x];
+    atomicAdd(a.g_bias + threadIdx.x, v);
+  }
+}
+
+// TransitionDown output: one thread per (pooled pixel, 8-channel chunk) scatters to the 4 pixels of its 2x2 window
+__global__ void __launch_bounds__(256) dz_td_kernel(DzArgs a) {
+  extern __shared__ float sm[];
+  const int nchunk = a.nch / 8, ppb = blockDim.x / nchunk;
+  const int j = threadIdx.x % nchunk, pl = threadIdx.x / nchunk;
+  DzConst* s_k = reinterpret_cast<DzConst*>(sm + 256 * 8);  // [nch]
+  for (int c = threadIdx.x; c < a.nch; c += blockDim.x) s_k[c] = dz_const(a, c);
+  __syncthreads();
+  DzConst k[8];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) k[c] = s_k[j * 8 + c];
+  float bsum[8], mk[8];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    bsum[c] = 0.f;
+    mk[c] = 1.f;
+  }
+  int mk_img = -1;
+  const long npool = (long)a.B * a.Hp * a.Wp;
+  if (pl < ppb)
+    for (long Pp = (long)blockIdx.x * ppb + pl; Pp < npool; Pp += (long)gridDim.x * ppb) {
+      const int px = (int)(Pp % a.Wp), py = (int)((Pp / a.Wp) % a.Hp), b = (int)(Pp / ((long)a.Wp * a.Hp));
+      if (a.mask != nullptr && b != mk_img) {
+        const float4* mp = reinterpret_cast<const float4*>(a.mask + (long)b * a.nch + j * 8);
+        const float4 m0 = __ldg(mp), m1 = __ldg(mp + 1);
+        mk[0] = m0.x; mk[1] = m0.y; mk[2] = m0.z; mk[3] = m0.w; mk[4] = m1.x; mk[5] = m1.y; mk[6] = m1.z; mk[7] = m1.w;
+        mk_img = b;
+      }
+      float dx[8], xv[8], c8[8];
+      unpack8(ldg128(a.dact + Pp * a.Ct + a.c_off + j * 8), dx);
+      unpack8(ldg128(a.act + Pp * a.Ct + a.c_off + j * 8), xv);
+      const uint2 am = *reinterpret_cast<const uint2*>(a.amax + Pp * a.nch + j * 8);
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const float xh = (xv[c] - k[c].mean) * k[c].rstd;
+        c8[c] = mk[c] * (dx[c] - k[c].A - xh * k[c].B);
+        bsum[c] += c8[c];
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        float o[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const uint32_t word = c < 4 ? am.x : am.y;
+          o[c] = (((word >> (8 * (c & 3))) & 0xff) == (uint32_t)q) ? c8[c] : 0.f;
+        }
+        const long P = ((long)b * a.H + 2 * py + (q >> 1)) * a.W + 2 * px + (q & 1);
+        *reinterpret_cast<uint4*>(a.dz + P * a.nch + j * 8) = pack8(o);
+      }
+    }
+  // rows / columns outside every pooling window (odd H or W) get no gradient
+  const int xw = a.W - 2 * a.Wp, xh = a.H - 2 * a.Hp;
+  if (xw > 0 || xh > 0) {
+    const long nextra = (long)a.B * ((long)xh * a.W + (long)(a.H - xh) * xw);
+    for (long e = (long)blockIdx.x * ppb + pl; pl < ppb && e < nextra; e += (long)gridDim.x * ppb) {
+      const long per = (long)xh * a.W + (long)(a.H - xh) * xw;
+      const int b = (int)(e / per);
+      long r = e - (long)b * per;
+      int y, x;
+      if (r < (long)xh * a.W) {
+        y = 2 * a.Hp + (int)(r / a.W);
+        x = (int)(r % a.W);
+      } else {
+        r -= (long)xh * a.W;
+        y = (int)(r / xw);
+        x = 2 * a.Wp + (int)(r % xw);
+      }
+      *reinterpret_cast<uint4*>(a.dz + (((long)b * a.H + y) * a.W + x) * a.nch + j * 8) = make_uint4(0, 0, 0, 0);
+    }
+  }
+  if (a.g_bias != nullptr) {
+#pragma unroll
+    for (int c = 0; c < 8; ++c) sm[threadIdx.x * 8 + c] = bsum[c];
+    __syncthreads();
+    for (int c = threadIdx.x; c < a.nch; c += blockDim.x) {
+      float acc = 0.f;
+      for (int l = 0; l < ppb; ++l) acc += sm[(l * nchunk + c / 8) * 8 + (c % 8)];
+      atomicAdd(a.g_bias + c, acc);
+    }
+  }
+}
+
+// TransitionUp output (80 channels): one thread per (output pixel, chunk) scatters into the column matrix
+// row (b,i,j), column tap*80 + c with (2i+ky, 2j+kx) = (Y, X); slots whose output pixel lies outside the cropped
+// image are zero-filled by the threads of the last input row / column.
+__global__ void __launch_bounds__(250) dz_tu_kernel(DzArgs a) {
+  extern __shared__ float sm[];
+  const int j = threadIdx.x % 10, pl = threadIdx.x / 10;   // 10 chunks of 8 channels, 25 pixel lanes
+  const int h = a.Hp, w = a.Wp;
+  DzConst* s_k = reinterpret_cast<DzConst*>(sm + 250 * 8);  // [80]
+  for (int c = threadIdx.x; c < 80; c += blockDim.x) s_k[c] = dz_const(a, c);
+  __syncthreads();
+  DzConst k[8];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) k[c] = s_k[j * 8 + c];
+  float bsum[8];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) bsum[c] = 0.f;
+  const long nout = (long)a.B * a.H * a.W;
+  for (long P = (long)blockIdx.x * 25 + pl; P < nout; P += (long)gridDim.x * 25) {
+    const int X = (int)(P % a.W), Y = (int)((P / a.W) % a.H), b = (int)(P / ((long)a.W * a.H));
+    float dx[8], xv[8], o[8];
+    unpack8(ldg128(a.dact + P * a.Ct + a.c_off + j * 8), dx);
+    unpack8(ldg128(a.act + P * a.Ct + a.c_off + j * 8), xv);
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const float xh = (xv[c] - k[c].mean) * k[c].rstd;
+      o[c] = dx[c] - k[c].A - xh * k[c].B;
+      bsum[c] += o[c];
+    }
+    const uint4 pk = pack8(o);
+    for (int ky = (Y & 1); ky < 3; ky += 2) {
+      const int ii = (Y - ky) >> 1;
+      if (ii < 0 || ii >= h) continue;
+      for (int kx = (X & 1); kx < 3; kx += 2) {
+        const int jj = (X - kx) >> 1;
+        if (jj < 0 || jj >= w) continue;
+        *reinterpret_cast<uint4*>(a.dz + (((long)b * h + ii) * w + jj) * 720 + (ky * 3 + kx) * 80 + j * 8) = pk;
+      }
+    }
+  }
+  // zero fill: slots (i, j, ky, kx) with 2i+ky >= H or 2j+kx >= W (only ky = 2 at i = h-1 when H = 2h, same for x)
+  const bool zrow = 2 * (h - 1) + 2 >= a.H, zcol = 2 * (w - 1) + 2 >= a.W;
+  if (zrow || zcol) {
+    const long nin = (long)a.B * h * w;
+    for (long Pi = (long)blockIdx.x * 25 + pl; Pi < nin; Pi += (long)gridDim.x * 25) {
+      const int jj = (int)(Pi % w), ii = (int)((Pi / w) % h);
+      if (ii != h - 1 && jj != w - 1) continue;
+      for (int tap = 0; tap < 9; ++tap) {
+        const int ky = tap / 3, kx = tap % 3;
+        if (2 * ii + ky >= a.H || 2 * jj + kx >= a.W)
+          *reinterpret_cast<uint4*>(a.dz + Pi * 720 + tap * 80 + j * 8) = make_uint4(0, 0, 0, 0);
+      }
+    }
+  }
+  if (a.g_bias != nullptr) {
+#pragma unroll
+    for (int c = 0; c < 8; ++c) sm[threadIdx.x * 8 + c] = bsum[c];
+    __syncthreads();
+    for (int c = threadIdx.x; c < 80; c += blockDim.x) {
+      float acc = 0.f;
+      for (int l = 0; l < 25; ++l) acc += sm[(l * 10 + c / 8) * 8 + (c % 8)];
+      atomicAdd(a.g_bias + c, acc);
+    }
+  }
+}
+
 int launch_dz_prepare(const DzArgs& a, int sm, cudaStream_t st) {
+  if (a.kind == 0 && a.planes && a.nch == 16) {
+    int grid = (int)std::min<long>((a.npx_out + 255) / 256, (long)sm * 8);
+    { ProfScope _ps(KC_DZ_PREPARE, st);
+    dz_dense16_kernel<<<grid, 256, 0, st>>>(a); }
+    RL_CUDA(cudaGetLastError());
+    return RL_OK;
+  }
+  if (a.kind == 1) {
+    const int nchunk = a.nch / 8, ppb = 256 / nchunk;
+    long npool = (long)a.B * a.Hp * a.Wp;
+    int grid = (int)std::max<long>(1, std::min<long>((npool + ppb - 1) / ppb, (long)sm * 8));
+    { ProfScope _ps(KC_DZ_PREPARE, st);
+    dz_td_kernel<<<grid, 256, 256 * 8 * sizeof(float) + a.nch * sizeof(DzConst), st>>>(a); }
+    RL_CUDA(cudaGetLastError());
+    return RL_OK;
+  }
+  if (a.kind == 2 && a.nch == 80) {
+    long nout = (long)a.B * a.H * a.W;
+    int grid = (int)std::max<long>(1, std::min<long>((nout + 24) / 25, (long)sm * 8));
+    { ProfScope _ps(KC_DZ_PREPARE, st);
+    dz_tu_kernel<<<grid, 250, 250 * 8 * sizeof(float) + 80 * sizeof(DzConst), st>>>(a); }
+    RL_CUDA(cudaGetLastError());
+    return RL_OK;
+  }
   size_t smem = (size_t)(256 * 8) * sizeof(float);
   long work = (a.kind == 0) ? a.npx_out : (a.kind == 1 ? (long)a.B * a.H * a.W : (long)a.B * a.Hp * a.Wp * 9);
   int nchunk = a.nch / 8;
