@@ -133,9 +133,39 @@ __device__ __forceinline__ void dgrad_prefetch(DgradPre& p, const __nv_bfloat16*
 
 // one 128-pixel tile x one channel block; P = this thread's pixel (or -1); S1/S2: per-thread running totals, index =
 // channel group (16 channels), the lane's channel inside the group is (lane >> 1) & 15.  pre[0..1] hold groups 0 and 1.
+// Cross-pixel sums of a warp (32 pixels) for 8 channels x 2 quantities through a private shared-memory scratch:
+// every lane writes its 8+8 values as a row (stride 12 floats: conflict-free 16-byte stores), then lane
+// (up, q, col) = (lane>>4, (lane>>3)&1, lane&7) adds 16 rows of column col of quantity q and the two row halves are
+// combined with one shuffle.  Returns Σ_pixels quantity q of channel col in every lane.
+constexpr int kScrPerWarp = 800;  // floats: gs matrix [32][12] at 0, gx matrix at 400 (16 banks apart)
+__device__ __forceinline__ float warp_colsum8(float* sc, const float* gs, const float* gx, int lane) {
+  float4* w0 = reinterpret_cast<float4*>(sc + lane * 12);
+  float4* w1 = reinterpret_cast<float4*>(sc + 400 + lane * 12);
+  w0[0] = make_float4(gs[0], gs[1], gs[2], gs[3]);
+  w0[1] = make_float4(gs[4], gs[5], gs[6], gs[7]);
+  w1[0] = make_float4(gx[0], gx[1], gx[2], gx[3]);
+  w1[1] = make_float4(gx[4], gx[5], gx[6], gx[7]);
+  __syncwarp();
+  const int col = lane & 7, q = (lane >> 3) & 1, up = lane >> 4;
+  const float* src = sc + q * 400 + col;
+  float acc = 0.f;
+#pragma unroll
+  for (int r = 0; r < 16; ++r) {
+    const int row = up ? 16 + ((r + 6) & 15) : r;  // rotation keeps the four 8-lane groups on disjoint banks
+    acc += src[row * 12];
+  }
+  acc += __shfl_xor_sync(0xffffffffu, acc, 16);
+  __syncwarp();
+  return acc;
+}
+
+// kSmemSums: cross-pixel sums through the shared-memory scratch (fewer instructions; used by the 1x1 kernel) or by
+// shuffle butterflies (no scratch: the 3x3 kernel prefers the shared memory as L1 for its overlapping halo tiles).
+template <bool kSmemSums>
 __device__ __forceinline__ void dgrad_epilogue(uint32_t tmem_acc, int warp, int lane, const __nv_bfloat16* xrow,
                                                __nv_bfloat16* drow, int cbase, int nvalid, const DgradConsts* k,
-                                               const DgradArgs& a, float* S1, float* S2, DgradPre* pre) {
+                                               const DgradArgs& a, float* S1, float* S2, DgradPre* pre, float* s_scr) {
+  float* sc = kSmemSums ? s_scr + warp * kScrPerWarp : nullptr;
 #pragma unroll
   for (int gi = 0; gi < 8; ++gi) {
     const int c0 = gi * 16;
@@ -146,7 +176,7 @@ __device__ __forceinline__ void dgrad_epilogue(uint32_t tmem_acc, int warp, int 
       if (gi + 2 < 8) dgrad_prefetch(pre[gi & 1], xrow, drow, c0 + 32, nvalid, (cbase + c0 + 32) >= a.rmw_from, a.variant);
       // two halves of 8 channels keep the fp32 temporaries small (register budget: 4 CTAs per SM)
       uint4 dpk[2];
-      float r1[2], r2[2];
+      float rs[2];
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         float gs[8], gx[8];
@@ -168,12 +198,17 @@ __device__ __forceinline__ void dgrad_epilogue(uint32_t tmem_acc, int warp, int 
           for (int i = 0; i < 8; ++i) gs[i] = gx[i] = 0.f;
           dpk[h] = make_uint4(0, 0, 0, 0);
         }
-        if (a.variant & 4) {  // triage switch: skip the BN-sum butterflies
-          r1[h] = gs[0];
-          r2[h] = gx[0];
+        if (a.variant & 4) {  // triage switch: skip the cross-pixel sums
+          rs[h] = gs[0] + gx[0];
+        } else if (kSmemSums) {
+          rs[h] = warp_colsum8(sc, gs, gx, lane);
         } else {
-          r1[h] = warp_reduce8(gs, lane);
-          r2[h] = warp_reduce8(gx, lane);
+          // butterflies: lane ends with the total of column (lane >> 2) & 7; lanes with bit 3 of... keep both quantities
+          const float r1 = warp_reduce8(gs, lane), r2 = warp_reduce8(gx, lane);
+          // re-distribute to the (up, q, col) convention of the scratch variant: col = lane & 7, q = (lane >> 3) & 1
+          const int src = (lane & 7) << 2;  // a lane that holds column (lane & 7)
+          const float a1 = __shfl_sync(0xffffffffu, r1, src), a2 = __shfl_sync(0xffffffffu, r2, src);
+          rs[h] = ((lane >> 3) & 1) ? a2 : a1;
         }
       }
       if (xrow != nullptr && !(a.variant & 8)) {
@@ -184,11 +219,11 @@ __device__ __forceinline__ void dgrad_epilogue(uint32_t tmem_acc, int warp, int 
           *reinterpret_cast<uint4*>(drow + c0 + 8) = dpk[1];
         }
       }
-      // lane keeps channel (lane&2 ? 8 : 0) + ((lane >> 2) & 7) of this group
-      S1[gi] += (lane & 2) ? r1[1] : r1[0];
-      S2[gi] += (lane & 2) ? r2[1] : r2[0];
+      // lane (up, q, col) keeps quantity q (0: Σg, 1: Σg(x-mean)) of channel 8*up + col of this group
+      S1[gi] += (lane & 16) ? rs[1] : rs[0];
     }
   }
+  (void)S2;
 }
 
 __device__ __forceinline__ void dgrad_consts_init(DgradConsts* k, float* s_rstd, const DgradArgs& a, int mb) {
@@ -212,14 +247,11 @@ __device__ __forceinline__ void dgrad_flush(float* s_sum /*[2][128]*/, const flo
                                             int nvalid) {
   for (int i = threadIdx.x; i < 256; i += 128) s_sum[i] = 0.f;
   __syncthreads();
-  if ((lane & 1) == 0) {
-    const int cl = ((lane >> 1) & 1) * 8 + ((lane >> 2) & 7);
+  {
+    const int cl = (lane >> 4) * 8 + (lane & 7), q = (lane >> 3) & 1;
 #pragma unroll
     for (int gi = 0; gi < 8; ++gi)
-      if (gi * 16 < nvalid) {
-        atomicAdd(&s_sum[gi * 16 + cl], S1[gi]);
-        atomicAdd(&s_sum[128 + gi * 16 + cl], S2[gi]);
-      }
+      if (gi * 16 < nvalid) atomicAdd(&s_sum[q * 128 + gi * 16 + cl], S1[gi]);
   }
   __syncthreads();
   const int cl = threadIdx.x;
@@ -354,7 +386,7 @@ __global__ void __launch_bounds__(128, 3) dgrad_dense_kernel(DgradArgs a) {
       mbar_wait(&bar_mma, n_mma & 1);
       ++n_mma;
       tc_fence_after();
-      dgrad_epilogue(tmem, warp, lane, xrow, drow, mb * 128, nvalid, kc, a, S1, S2, pre);
+      dgrad_epilogue<false>(tmem, warp, lane, xrow, drow, mb * 128, nvalid, kc, a, S1, S2, pre, nullptr);
       tc_fence_before();
     }
     if (ntiles == 0 && tid == 0) mbar_wait(&bar_w, n_w & 1);
@@ -375,6 +407,7 @@ __global__ void __launch_bounds__(128, 3) dgrad_td_kernel(DgradArgs a) {
   DgradConsts* kcs = reinterpret_cast<DgradConsts*>(smem + 2 * 32768);
   float* s_rstd = reinterpret_cast<float*>(kcs + 1);
   float* s_sum = s_rstd + 128;
+  float* s_scr = s_sum + 256;
   __shared__ uint64_t bar_full[2], bar_done[2];
   __shared__ uint32_t tmem_base_s;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -457,7 +490,7 @@ __global__ void __launch_bounds__(128, 3) dgrad_td_kernel(DgradArgs a) {
         mbar_wait(&bar_done[s], u & 1);
         tc_fence_after();
       }
-      dgrad_epilogue(tmem, warp, lane, xrow, drow, mb * 128, nvalid, kcs, a, S1, S2, pre);
+      dgrad_epilogue<true>(tmem, warp, lane, xrow, drow, mb * 128, nvalid, kcs, a, S1, S2, pre, s_scr);
       tc_fence_before();
       __syncthreads();
     }
@@ -478,8 +511,8 @@ int launch_dgrad(const DgradArgs& a_in, int grid, cudaStream_t st) {
   a.variant = variant;
   static bool configured = false;
   if (!configured) {
-    RL_CUDA(cudaFuncSetAttribute(dgrad_dense_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
-    RL_CUDA(cudaFuncSetAttribute(dgrad_td_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
+    RL_CUDA(cudaFuncSetAttribute(dgrad_dense_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 84 * 1024));
+    RL_CUDA(cudaFuncSetAttribute(dgrad_td_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 84 * 1024));
     configured = true;
   }
   if (a.dense) {
@@ -488,7 +521,7 @@ int launch_dgrad(const DgradArgs& a_in, int grid, cudaStream_t st) {
     { ProfScope _ps(KC_DGRAD_DENSE, st);
   dgrad_dense_kernel<<<grid, 128, smem, st>>>(a); }
   } else {
-    size_t smem = 2 * 32768 + sizeof(DgradConsts) + 384 * sizeof(float);
+    size_t smem = 2 * 32768 + sizeof(DgradConsts) + (384 + 4 * kScrPerWarp) * sizeof(float);
     { ProfScope _ps(KC_DGRAD_TD, st);
   dgrad_td_kernel<<<grid, 128, smem, st>>>(a); }
   }
