@@ -25,6 +25,26 @@ struct ProfScope {
 };
 }  // namespace rl
 
+namespace rl {
+// Programmatic dependent launch: the kernel may start while its stream predecessor is still draining; it must execute
+// pdl_wait() (griddepcontrol.wait) before touching global memory.  Opt-in with RL_PDL=1 (slower on B200 in round 1).
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, args...);
+}
+}  // namespace rl
+
 #define RL_CUDA(expr)                                                                                   \
   do {                                                                                                  \
     cudaError_t _e = (expr);                                                                            \

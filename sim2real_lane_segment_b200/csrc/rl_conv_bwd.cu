@@ -301,6 +301,8 @@ __global__ void __launch_bounds__(128, 3) dgrad_dense_kernel(DgradArgs a) {
     fence_mbar_init();
   }
   if (warp == 0) tmem_alloc(&tmem_base_s, 128);
+  pdl_trigger();
+  pdl_wait();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -423,6 +425,8 @@ __global__ void __launch_bounds__(128, 3) dgrad_td_kernel(DgradArgs a) {
     fence_mbar_init();
   }
   if (warp == 0) tmem_alloc(&tmem_base_s, 128);
+  pdl_trigger();
+  pdl_wait();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -518,14 +522,16 @@ int launch_dgrad(const DgradArgs& a_in, int grid, cudaStream_t st) {
   if (a.dense) {
     if (a.strip_w + 2 > 165) return rl_fail(RL_ERR_SHAPE, "dgrad: strip too wide");
     size_t smem = 36864 + 2 * kDzRows * 16 + sizeof(DgradConsts) + 384 * sizeof(float);
+    const int nmb = (a.Cin + 127) / 128;
+    const long vrows = (long)a.B * (a.H + 1);
+    const bool split = nmb > 1 && vrows * (a.W + 2) <= 40000;  // small level: channel blocks in parallel CTAs (rl_api.cu sizes grid.x accordingly)
     { ProfScope _ps(KC_DGRAD_DENSE, st);
-  dgrad_dense_kernel<<<grid, 128, smem, st>>>(a); }
+    RL_CUDA(launch_pdl(dgrad_dense_kernel, dim3(grid, split ? nmb : 1), dim3(128), smem, st, a)); }
   } else {
     size_t smem = 2 * 32768 + sizeof(DgradConsts) + (384 + 4 * kScrPerWarp) * sizeof(float);
     { ProfScope _ps(KC_DGRAD_TD, st);
-  dgrad_td_kernel<<<grid, 128, smem, st>>>(a); }
+    RL_CUDA(launch_pdl(dgrad_td_kernel, dim3(grid), dim3(128), smem, st, a)); }
   }
-  RL_CUDA(cudaGetLastError());
   return RL_OK;
 }
 
@@ -565,6 +571,8 @@ __global__ void __launch_bounds__(kWgThreads, 2) wgrad_kernel(WgradArgs a) {
     fence_mbar_init();
   }
   if (warp == 0) tmem_alloc(&tmem_base_s, 256);
+  pdl_trigger();
+  pdl_wait();
   if (tid < 128) {
     float s = 0.f, t = 0.f;
     if (a.transform && tid < ca) {
@@ -710,7 +718,7 @@ int launch_wgrad(const WgradArgs& a, int nruns, int nmb, int nparts, cudaStream_
   size_t smem = 1024 + 3 * (16384 + (size_t)npmax * 128);
   if (smem > 160 * 1024) return rl_fail(RL_ERR_SHAPE, "wgrad: smem %zu too large", smem);
   { ProfScope _ps(KC_WGRAD, st);
-  wgrad_kernel<<<dim3(nruns, nmb, nparts), kWgThreads, smem, st>>>(a); }
+  RL_CUDA(launch_pdl(wgrad_kernel, dim3(nruns, nmb, nparts), dim3(kWgThreads), smem, st, a)); }
   RL_CUDA(cudaGetLastError());
   return RL_OK;
 }

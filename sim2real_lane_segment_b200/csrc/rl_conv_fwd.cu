@@ -40,7 +40,6 @@ __global__ void __launch_bounds__(kFwdThreads, 2) dense_fwd_kernel(DenseFwdArgs 
   __shared__ __align__(16) float s_bias16[16];
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  if (tid < 16) s_bias16[tid] = a.bias[tid];
 
   // ---- work item: rows [R0,R1) of the level (all images stacked), columns [x0,x1)
   const int run = blockIdx.x / a.nstrips, strip = blockIdx.x % a.nstrips;
@@ -64,12 +63,15 @@ __global__ void __launch_bounds__(kFwdThreads, 2) dense_fwd_kernel(DenseFwdArgs 
     fence_mbar_init();
   }
   if (warp == 0) tmem_alloc(&tmem_base_s, 256);
+  for (int i = tid; i < 4 * kRing * 4; i += kFwdThreads) zs[i] = 0.f;
+  pdl_trigger();
+  pdl_wait();  // ---- everything above is CTA-local; global memory only from here on
+  if (tid < 16) s_bias16[tid] = a.bias[tid];
   for (int c = tid; c < a.Cin; c += kFwdThreads) {
     BnCoef k = bn_coef(a.bn, c);
     s_s[c] = k.s;
     s_t[c] = k.t;
   }
-  for (int i = tid; i < 4 * kRing * 4; i += kFwdThreads) zs[i] = 0.f;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -306,6 +308,8 @@ __global__ void __launch_bounds__(128, 2) gemm_px_kernel(GemmPxArgs a) {
     fence_mbar_init();
   }
   if (warp == 0) tmem_alloc(&tmem_base_s, 256);
+  pdl_trigger();
+  pdl_wait();
   if (a.transform)
     for (int c = tid; c < a.K; c += 128) {
       BnCoef k = bn_coef(a.bn, c);
@@ -471,8 +475,7 @@ int launch_dense_fwd(const DenseFwdArgs& a, int grid, cudaStream_t st) {
   }
   if (smem > 110 * 1024) return rl_fail(RL_ERR_SHAPE, "dense_fwd: smem %zu too large", smem);
   { ProfScope _ps(KC_DENSE_FWD, st);
-  dense_fwd_kernel<<<grid, kFwdThreads, smem, st>>>(a); }
-  RL_CUDA(cudaGetLastError());
+  RL_CUDA(launch_pdl(dense_fwd_kernel, dim3(grid), dim3(kFwdThreads), smem, st, a)); }
   return RL_OK;
 }
 
@@ -487,8 +490,7 @@ int launch_gemm_px(const GemmPxArgs& a, int grid_x, int nparts, cudaStream_t st)
   }
   if (smem > 110 * 1024) return rl_fail(RL_ERR_SHAPE, "gemm_px: smem %zu too large (K=%d np=%d)", smem, a.K, npmax);
   { ProfScope _ps(KC_GEMM_PX, st);
-  gemm_px_kernel<<<dim3(grid_x, nparts), 128, smem, st>>>(a); }
-  RL_CUDA(cudaGetLastError());
+  RL_CUDA(launch_pdl(gemm_px_kernel, dim3(grid_x, nparts), dim3(128), smem, st, a)); }
   return RL_OK;
 }
 

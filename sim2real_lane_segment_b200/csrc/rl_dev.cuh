@@ -36,7 +36,7 @@ __device__ __forceinline__ BnCoef bn_coef(const BnSrc& b, int c) {
     double v = b.stats[b.Ct + c] * b.inv_n - m * m;
     if (v < 0.0) v = 0.0;
     k.mean = (float)m;
-    k.rstd = (float)(1.0 / sqrt(v + (double)kBnEps));
+    k.rstd = rsqrtf((float)v + kBnEps);  // fp64 only for the cancellation-prone E[x^2] - E[x]^2; fp32 rsqrt afterwards
   }
   k.gamma = b.gamma[rc];
   k.s = k.gamma * k.rstd;

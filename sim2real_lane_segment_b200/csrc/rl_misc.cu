@@ -163,6 +163,8 @@ int launch_first_fwd(const Plan* p, const float* x, const float* params, cudaStr
 __global__ void __launch_bounds__(256) channel_stats_kernel(const __nv_bfloat16* __restrict__ arena, long npx, int Ct,
                                                             int c_off, int nch, double* stats) {
   extern __shared__ float sred[];  // [blockDim][16]
+  pdl_trigger();
+  pdl_wait();
   const int nchunk = nch / 8;
   const int ppb = blockDim.x / nchunk;  // pixel lanes per block
   const int j = threadIdx.x % nchunk, pl = threadIdx.x / nchunk;
@@ -201,8 +203,7 @@ int launch_channel_stats(const __nv_bfloat16* arena, long npx, int Ct, int c_off
   int nchunk = nch / 8, ppb = 256 / nchunk;
   int grid = (int)std::min<long>((npx + ppb - 1) / ppb, (long)sm * 4);
   { ProfScope _ps(KC_STATS, st);
-  channel_stats_kernel<<<grid, 256, 256 * 16 * sizeof(float), st>>>(arena, npx, Ct, c_off, nch, stats); }
-  RL_CUDA(cudaGetLastError());
+  RL_CUDA(launch_pdl(channel_stats_kernel, dim3(grid), dim3(256), 256 * 16 * sizeof(float), st, arena, npx, Ct, c_off, nch, stats)); }
   return RL_OK;
 }
 
@@ -213,6 +214,8 @@ int launch_channel_stats(const __nv_bfloat16* arena, long npx, int Ct, int c_off
 __global__ void __launch_bounds__(256) tu_col2im_kernel(const __nv_bfloat16* __restrict__ ycol, __nv_bfloat16* out,
                                                         const float* __restrict__ bias, int B, int h, int w, int H, int W,
                                                         int Ct, int o_off) {
+  pdl_trigger();
+  pdl_wait();
   const long total = (long)B * H * W * 10;
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
     const int j = (int)(i % 10);
@@ -248,8 +251,7 @@ int launch_tu_col2im(const __nv_bfloat16* ycol, __nv_bfloat16* out, const float*
   long total = (long)B * H * W * 10;
   int grid = (int)std::min<long>((total + 255) / 256, 148L * 16);
   { ProfScope _ps(KC_TU_COL2IM, st);
-  tu_col2im_kernel<<<grid, 256, 0, st>>>(ycol, out, bias, B, h, w, H, W, Ct, o_off); }
-  RL_CUDA(cudaGetLastError());
+  RL_CUDA(launch_pdl(tu_col2im_kernel, dim3(grid), dim3(256), 0, st, ycol, out, bias, B, h, w, H, W, Ct, o_off)); }
   return RL_OK;
 }
 
@@ -529,7 +531,7 @@ __global__ void __launch_bounds__(256) dz_prepare_kernel(DzArgs a) {
     double m = a.stats[gc] * a.inv_n_out, v = a.stats[a.Ct + gc] * a.inv_n_out - m * m;
     if (v < 0) v = 0;
     c_mean[k] = (float)m;
-    c_rstd[k] = (float)(1.0 / sqrt(v + (double)kBnEps));
+    c_rstd[k] = rsqrtf((float)v + kBnEps);
     c_A[k] = (float)(a.acc[gc] * a.inv_n_out);
     c_B[k] = (float)(a.acc[a.Ct + gc] * a.inv_n_out);
     mk[k] = 1.f;
@@ -669,6 +671,8 @@ __device__ __forceinline__ DzConst dz_const(const DzArgs& a, int c) {
 __global__ void __launch_bounds__(256) dz_dense16_kernel(DzArgs a) {
   __shared__ float s_red[8][16];
   __shared__ DzConst s_k[16];
+  pdl_trigger();
+  pdl_wait();
   if (threadIdx.x < 16) s_k[threadIdx.x] = dz_const(a, threadIdx.x);
   __syncthreads();
   DzConst k[16];
@@ -725,6 +729,8 @@ __global__ void __launch_bounds__(256) dz_dense16_kernel(DzArgs a) {
 // TransitionDown output: one thread per (pooled pixel, 8-channel chunk) scatters to the 4 pixels of its 2x2 window
 __global__ void __launch_bounds__(256) dz_td_kernel(DzArgs a) {
   extern __shared__ float sm[];
+  pdl_trigger();
+  pdl_wait();
   const int nchunk = a.nch / 8, ppb = blockDim.x / nchunk;
   const int j = threadIdx.x % nchunk, pl = threadIdx.x / nchunk;
   DzConst* s_k = reinterpret_cast<DzConst*>(sm + 256 * 8);  // [nch]
@@ -809,6 +815,8 @@ __global__ void __launch_bounds__(256) dz_td_kernel(DzArgs a) {
 // image are zero-filled by the threads of the last input row / column.
 __global__ void __launch_bounds__(250) dz_tu_kernel(DzArgs a) {
   extern __shared__ float sm[];
+  pdl_trigger();
+  pdl_wait();
   const int j = threadIdx.x % 10, pl = threadIdx.x / 10;   // 10 chunks of 8 channels, 25 pixel lanes
   const int h = a.Hp, w = a.Wp;
   DzConst* s_k = reinterpret_cast<DzConst*>(sm + 250 * 8);  // [80]
@@ -873,8 +881,7 @@ int launch_dz_prepare(const DzArgs& a, int sm, cudaStream_t st) {
   if (a.kind == 0 && a.planes && a.nch == 16) {
     int grid = (int)std::min<long>((a.npx_out + 255) / 256, (long)sm * 8);
     { ProfScope _ps(KC_DZ_PREPARE, st);
-    dz_dense16_kernel<<<grid, 256, 0, st>>>(a); }
-    RL_CUDA(cudaGetLastError());
+    RL_CUDA(launch_pdl(dz_dense16_kernel, dim3(grid), dim3(256), 0, st, a)); }
     return RL_OK;
   }
   if (a.kind == 1) {
@@ -882,16 +889,14 @@ int launch_dz_prepare(const DzArgs& a, int sm, cudaStream_t st) {
     long npool = (long)a.B * a.Hp * a.Wp;
     int grid = (int)std::max<long>(1, std::min<long>((npool + ppb - 1) / ppb, (long)sm * 8));
     { ProfScope _ps(KC_DZ_PREPARE, st);
-    dz_td_kernel<<<grid, 256, 256 * 8 * sizeof(float) + a.nch * sizeof(DzConst), st>>>(a); }
-    RL_CUDA(cudaGetLastError());
+    RL_CUDA(launch_pdl(dz_td_kernel, dim3(grid), dim3(256), 256 * 8 * sizeof(float) + a.nch * sizeof(DzConst), st, a)); }
     return RL_OK;
   }
   if (a.kind == 2 && a.nch == 80) {
     long nout = (long)a.B * a.H * a.W;
     int grid = (int)std::max<long>(1, std::min<long>((nout + 24) / 25, (long)sm * 8));
     { ProfScope _ps(KC_DZ_PREPARE, st);
-    dz_tu_kernel<<<grid, 250, 250 * 8 * sizeof(float) + 80 * sizeof(DzConst), st>>>(a); }
-    RL_CUDA(cudaGetLastError());
+    RL_CUDA(launch_pdl(dz_tu_kernel, dim3(grid), dim3(250), 250 * 8 * sizeof(float) + 80 * sizeof(DzConst), st, a)); }
     return RL_OK;
   }
   size_t smem = (size_t)(256 * 8) * sizeof(float);
