@@ -1,4 +1,5 @@
 // rl_api.cu — extern "C" boundary (include/rightlane.h) and the host-side layer schedule.
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -62,7 +63,16 @@ int rl_plan_create(rl_plan** out, int B, int H, int W, int num_cls, int training
   return RL_OK;
 }
 
-void rl_plan_destroy(rl_plan* h) { delete h; }
+void rl_plan_destroy(rl_plan* h) {
+  if (!h) return;
+  Plan& p = h->p;
+  for (int i = 0; i < 2; ++i) {
+    if (p.ev_dz[i]) cudaEventDestroy((cudaEvent_t)p.ev_dz[i]);
+    if (p.ev_wg[i]) cudaEventDestroy((cudaEvent_t)p.ev_wg[i]);
+  }
+  if (p.side_stream) cudaStreamDestroy((cudaStream_t)p.side_stream);
+  delete h;
+}
 long rl_plan_workspace_bytes(const rl_plan* h) { return h ? (long)h->p.ws_bytes : 0; }
 long rl_plan_num_params(const rl_plan* h) { return h ? h->p.n_params : 0; }
 long rl_plan_num_bn_buffers(const rl_plan* h) { return h ? h->p.n_bnbuf : 0; }
@@ -141,6 +151,18 @@ int rl_plan_bind(rl_plan* h, void* workspace, void* stream) {
   p.n_bn = (int)bt.size();
   RL_CUDA(cudaMemcpyAsync(wsb(&p) + p.bntab_off, bt.data(), bt.size() * sizeof(BnTabEntry), cudaMemcpyHostToDevice, st));
   if (p.training && p.dzp_bytes) RL_CUDA(cudaMemsetAsync(wsb(&p) + p.dzp_off_all, 0, p.dzp_bytes, st));
+  if (p.training && !p.side_stream) {
+    cudaStream_t s2;
+    RL_CUDA(cudaStreamCreateWithFlags(&s2, cudaStreamNonBlocking));
+    p.side_stream = s2;
+    for (int i = 0; i < 2; ++i) {
+      cudaEvent_t e;
+      RL_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+      p.ev_dz[i] = e;
+      RL_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+      p.ev_wg[i] = e;
+    }
+  }
   RL_CUDA(cudaStreamSynchronize(st));  // host vectors go out of scope
   // dropout scales default to 1 (no dropout)
   return rl_set_dropout(h, 0.f, 0, 0, stream);
@@ -313,8 +335,8 @@ int rl_sgd_nesterov_step(float* params, const float* grads, float* buf, long n, 
 // ------------------------------------------------------------------------------------------------
 // backward schedule: reverse of the forward layer list
 // ------------------------------------------------------------------------------------------------
-static int wgrad_runs(const Plan* p, long npx, int nmb, int nparts, long* px_per_cta) {
-  long want = std::max(1L, (long)(2 * p->sm_count) / std::max(1, nmb * nparts));
+static int wgrad_runs(const Plan* p, long npx, int nmb, int nparts, long* px_per_cta, int ctas_per_sm = 2) {
+  long want = std::max(1L, (long)(ctas_per_sm * p->sm_count) / std::max(1, nmb * nparts));
   long chunks = (npx + 63) / 64;
   long runs = std::min(want, chunks);
   long cpr = (chunks + runs - 1) / runs;
@@ -333,6 +355,24 @@ extern "C" int rl_backward(rl_plan* h, const float* params, const float* x, floa
   int rc;
   RL_CUDA(cudaMemsetAsync(wsb(p) + p->acc_off_all, 0, p->acc_bytes, st));
   __nv_bfloat16* tmp = (__nv_bfloat16*)(wsb(p) + p->tmp_off);
+  // DenseLayer weight gradients run on a side stream, concurrently with the dz_prepare -> dgrad chain of the following
+  // layers (they only share read-only inputs); RL_OVERLAP=0 keeps everything on the caller's stream.
+  static int overlap = -1;
+  if (overlap < 0) {
+    const char* e = getenv("RL_OVERLAP");
+    overlap = (e && e[0] == '0') ? 0 : 1;
+  }
+  cudaStream_t st2 = overlap ? (cudaStream_t)p->side_stream : st;
+  // CTAs per SM the two concurrent kernels are sized for (tuning knobs; co-residency: 2 x 56 KB + 1 x 105 KB of smem)
+  static int dg_ctas = -1, wg_ctas = -1;
+  if (dg_ctas < 0) {
+    const char* e = getenv("RL_DG_CTAS");
+    dg_ctas = e ? atoi(e) : 3;
+    e = getenv("RL_WG_CTAS");
+    wg_ctas = e ? atoi(e) : 2;
+  }
+  int dense_count = 0;
+  p->ev_wg_used[0] = p->ev_wg_used[1] = false;
   {  // classifier weight gradient: dW[k, c] = sum_p dl[p, k] * f[p, c]
     WgradArgs w;
     memset(&w, 0, sizeof(w));
@@ -378,13 +418,19 @@ extern "C" int rl_backward(rl_plan* h, const float* params, const float* x, floa
     if (L.type == L_DENSE) {
       z.kind = 0;
       z.mask = (const float*)(wsb(p) + L.mask_off);
+      const int q = dense_count++ & 1;  // dz buffer of this layer
       z.planes = 1;
-      z.dz = (__nv_bfloat16*)(wsb(p) + lin.dzp_off);
+      z.dz = (__nv_bfloat16*)(wsb(p) + lin.dzp_off + (size_t)q * lin.dzp_npos * 32);
       z.dz_npos = lin.dzp_npos;
       z.dz_guard = lin.dzp_guard;
       z.H = lin.H;
       z.W = lin.W;
+      if (overlap && p->ev_wg_used[q]) RL_CUDA(cudaStreamWaitEvent(st, (cudaEvent_t)p->ev_wg[q], 0));  // buffer q free again
       if ((rc = launch_dz_prepare(z, sm, st))) return rc;
+      if (overlap) {
+        RL_CUDA(cudaEventRecord((cudaEvent_t)p->ev_dz[q], st));
+        RL_CUDA(cudaStreamWaitEvent(st2, (cudaEvent_t)p->ev_dz[q], 0));
+      }
       DgradArgs d;
       memset(&d, 0, sizeof(d));
       d.dense = 1;
@@ -411,7 +457,7 @@ extern "C" int rl_backward(rl_plan* h, const float* params, const float* x, floa
       // small levels run their channel blocks in parallel CTAs (launch_dgrad splits over grid.y): keep one wave in total
       const int nmb_d = (L.cin + 127) / 128;
       const bool split = nmb_d > 1 && (long)vrows * (lin.W + 2) <= 40000;
-      int nruns = std::max(1, std::min(vrows, (3 * sm) / (d.nstrips * (split ? nmb_d : 1))));
+      int nruns = std::max(1, std::min(vrows, (dg_ctas * sm) / (d.nstrips * (split ? nmb_d : 1))));
       d.vrows_per_cta = (vrows + nruns - 1) / nruns;
       nruns = (vrows + d.vrows_per_cta - 1) / d.vrows_per_cta;
       if ((rc = launch_dgrad(d, nruns * d.nstrips, st))) return rc;
@@ -437,8 +483,12 @@ extern "C" int rl_backward(rl_plan* h, const float* params, const float* x, floa
       w.Cin_w = L.cin;
       w.cs_perm = L.cs_perm;
       const int nmb = (L.cin + 127) / 128;
-      int wr = wgrad_runs(p, w.npx, nmb, 1, &w.px_per_cta);
-      if ((rc = launch_wgrad(w, wr, nmb, 1, st))) return rc;
+      int wr = wgrad_runs(p, w.npx, nmb, 1, &w.px_per_cta, wg_ctas);
+      if ((rc = launch_wgrad(w, wr, nmb, 1, st2))) return rc;
+      if (overlap) {
+        RL_CUDA(cudaEventRecord((cudaEvent_t)p->ev_wg[q], st2));
+        p->ev_wg_used[q] = true;
+      }
     } else if (L.type == L_TD) {
       z.kind = 1;
       z.mask = (const float*)(wsb(p) + L.mask_off);
@@ -559,5 +609,8 @@ extern "C" int rl_backward(rl_plan* h, const float* params, const float* x, floa
       if ((rc = launch_wgrad(w, wr, 1, 1, st))) return rc;
     }
   }
+  if (overlap)  // join: every weight gradient is complete before the caller's stream continues (optimizer, all-reduce)
+    for (int q = 0; q < 2; ++q)
+      if (p->ev_wg_used[q]) RL_CUDA(cudaStreamWaitEvent(st, (cudaEvent_t)p->ev_wg[q], 0));
   return RL_OK;
 }

@@ -30,6 +30,9 @@ int build_plan(Plan* p, int B, int H, int W, int num_cls, int training) {
   p->num_cls = num_cls;
   p->training = training != 0;
   p->ws = nullptr;
+  p->side_stream = nullptr;
+  p->ev_dz[0] = p->ev_dz[1] = p->ev_wg[0] = p->ev_wg[1] = nullptr;
+  p->ev_wg_used[0] = p->ev_wg_used[1] = false;
   p->err[0] = 0;
   if (B < 1 || H < 32 || W < 32 || num_cls < 2 || num_cls > 4) {
     snprintf(p->err, sizeof(p->err), "unsupported shape B=%d H=%d W=%d num_cls=%d (need H,W>=32, 2<=C<=4)", B, H, W,
@@ -192,7 +195,7 @@ int build_plan(Plan* p, int B, int H, int W, int num_cls, int training) {
     Level& L = p->lv[l];
     L.dzp_guard = L.W + 3;
     L.dzp_npos = L.dzp_guard + (long)B * (L.H + 1) * (L.W + 2) + 128 + 2 * (L.W + 2) + 8;
-    L.dzp_off = training ? carve((size_t)L.dzp_npos * 32) : 0;
+    L.dzp_off = training ? carve((size_t)L.dzp_npos * 32 * 2) : 0;
   }
   p->dzp_bytes = ws - p->dzp_off_all;
   p->dl_bytes = training ? (size_t)p->lv[0].px * 16 * 2 : 0;

@@ -39,8 +39,8 @@ struct Level {
   long px;                       // B*H*W
   // zero-padded planes of the 16-channel output gradient of a DenseLayer (training):
   // two planes [npos][8] bf16; position(b,y,x) = guard + (b*(H+1)+y)*(W+2) + x+1; pads are never written
-  size_t dzp_off;
-  long dzp_npos, dzp_guard;
+  size_t dzp_off;                // two buffers of 2 planes each (alternate DenseLayers of the level use alternate buffers,
+  long dzp_npos, dzp_guard;      // so a layer's weight gradient can still read its dz while the next layer's is written)
 };
 
 struct Layer {
@@ -88,6 +88,10 @@ struct Plan {
   size_t xcol_off;                    // first conv: bf16 im2col rows [px0][32] kept for its weight gradient
   size_t ws_bytes;
   void* ws;                           // bound workspace (device)
+  void* side_stream;                  // cudaStream_t: DenseLayer weight gradients run here, concurrently with the dgrad chain
+  void* ev_dz[2];                     // cudaEvent_t: dz planes of buffer q written (main stream)
+  void* ev_wg[2];                     // cudaEvent_t: weight gradient that read buffer q finished (side stream)
+  bool ev_wg_used[2];
   bool training;                      // arenas for gradients present
   char err[256];
 };
