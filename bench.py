@@ -118,6 +118,30 @@ def conv_flops_per_image(H, W):
     return f
 
 
+def synthetic_batch(B, H, W, num_cls, seed):
+    """Duckietown-shaped synthetic data: x ~ N(0,1) like post-Normalize images, y a piecewise-constant
+    4-class map (background, right-lane trapezoid, left-lane trapezoid, obstacle blob) so classes are spatially coherent."""
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(B, 3, H, W, generator=g)
+    y = torch.zeros(B, H, W, dtype=torch.int64)
+    ys = torch.arange(H).view(H, 1).float()
+    xs = torch.arange(W).view(1, W).float()
+    r = torch.rand(B, 6, generator=g)
+    for b in range(B):
+        top = H * (0.45 + 0.1 * float(r[b, 0]))
+        cx = W * (0.35 + 0.3 * float(r[b, 1]))
+        half = W * (0.03 + 0.22 * ((ys - top) / max(H - top, 1)).clamp(0, 1))
+        low = ys >= top
+        y[b][low & (xs >= cx) & (xs < cx + 2 * half)] = 1
+        if num_cls > 2:
+            y[b][low & (xs < cx) & (xs >= cx - 2 * half)] = 2
+        if num_cls > 3 and float(r[b, 2]) > 0.3:
+            oy, ox = H * (0.5 + 0.4 * float(r[b, 3])), W * float(r[b, 4])
+            y[b][((ys - oy) ** 2 + (xs - ox) ** 2) < (0.06 * H) ** 2] = 3
+    return x, y
+
+
 # ------------------------------------------------------------------------------------------------ reference arm
 def run_reference(args, rank):
     """The reference's own CPU path.  Its model code cannot travel to the GPU box (/root/reference is absent there) and
@@ -177,11 +201,10 @@ def run_b200(args, rank, world, local_rank):
     L.rl_launch_count.restype = ctypes.c_long
 
     # synthetic data: a few distinct batches, per-rank seed
-    from oracle import steps as osteps  # data generator only (test infrastructure reused for synthetic inputs)
     nb = 4
     host = []
     for i in range(nb):
-        x, y = osteps.synthetic_batch(B, H, W, C, seed=42 + rank * 100 + i)
+        x, y = synthetic_batch(B, H, W, C, seed=42 + rank * 100 + i)
         host.append((x.pin_memory(), y.pin_memory()))
     devb = [(x.to(dev), y.to(dev)) for x, y in host]
 
@@ -298,7 +321,8 @@ def run_b200(args, rank, world, local_rank):
     # ---- CPU baseline (oracle port) on a bounded sample, rank 0 at N=1 only
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        from oracle import fcdensenet as net
+        from oracle import fcdensenet as net      # cpu_baseline leg: the only place this arm touches oracle/
+        from oracle import steps as osteps
         cores = os.cpu_count() or 1
         torch.set_num_threads(cores)
         sd = net.init_state_dict(num_cls=C, seed=42)
