@@ -106,6 +106,10 @@ int rl_profile_begin(void);
 int rl_profile_end(double* ms, long* launches);
 int rl_profile_launches(float* ms, int* kernel_class, int max); /* per-launch times of the last profiled region */
 
+/* runtime switches: "overlap" (default 1) runs the DenseLayer weight-gradient kernels of rl_backward on a plan-owned
+ * side stream concurrently with the input-gradient chain (joined before rl_backward returns control of the stream). */
+int rl_set_option(const char* name, int value);
+
 /* test hook: one 128 x N x K tcgen05 GEMM through the shared-memory operand conventions of csrc/rl_umma.cuh */
 int rl_selftest_umma(const void* A, int a_rows, int a_cols, int a_mn_major, int a_row_shift, const void* B, int b_rows,
                      int b_cols, int b_mn_major, int b_row_shift, int N, int K, float* D, int bulk_b, void* stream);

@@ -335,6 +335,8 @@ int rl_sgd_nesterov_step(float* params, const float* grads, float* buf, long n, 
 // ------------------------------------------------------------------------------------------------
 // backward schedule: reverse of the forward layer list
 // ------------------------------------------------------------------------------------------------
+static int g_overlap = -1;  // DenseLayer weight gradients on the plan's side stream (RL_OVERLAP env / rl_set_option)
+
 static int wgrad_runs(const Plan* p, long npx, int nmb, int nparts, long* px_per_cta, int ctas_per_sm = 2) {
   long want = std::max(1L, (long)(ctas_per_sm * p->sm_count) / std::max(1, nmb * nparts));
   long chunks = (npx + 63) / 64;
@@ -357,11 +359,11 @@ extern "C" int rl_backward(rl_plan* h, const float* params, const float* x, floa
   __nv_bfloat16* tmp = (__nv_bfloat16*)(wsb(p) + p->tmp_off);
   // DenseLayer weight gradients run on a side stream, concurrently with the dz_prepare -> dgrad chain of the following
   // layers (they only share read-only inputs); RL_OVERLAP=0 keeps everything on the caller's stream.
-  static int overlap = -1;
-  if (overlap < 0) {
+  if (g_overlap < 0) {
     const char* e = getenv("RL_OVERLAP");
-    overlap = (e && e[0] == '0') ? 0 : 1;
+    g_overlap = (e && e[0] == '0') ? 0 : 1;
   }
+  const int overlap = g_overlap;
   cudaStream_t st2 = overlap ? (cudaStream_t)p->side_stream : st;
   // CTAs per SM the two concurrent kernels are sized for (tuning knobs; co-residency: 2 x 56 KB + 1 x 105 KB of smem)
   static int dg_ctas = -1, wg_ctas = -1;
@@ -613,4 +615,12 @@ extern "C" int rl_backward(rl_plan* h, const float* params, const float* x, floa
     for (int q = 0; q < 2; ++q)
       if (p->ev_wg_used[q]) RL_CUDA(cudaStreamWaitEvent(st, (cudaEvent_t)p->ev_wg[q], 0));
   return RL_OK;
+}
+
+extern "C" int rl_set_option(const char* name, int value) {
+  if (name && strcmp(name, "overlap") == 0) {
+    g_overlap = value ? 1 : 0;
+    return RL_OK;
+  }
+  return rl_fail(RL_ERR_ARG, "rl_set_option: unknown option");
 }

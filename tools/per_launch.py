@@ -15,6 +15,7 @@ def step(i):
     opt.zero_grad(); l = m.training_step((x, y), i); l.backward(); opt.step()
 for i in range(3): step(i)
 L = _lib.lib()
+L.rl_set_option(b'overlap', 0)
 L.rl_profile_begin(); step(0)
 msb = (ctypes.c_double * 13)(); lnb = (ctypes.c_long * 13)()
 L.rl_profile_end(msb, lnb)
