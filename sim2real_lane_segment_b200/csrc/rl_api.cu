@@ -66,7 +66,7 @@ int rl_plan_create(rl_plan** out, int B, int H, int W, int num_cls, int training
 void rl_plan_destroy(rl_plan* h) {
   if (!h) return;
   Plan& p = h->p;
-  for (int i = 0; i < 2; ++i) {
+  for (int i = 0; i < 4; ++i) {
     if (p.ev_dz[i]) cudaEventDestroy((cudaEvent_t)p.ev_dz[i]);
     if (p.ev_wg[i]) cudaEventDestroy((cudaEvent_t)p.ev_wg[i]);
   }
@@ -155,7 +155,7 @@ int rl_plan_bind(rl_plan* h, void* workspace, void* stream) {
     cudaStream_t s2;
     RL_CUDA(cudaStreamCreateWithFlags(&s2, cudaStreamNonBlocking));
     p.side_stream = s2;
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < 4; ++i) {
       cudaEvent_t e;
       RL_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
       p.ev_dz[i] = e;
@@ -373,8 +373,28 @@ extern "C" int rl_backward(rl_plan* h, const float* params, const float* x, floa
     e = getenv("RL_WG_CTAS");
     wg_ctas = e ? atoi(e) : 2;
   }
-  int dense_count = 0;
-  p->ev_wg_used[0] = p->ev_wg_used[1] = false;
+  int dense_count = 0, other_count = 0;
+  for (int i = 0; i < 4; ++i) p->ev_wg_used[i] = false;
+  const size_t tmp_stride = (p->tmp_bytes + 1023) / 1024 * 1024;
+  // fork / join helpers for a weight gradient that reads dz buffer q on the side stream
+  auto before_dz = [&](int q) -> int {
+    if (overlap && p->ev_wg_used[q]) RL_CUDA(cudaStreamWaitEvent(st, (cudaEvent_t)p->ev_wg[q], 0));  // buffer q free again
+    return RL_OK;
+  };
+  auto after_dz = [&](int q) -> int {
+    if (overlap) {
+      RL_CUDA(cudaEventRecord((cudaEvent_t)p->ev_dz[q], st));
+      RL_CUDA(cudaStreamWaitEvent(st2, (cudaEvent_t)p->ev_dz[q], 0));
+    }
+    return RL_OK;
+  };
+  auto after_wg = [&](int q) -> int {
+    if (overlap) {
+      RL_CUDA(cudaEventRecord((cudaEvent_t)p->ev_wg[q], st2));
+      p->ev_wg_used[q] = true;
+    }
+    return RL_OK;
+  };
   {  // classifier weight gradient: dW[k, c] = sum_p dl[p, k] * f[p, c]
     WgradArgs w;
     memset(&w, 0, sizeof(w));
@@ -414,6 +434,11 @@ extern "C" int rl_backward(rl_plan* h, const float* params, const float* x, floa
     z.npx_out = lout.px;
     z.inv_n_out = 1.0 / (double)lout.px;
     z.HW_out = lout.H * lout.W;
+    int tq = 2;
+    if (L.type != L_DENSE) {
+      tq = 2 + (other_count++ & 1);
+      tmp = (__nv_bfloat16*)(wsb(p) + p->tmp_off + (size_t)(tq - 2) * tmp_stride);
+    }
     z.dz = tmp;
     z.g_bias = grads + L.p_b;
     z.B = p->B;
@@ -427,12 +452,9 @@ extern "C" int rl_backward(rl_plan* h, const float* params, const float* x, floa
       z.dz_guard = lin.dzp_guard;
       z.H = lin.H;
       z.W = lin.W;
-      if (overlap && p->ev_wg_used[q]) RL_CUDA(cudaStreamWaitEvent(st, (cudaEvent_t)p->ev_wg[q], 0));  // buffer q free again
+      if ((rc = before_dz(q))) return rc;
       if ((rc = launch_dz_prepare(z, sm, st))) return rc;
-      if (overlap) {
-        RL_CUDA(cudaEventRecord((cudaEvent_t)p->ev_dz[q], st));
-        RL_CUDA(cudaStreamWaitEvent(st2, (cudaEvent_t)p->ev_dz[q], 0));
-      }
+      if ((rc = after_dz(q))) return rc;
       DgradArgs d;
       memset(&d, 0, sizeof(d));
       d.dense = 1;
@@ -487,10 +509,7 @@ extern "C" int rl_backward(rl_plan* h, const float* params, const float* x, floa
       const int nmb = (L.cin + 127) / 128;
       int wr = wgrad_runs(p, w.npx, nmb, 1, &w.px_per_cta, wg_ctas);
       if ((rc = launch_wgrad(w, wr, nmb, 1, st2))) return rc;
-      if (overlap) {
-        RL_CUDA(cudaEventRecord((cudaEvent_t)p->ev_wg[q], st2));
-        p->ev_wg_used[q] = true;
-      }
+      if ((rc = after_wg(q))) return rc;
     } else if (L.type == L_TD) {
       z.kind = 1;
       z.mask = (const float*)(wsb(p) + L.mask_off);
@@ -499,7 +518,9 @@ extern "C" int rl_backward(rl_plan* h, const float* params, const float* x, floa
       z.W = lin.W;
       z.Hp = lout.H;
       z.Wp = lout.W;
+      if ((rc = before_dz(tq))) return rc;
       if ((rc = launch_dz_prepare(z, sm, st))) return rc;
+      if ((rc = after_dz(tq))) return rc;
       DgradArgs d;
       memset(&d, 0, sizeof(d));
       d.dense = 0;
@@ -540,14 +561,17 @@ extern "C" int rl_backward(rl_plan* h, const float* params, const float* x, floa
       w.Cin_w = L.cin;
       const int nmb = (L.cin + 127) / 128;
       int wr = wgrad_runs(p, w.npx, nmb, nparts, &w.px_per_cta);
-      if ((rc = launch_wgrad(w, wr, nmb, nparts, st))) return rc;
+      if ((rc = launch_wgrad(w, wr, nmb, nparts, st2))) return rc;
+      if ((rc = after_wg(tq))) return rc;
     } else if (L.type == L_TU) {
       z.kind = 2;
       z.H = lout.H;
       z.W = lout.W;
       z.Hp = lin.H;
       z.Wp = lin.W;
+      if ((rc = before_dz(tq))) return rc;
       if ((rc = launch_dz_prepare(z, sm, st))) return rc;
+      if ((rc = after_dz(tq))) return rc;
       GemmPxArgs a;
       memset(&a, 0, sizeof(a));
       a.A = tmp;
@@ -587,9 +611,11 @@ extern "C" int rl_backward(rl_plan* h, const float* params, const float* x, floa
       w.W = lin.W;
       w.gw = grads + L.p_w;
       int wr = wgrad_runs(p, w.npx, 1, 3, &w.px_per_cta);
-      if ((rc = launch_wgrad(w, wr, 1, 3, st))) return rc;
+      if ((rc = launch_wgrad(w, wr, 1, 3, st2))) return rc;
+      if ((rc = after_wg(tq))) return rc;
     } else {  // L_FIRST: weight gradient only (the image needs no gradient)
       z.kind = 0;
+      if ((rc = before_dz(tq))) return rc;
       if ((rc = launch_dz_prepare(z, sm, st))) return rc;
       WgradArgs w;
       memset(&w, 0, sizeof(w));
@@ -612,7 +638,7 @@ extern "C" int rl_backward(rl_plan* h, const float* params, const float* x, floa
     }
   }
   if (overlap)  // join: every weight gradient is complete before the caller's stream continues (optimizer, all-reduce)
-    for (int q = 0; q < 2; ++q)
+    for (int q = 0; q < 4; ++q)
       if (p->ev_wg_used[q]) RL_CUDA(cudaStreamWaitEvent(st, (cudaEvent_t)p->ev_wg[q], 0));
   return RL_OK;
 }

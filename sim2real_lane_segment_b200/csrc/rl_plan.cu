@@ -31,8 +31,10 @@ int build_plan(Plan* p, int B, int H, int W, int num_cls, int training) {
   p->training = training != 0;
   p->ws = nullptr;
   p->side_stream = nullptr;
-  p->ev_dz[0] = p->ev_dz[1] = p->ev_wg[0] = p->ev_wg[1] = nullptr;
-  p->ev_wg_used[0] = p->ev_wg_used[1] = false;
+  for (int i = 0; i < 4; ++i) {
+    p->ev_dz[i] = p->ev_wg[i] = nullptr;
+    p->ev_wg_used[i] = false;
+  }
   p->err[0] = 0;
   if (B < 1 || H < 32 || W < 32 || num_cls < 2 || num_cls > 4) {
     snprintf(p->err, sizeof(p->err), "unsupported shape B=%d H=%d W=%d num_cls=%d (need H,W>=32, 2<=C<=4)", B, H, W,
@@ -188,7 +190,7 @@ int build_plan(Plan* p, int B, int H, int W, int num_cls, int training) {
     if (need > tmp) tmp = need;
   }
   p->tmp_bytes = tmp;
-  p->tmp_off = carve(tmp);
+  p->tmp_off = carve(training ? 2 * align_up(tmp, 1024) : tmp);  // training: two buffers (side-stream weight gradients)
   p->xcol_off = training ? carve((size_t)p->lv[0].px * 32 * 2) : 0;
   p->dzp_off_all = ws;
   for (int l = 0; l < kLevels; ++l) {

@@ -89,9 +89,9 @@ struct Plan {
   size_t ws_bytes;
   void* ws;                           // bound workspace (device)
   void* side_stream;                  // cudaStream_t: DenseLayer weight gradients run here, concurrently with the dgrad chain
-  void* ev_dz[2];                     // cudaEvent_t: dz planes of buffer q written (main stream)
-  void* ev_wg[2];                     // cudaEvent_t: weight gradient that read buffer q finished (side stream)
-  bool ev_wg_used[2];
+  void* ev_dz[4];                     // cudaEvent_t: dz buffer q written (main stream); 0,1: DenseLayer planes, 2,3: scratch
+  void* ev_wg[4];                     // cudaEvent_t: weight gradient that read buffer q finished (side stream)
+  bool ev_wg_used[4];
   bool training;                      // arenas for gradients present
   char err[256];
 };
