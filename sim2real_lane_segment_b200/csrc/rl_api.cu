@@ -151,6 +151,12 @@ int rl_plan_bind(rl_plan* h, void* workspace, void* stream) {
   p.n_bn = (int)bt.size();
   RL_CUDA(cudaMemcpyAsync(wsb(&p) + p.bntab_off, bt.data(), bt.size() * sizeof(BnTabEntry), cudaMemcpyHostToDevice, st));
   if (p.training && p.dzp_bytes) RL_CUDA(cudaMemsetAsync(wsb(&p) + p.dzp_off_all, 0, p.dzp_bytes, st));
+  // ---- tensor maps of the level arenas (activation tiles of the DenseLayer forward go through the TMA engine)
+  p.tmap_ok = true;
+  for (int l = 0; l < kLevels; ++l) {
+    int rc = encode_arena_tmap(p.tmap_act[l], act_of(&p, l), p.lv[l].px, p.lv[l].Ct);
+    if (rc) return rc;
+  }
   if (p.training && !p.side_stream) {
     cudaStream_t s2;
     RL_CUDA(cudaStreamCreateWithFlags(&s2, cudaStreamNonBlocking));
@@ -180,6 +186,12 @@ int rl_set_dropout(rl_plan* h, float p_drop, unsigned long long seed, unsigned l
                            step, (cudaStream_t)stream);
 }
 
+// DenseLayer forward through the tensor-map TMA kernel (RL_FWD_TMA=0 selects the register-staged kernel)
+static const bool g_fwd_tma = []() {
+  const char* e = getenv("RL_FWD_TMA");
+  return !(e && e[0] == '0');
+}();
+
 int rl_forward(rl_plan* h, const float* params, const float* bnbuf, const float* x, int train, void* stream) {
   if (!h || !h->p.ws) return rl_fail(RL_ERR_STATE, "rl_forward: plan not bound");
   if (!params || !x || (!train && !bnbuf)) return rl_fail(RL_ERR_ARG, "rl_forward: null argument");
@@ -205,7 +217,8 @@ int rl_forward(rl_plan* h, const float* params, const float* bnbuf, const float*
       a.rows_total = p->B * li.H;
       a.strip_w = 160;
       a.nstrips = (li.W + a.strip_w - 1) / a.strip_w;
-      int nruns = std::max(1, std::min(a.rows_total, (2 * sm) / a.nstrips));
+      const bool use_tma = g_fwd_tma && a.nstrips == 1 && p->tmap_ok;
+      int nruns = std::max(1, std::min(a.rows_total, ((use_tma ? 1 : 2) * sm) / a.nstrips));
       a.rows_per_cta = (a.rows_total + nruns - 1) / nruns;
       nruns = (a.rows_total + a.rows_per_cta - 1) / a.rows_per_cta;
       a.wpk = wsb(p) + L.wpk_fwd;
@@ -213,7 +226,9 @@ int rl_forward(rl_plan* h, const float* params, const float* bnbuf, const float*
       a.mask = train ? (const float*)(wsb(p) + L.mask_off) : nullptr;
       a.bn = make_bn(p, L, params, bnbuf, train);
       a.stats_out = train ? stats_of(p, L.lvl_in) : nullptr;
-      if ((rc = launch_dense_fwd(a, nruns * a.nstrips, st))) return rc;
+      if (use_tma) {
+        if ((rc = launch_dense_fwd_tma(a, p->tmap_act[L.lvl_in], nruns, st))) return rc;
+      } else if ((rc = launch_dense_fwd(a, nruns * a.nstrips, st))) return rc;
     } else if (L.type == L_TD) {
       GemmPxArgs a;
       memset(&a, 0, sizeof(a));

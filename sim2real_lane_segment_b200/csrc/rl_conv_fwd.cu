@@ -9,6 +9,9 @@
 // The growth-16 convolution is computed "taps-as-N": one GEMM  Y[p, (tap,co)] = Σ_c relu(bn(x))[p,c] · W[(tap,co), c]
 // with N = 9*16 = 144 and K = Cin, so every activation is read exactly once and never needs a halo; the
 // 3x3 structure is resolved on the 16-channel side by a shift-add (col2im) of the 9 tap planes in shared memory.
+#include <cuda.h>
+#include <string.h>
+
 #include "rl_common.cuh"
 #include "rl_dev.cuh"
 #include "rl_kernels.h"
@@ -275,6 +278,352 @@ __global__ void __launch_bounds__(kFwdThreads, 2) dense_fwd_kernel(DenseFwdArgs 
   tc_fence_before();
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem, 256);
+}
+
+// ================================================================================================
+// dense_fwd_tma_kernel — the same layer, fed by the tensor-map TMA engine.  One CTA per SM, 10 warps:
+//   warp 9     : activation producer. One lane issues cp.async.bulk.tensor.2d (128 pixels x 64 channels, 128-byte
+//                swizzle) into a 6-deep ring: up to 96 KB of raw activations in flight per SM with no registers held.
+//   warps 0-3  : BN+ReLU in place on a landed stage (LDS.128 -> fma/relu -> STS.128 at the same address; a thread's
+//                8-channel group is the same for all of its 8 rows, so s/t are fetched once per stage).
+//   warp 8     : weight chunks by 1-D bulk TMA (3-deep ring) and tcgen05.mma issue (A: SWIZZLE_128B K-major straight
+//                from the tensor-map layout, B: the packed chunk layout), two 144-column accumulators in TMEM.
+//   warps 4-7  : epilogue (col2im of the 9 tap planes, bias, Dropout2d scale, concat-slice store, Σx, Σx²) of tile i
+//                while the other roles are already on tile i+1.
+// Requires a full-width strip (W <= 160): the 128 input pixels of a tile are then 128 consecutive arena rows.
+// ================================================================================================
+constexpr int kF2Threads = 320;
+constexpr int kF2A = 6, kF2W = 3;
+constexpr int kF2ABytes = 16384, kF2WBytes = 18432;
+
+struct alignas(64) DenseFwdTmaArgs {
+  CUtensorMap tmap;
+  DenseFwdArgs a;
+};
+
+__device__ __forceinline__ void epilogue_sync() { asm volatile("bar.sync 2, 128;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* tm, int c0, int c1, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+// K-major operand in the canonical 128-byte-swizzle layout (rows of 64 bf16, 8-row atoms 1024 B apart)
+__device__ __forceinline__ uint64_t desc_sw128_kmajor(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFFu);
+  d |= (uint64_t)1 << 16;             // LBO: unused for swizzled K-major
+  d |= (uint64_t)(1024u >> 4) << 32;  // SBO
+  d |= (uint64_t)1 << 46;             // descriptor version
+  d |= (uint64_t)2 << 61;             // SWIZZLE_128B
+  return d;
+}
+
+__global__ void __launch_bounds__(kF2Threads, 1) dense_fwd_tma_kernel(const __grid_constant__ DenseFwdTmaArgs P) {
+  const DenseFwdArgs& a = P.a;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // SWIZZLE_128B atoms want 1024-byte alignment
+  uint8_t* sA = smem;
+  uint8_t* sW = smem + kF2A * kF2ABytes;
+  float* zs = reinterpret_cast<float*>(sW + kF2W * kF2WBytes);  // col2im ring [4][kRing][4]
+  float* s_s = zs + 4 * kRing * 4;
+  float* s_t = s_s + a.Cin;
+  // a_full: TMA bytes landed; a_ready: 128 transform threads done; a_empty: the MMAs reading the stage retired
+  __shared__ uint64_t a_full[kF2A], a_ready[kF2A], a_empty[kF2A], w_full[kF2W], w_empty[kF2W], acc_full[2], acc_empty[2];
+  __shared__ uint32_t tmem_base_s;
+  __shared__ float red[4][32];
+  __shared__ __align__(16) float s_bias16[16];
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int R0 = blockIdx.x * a.rows_per_cta, R1 = min(R0 + a.rows_per_cta, a.rows_total);
+  const int rin0 = max(R0 - 1, 0), rin1 = min(R1 + 1, a.rows_total);
+  const int SW = a.W;
+  const int n_in = (rin1 - rin0) * SW;
+  const int ntiles = (n_in + 127) / 128;
+  const int nkc = (a.Cin + 63) / 64;
+  const uint32_t total = (uint32_t)ntiles * (uint32_t)nkc;
+
+  if (tid == 0) {
+    for (int i = 0; i < kF2A; ++i) {
+      mbar_init(&a_full[i], 1);
+      mbar_init(&a_ready[i], 128);
+      mbar_init(&a_empty[i], 1);
+    }
+    for (int i = 0; i < kF2W; ++i) {
+      mbar_init(&w_full[i], 1);
+      mbar_init(&w_empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&acc_full[i], 1);
+      mbar_init(&acc_empty[i], 128);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 0) tmem_alloc(&tmem_base_s, 512);
+  for (int i = tid; i < 4 * kRing * 4; i += kF2Threads) zs[i] = 0.f;
+  if (tid < 16) s_bias16[tid] = a.bias[tid];
+  for (int c = tid; c < a.Cin; c += kF2Threads) {
+    BnCoef k = bn_coef(a.bn, c);
+    s_s[c] = k.s;
+    s_t[c] = k.t;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_s;
+
+  if (warp == 9) {
+    // =============================================================== activation producer
+    if (lane == 0) {
+      const int P0 = rin0 * a.W;
+      uint32_t g = 0;
+      for (int tile = 0; tile < ntiles; ++tile)
+        for (int kc = 0; kc < nkc; ++kc, ++g) {
+          const uint32_t s = g % kF2A, u = g / kF2A;
+          if (u > 0) mbar_wait(&a_empty[s], (u - 1) & 1);
+          mbar_arrive_expect_tx(&a_full[s], kF2ABytes);
+          tma_load_2d(sA + s * kF2ABytes, &P.tmap, kc * 64, P0 + tile * 128, &a_full[s]);
+        }
+    }
+  } else if (warp == 8) {
+    // =============================================================== weight TMA + MMA issue
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_bf16(144, 0, 0);
+      auto issue_w = [&](uint32_t gg) {
+        const int kc = (int)(gg % (uint32_t)nkc);
+        const uint32_t s = gg % kF2W, u = gg / kF2W;
+        if (u > 0) mbar_wait(&w_empty[s], (u - 1) & 1);
+        const int ck = min(64, a.Cin - kc * 64);
+        const uint32_t wbytes = (uint32_t)(ck / 8) * 144 * 16;
+        mbar_arrive_expect_tx(&w_full[s], wbytes);
+        bulk_g2s(sW + s * kF2WBytes, a.wpk + (size_t)kc * kF2WBytes, wbytes, &w_full[s]);
+      };
+      if (total > 0) issue_w(0);
+      if (total > 1) issue_w(1);
+      uint32_t g = 0;
+      for (int tile = 0; tile < ntiles; ++tile) {
+        const uint32_t buf = tile & 1;
+        if (tile >= 2) {
+          mbar_wait(&acc_empty[buf], ((tile >> 1) - 1) & 1);  // the epilogue drained this accumulator
+          tc_fence_after();
+        }
+        for (int kc = 0; kc < nkc; ++kc, ++g) {
+          if (g + 2 < total) issue_w(g + 2);
+          const uint32_t sa = g % kF2A, ua = g / kF2A, sw = g % kF2W, uw = g / kF2W;
+          const int ck = min(64, a.Cin - kc * 64);
+          mbar_wait(&a_ready[sa], ua & 1);
+          mbar_wait(&w_full[sw], uw & 1);
+          tc_fence_after();
+          const uint32_t aaddr = smem_u32(sA + sa * kF2ABytes), waddr = smem_u32(sW + sw * kF2WBytes);
+          for (int kk = 0; kk < ck / 16; ++kk)
+            umma_ss(tmem + buf * 256, desc_sw128_kmajor(aaddr + kk * 32), desc_kmajor(waddr + kk * 2 * 16 * 144, 144), idesc,
+                    (kc | kk) != 0);
+          umma_commit(&a_empty[sa]);
+          umma_commit(&w_empty[sw]);
+          if (kc == nkc - 1) umma_commit(&acc_full[buf]);
+        }
+      }
+    }
+  } else if (warp < 4) {
+    // =============================================================== BN + ReLU in place
+    // physical 16-byte slot q = i*128 + tid of a stage: row = q >> 3, slot-in-row = q & 7, holding the logical
+    // 8-channel group j = slot ^ (row & 7) -- the same j for every i
+    const int j = (tid & 7) ^ ((tid >> 3) & 7);
+    uint32_t g = 0;
+    for (int tile = 0; tile < ntiles; ++tile)
+      for (int kc = 0; kc < nkc; ++kc, ++g) {
+        const uint32_t s = g % kF2A, u = g / kF2A;
+        const int ck = min(64, a.Cin - kc * 64);
+        mbar_wait(&a_full[s], u & 1);
+        if (8 * j < ck) {
+          const float* sp = s_s + kc * 64 + 8 * j;
+          const float* tp = s_t + kc * 64 + 8 * j;
+          const float4 s0 = *reinterpret_cast<const float4*>(sp), s1 = *reinterpret_cast<const float4*>(sp + 4);
+          const float4 t0 = *reinterpret_cast<const float4*>(tp), t1 = *reinterpret_cast<const float4*>(tp + 4);
+          uint4* base = reinterpret_cast<uint4*>(sA + s * kF2ABytes) + tid;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const uint4 v = base[i * 128];
+            const float2 p0 = unpack_bf16x2(v.x), p1 = unpack_bf16x2(v.y), p2 = unpack_bf16x2(v.z), p3 = unpack_bf16x2(v.w);
+            uint4 o;
+            o.x = pack_bf16x2_relu(fmaf(p0.x, s0.x, t0.x), fmaf(p0.y, s0.y, t0.y));
+            o.y = pack_bf16x2_relu(fmaf(p1.x, s0.z, t0.z), fmaf(p1.y, s0.w, t0.w));
+            o.z = pack_bf16x2_relu(fmaf(p2.x, s1.x, t1.x), fmaf(p2.y, s1.y, t1.y));
+            o.w = pack_bf16x2_relu(fmaf(p3.x, s1.z, t1.z), fmaf(p3.y, s1.w, t1.w));
+            base[i * 128] = o;
+          }
+        }
+        fence_proxy_async();
+        mbar_arrive(&a_ready[s]);
+      }
+  } else {
+    // =============================================================== epilogue warps 4-7
+    const int et = tid - 128, ew = warp - 4;
+    float st_sum[16], st_sq[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) st_sum[i] = st_sq[i] = 0.f;
+    int emit_pos = 0;
+    for (int tile = 0; tile < ntiles; ++tile) {
+      const int t0 = tile * 128;
+      const uint32_t buf = tile & 1;
+      mbar_wait(&acc_full[buf], (tile >> 1) & 1);
+      tc_fence_after();
+      const int t = t0 + et;
+      const bool in_valid = t < n_in;
+      int rr = 0, cc = 0;
+      if (in_valid) {
+        rr = t / SW;
+        cc = t - rr * SW;
+      }
+      const int r = rin0 + rr, xx = cc;
+      const int ri = r % a.H;
+#pragma unroll 1
+      for (int tap = 0; tap < 9; ++tap) {
+        const int dy = tap / 3 - 1, dx = tap % 3 - 1;
+        float v[16];
+        tmem_ld16(tmem + buf * 256 + ((uint32_t)(ew * 32) << 16) + tap * 16, v);
+        if (tap == 8) {
+          tc_fence_before();
+          mbar_arrive(&acc_empty[buf]);
+        }
+        const int qr = r - dy, qx = xx - dx, qi = ri - dy;
+        if (in_valid && qi >= 0 && qi < a.H && qr >= R0 && qr < R1 && qx >= 0 && qx < a.W) {
+          const int uidx = (t - dy * SW - dx + SW + 1) & (kRing - 1);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            float4* p = reinterpret_cast<float4*>(zs + ((size_t)q * kRing + uidx) * 4);
+            float4 o = *p;
+            o.x += v[q * 4 + 0];
+            o.y += v[q * 4 + 1];
+            o.z += v[q * 4 + 2];
+            o.w += v[q * 4 + 3];
+            *p = o;
+          }
+        }
+        epilogue_sync();
+      }
+      const int lim = (tile == ntiles - 1) ? n_in : max(0, min(t0 + 128 - SW - 1, n_in));
+      for (int e0 = emit_pos; e0 < lim; e0 += 128) {
+        const int e = e0 + et;
+        if (e < lim) {
+          const int er = e / SW, ec = e - er * SW;
+          const int orow = rin0 + er, ox = ec;
+          if (orow >= R0 && orow < R1) {
+            const int uidx = (e + SW + 1) & (kRing - 1);
+            const int img = orow / a.H;
+            float o[16];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              float4* p = reinterpret_cast<float4*>(zs + ((size_t)q * kRing + uidx) * 4);
+              float4 z = *p;
+              *p = make_float4(0.f, 0.f, 0.f, 0.f);
+              o[q * 4 + 0] = z.x;
+              o[q * 4 + 1] = z.y;
+              o[q * 4 + 2] = z.z;
+              o[q * 4 + 3] = z.w;
+            }
+            uint32_t pk[8];
+            float mk[16];
+            if (a.mask != nullptr) {
+              const float4* mp = reinterpret_cast<const float4*>(a.mask + (size_t)img * 16);
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const float4 m4 = __ldg(mp + q);
+                mk[4 * q] = m4.x;
+                mk[4 * q + 1] = m4.y;
+                mk[4 * q + 2] = m4.z;
+                mk[4 * q + 3] = m4.w;
+              }
+            } else {
+#pragma unroll
+              for (int c = 0; c < 16; ++c) mk[c] = 1.f;
+            }
+#pragma unroll
+            for (int c = 0; c < 16; c += 2) {
+              float y0 = (o[c] + s_bias16[c]) * mk[c], y1 = (o[c + 1] + s_bias16[c + 1]) * mk[c + 1];
+              pk[c >> 1] = pack_bf16x2(y0, y1);
+              float2 rb = unpack_bf16x2(pk[c >> 1]);
+              st_sum[c] += rb.x;
+              st_sq[c] += rb.x * rb.x;
+              st_sum[c + 1] += rb.y;
+              st_sq[c + 1] += rb.y * rb.y;
+            }
+            st256(a.act_out + ((size_t)orow * a.W + ox) * a.Ct + a.Cin, make_uint4(pk[0], pk[1], pk[2], pk[3]),
+                  make_uint4(pk[4], pk[5], pk[6], pk[7]));
+          }
+        }
+      }
+      emit_pos = max(emit_pos, lim);
+      epilogue_sync();
+    }
+    if (a.stats_out != nullptr) {
+#pragma unroll
+      for (int c = 0; c < 16; ++c) {
+        float s1 = warp_sum(st_sum[c]), s2 = warp_sum(st_sq[c]);
+        if (lane == 0) {
+          red[ew][c] = s1;
+          red[ew][16 + c] = s2;
+        }
+      }
+      epilogue_sync();
+      if (et < 32) {
+        float v = red[0][et] + red[1][et] + red[2][et] + red[3][et];
+        const int c = et & 15;
+        atomicAdd(a.stats_out + (et < 16 ? 0 : a.Ct) + a.Cin + c, (double)v);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
+size_t dense_fwd_tma_smem(int Cin) {
+  return 1024 + (size_t)kF2A * kF2ABytes + (size_t)kF2W * kF2WBytes + 4 * kRing * 16 + (size_t)Cin * 8;
+}
+
+int launch_dense_fwd_tma(const DenseFwdArgs& a, const void* tmap, int grid, cudaStream_t st) {
+  const size_t smem = dense_fwd_tma_smem(a.Cin);
+  static bool configured = false;
+  if (!configured) {
+    RL_CUDA(cudaFuncSetAttribute(dense_fwd_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    configured = true;
+  }
+  if (smem > 200 * 1024) return rl_fail(RL_ERR_SHAPE, "dense_fwd_tma: smem %zu too large", smem);
+  if (a.nstrips != 1 || a.W > 160) return rl_fail(RL_ERR_SHAPE, "dense_fwd_tma: needs a full-width strip");
+  DenseFwdTmaArgs P;
+  memcpy(&P.tmap, tmap, sizeof(CUtensorMap));
+  P.a = a;
+  { ProfScope _ps(KC_DENSE_FWD, st);
+  RL_CUDA(launch_pdl(dense_fwd_tma_kernel, dim3(grid), dim3(kF2Threads), smem, st, P)); }
+  return RL_OK;
+}
+
+int encode_arena_tmap(void* tmap_out, const void* arena, long npx, int Ct) {
+  typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                               const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static EncodeFn fn = nullptr;
+  if (fn == nullptr) {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    RL_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q));
+    if (f == nullptr || q != cudaDriverEntryPointSuccess) return rl_fail(RL_ERR_CUDA, "cuTensorMapEncodeTiled not available");
+    fn = (EncodeFn)f;
+  }
+  CUtensorMap tm;
+  const cuuint64_t dims[2] = {(cuuint64_t)Ct, (cuuint64_t)npx};
+  const cuuint64_t strides[1] = {(cuuint64_t)Ct * 2};
+  const cuuint32_t box[2] = {64, 128};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = fn(&tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(arena), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return rl_fail(RL_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) for [%ld][%d]", (int)r, npx, Ct);
+  memcpy(tmap_out, &tm, sizeof(tm));
+  return RL_OK;
 }
 
 size_t dense_fwd_smem(int Cin) { return (((size_t)Cin * 8 + 127) & ~(size_t)127) + 4 * kRing * 16 + 2 * (16384 + 18432); }

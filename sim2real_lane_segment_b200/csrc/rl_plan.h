@@ -88,6 +88,8 @@ struct Plan {
   size_t xcol_off;                    // first conv: bf16 im2col rows [px0][32] kept for its weight gradient
   size_t ws_bytes;
   void* ws;                           // bound workspace (device)
+  alignas(64) unsigned char tmap_act[6][128];  // CUtensorMap per level arena: [pixels][Ct] bf16, box 128 px x 64 ch, 128-byte swizzle
+  bool tmap_ok;
   void* side_stream;                  // cudaStream_t: DenseLayer weight gradients run here, concurrently with the dgrad chain
   void* ev_dz[4];                     // cudaEvent_t: dz buffer q written (main stream); 0,1: DenseLayer planes, 2,3: scratch
   void* ev_wg[4];                     // cudaEvent_t: weight gradient that read buffer q finished (side stream)
