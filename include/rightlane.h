@@ -107,7 +107,9 @@ int rl_profile_end(double* ms, long* launches);
 int rl_profile_launches(float* ms, int* kernel_class, int max); /* per-launch times of the last profiled region */
 
 /* runtime switches: "overlap" (default 1) runs the DenseLayer weight-gradient kernels of rl_backward on a plan-owned
- * side stream concurrently with the input-gradient chain (joined before rl_backward returns control of the stream). */
+ * side stream concurrently with the input-gradient chain (joined before rl_backward returns control of the stream);
+ * "fwd_tma" (default 1) runs the DenseLayer forward of levels up to 160 pixels wide through the tensor-map TMA kernel
+ * (0: the register-staged kernel that wider levels always use; both produce identical bits). */
 int rl_set_option(const char* name, int value);
 
 /* test hook: one 128 x N x K tcgen05 GEMM through the shared-memory operand conventions of csrc/rl_umma.cuh */

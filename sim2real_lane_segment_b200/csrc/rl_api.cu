@@ -187,9 +187,14 @@ int rl_set_dropout(rl_plan* h, float p_drop, unsigned long long seed, unsigned l
 }
 
 // DenseLayer forward through the tensor-map TMA kernel (RL_FWD_TMA=0 selects the register-staged kernel)
-static const bool g_fwd_tma = []() {
+static bool g_fwd_tma = []() {
   const char* e = getenv("RL_FWD_TMA");
   return !(e && e[0] == '0');
+}();
+
+static const int g_fwd_dbg = []() {
+  const char* e = getenv("RL_FWD_DBG");
+  return e ? atoi(e) : 0;
 }();
 
 int rl_forward(rl_plan* h, const float* params, const float* bnbuf, const float* x, int train, void* stream) {
@@ -226,6 +231,7 @@ int rl_forward(rl_plan* h, const float* params, const float* bnbuf, const float*
       a.mask = train ? (const float*)(wsb(p) + L.mask_off) : nullptr;
       a.bn = make_bn(p, L, params, bnbuf, train);
       a.stats_out = train ? stats_of(p, L.lvl_in) : nullptr;
+      a.dbg = g_fwd_dbg;
       if (use_tma) {
         if ((rc = launch_dense_fwd_tma(a, p->tmap_act[L.lvl_in], nruns, st))) return rc;
       } else if ((rc = launch_dense_fwd(a, nruns * a.nstrips, st))) return rc;
@@ -661,6 +667,10 @@ extern "C" int rl_backward(rl_plan* h, const float* params, const float* x, floa
 extern "C" int rl_set_option(const char* name, int value) {
   if (name && strcmp(name, "overlap") == 0) {
     g_overlap = value ? 1 : 0;
+    return RL_OK;
+  }
+  if (name && strcmp(name, "fwd_tma") == 0) {
+    g_fwd_tma = value != 0;
     return RL_OK;
   }
   return rl_fail(RL_ERR_ARG, "rl_set_option: unknown option");

@@ -10,6 +10,8 @@
 // with N = 9*16 = 144 and K = Cin, so every activation is read exactly once and never needs a halo; the
 // 3x3 structure is resolved on the 16-channel side by a shift-add (col2im) of the 9 tap planes in shared memory.
 #include <cuda.h>
+
+#include <algorithm>
 #include <string.h>
 
 #include "rl_common.cuh"
@@ -178,7 +180,7 @@ __global__ void __launch_bounds__(kFwdThreads, 2) dense_fwd_kernel(DenseFwdArgs 
       const int ri = r % a.H;
 #pragma unroll 1
       for (int tap = 0; tap < 9; ++tap) {
-        const int dy = tap / 3 - 1, dx = tap % 3 - 1;
+        const int dx = tap / 3 - 1, dy = tap % 3 - 1;  // tap slots are packed dx-major
         float v[16];
         tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16) + tap * 16, v);
         if (tap == 8) {  // accumulator fully read by this thread: the next tile's MMAs may overwrite it
@@ -293,12 +295,14 @@ __global__ void __launch_bounds__(kFwdThreads, 2) dense_fwd_kernel(DenseFwdArgs 
 // Requires a full-width strip (W <= 160): the 128 input pixels of a tile are then 128 consecutive arena rows.
 // ================================================================================================
 constexpr int kF2Threads = 320;
-constexpr int kF2A = 6, kF2W = 3;
+constexpr int kF2A = 6, kF2W = 3;  // maximum activation ring depth; weight ring depth in streaming mode
 constexpr int kF2ABytes = 16384, kF2WBytes = 18432;
 
 struct alignas(64) DenseFwdTmaArgs {
   CUtensorMap tmap;
   DenseFwdArgs a;
+  int na;          // activation ring depth (3..6 stages of 16 KB)
+  int w_resident;  // all weight chunks stay in shared memory for the whole CTA (else a 3-deep streaming ring)
 };
 
 __device__ __forceinline__ void epilogue_sync() { asm volatile("bar.sync 2, 128;" ::: "memory"); }
@@ -325,9 +329,12 @@ __global__ void __launch_bounds__(kF2Threads, 1) dense_fwd_tma_kernel(const __gr
   const DenseFwdArgs& a = P.a;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // SWIZZLE_128B atoms want 1024-byte alignment
+  const int nkc = (a.Cin + 63) / 64;
+  const uint32_t NA = (uint32_t)P.na;
+  const bool wres = P.w_resident != 0;
   uint8_t* sA = smem;
-  uint8_t* sW = smem + kF2A * kF2ABytes;
-  float* zs = reinterpret_cast<float*>(sW + kF2W * kF2WBytes);  // col2im ring [4][kRing][4]
+  uint8_t* sW = smem + NA * kF2ABytes;
+  float* zs = reinterpret_cast<float*>(sW + (wres ? nkc : kF2W) * kF2WBytes);  // col2im ring [4][kRing][4]
   float* s_s = zs + 4 * kRing * 4;
   float* s_t = s_s + a.Cin;
   // a_full: TMA bytes landed; a_ready: 128 transform threads done; a_empty: the MMAs reading the stage retired
@@ -342,13 +349,12 @@ __global__ void __launch_bounds__(kF2Threads, 1) dense_fwd_tma_kernel(const __gr
   const int SW = a.W;
   const int n_in = (rin1 - rin0) * SW;
   const int ntiles = (n_in + 127) / 128;
-  const int nkc = (a.Cin + 63) / 64;
   const uint32_t total = (uint32_t)ntiles * (uint32_t)nkc;
 
   if (tid == 0) {
     for (int i = 0; i < kF2A; ++i) {
       mbar_init(&a_full[i], 1);
-      mbar_init(&a_ready[i], 128);
+      mbar_init(&a_ready[i], 4);  // one arrival per transform warp
       mbar_init(&a_empty[i], 1);
     }
     for (int i = 0; i < kF2W; ++i) {
@@ -357,7 +363,7 @@ __global__ void __launch_bounds__(kF2Threads, 1) dense_fwd_tma_kernel(const __gr
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&acc_full[i], 1);
-      mbar_init(&acc_empty[i], 128);
+      mbar_init(&acc_empty[i], 4);  // one arrival per epilogue warp
     }
     fence_mbar_init();
   }
@@ -378,13 +384,20 @@ __global__ void __launch_bounds__(kF2Threads, 1) dense_fwd_tma_kernel(const __gr
     // =============================================================== activation producer
     if (lane == 0) {
       const int P0 = rin0 * a.W;
-      uint32_t g = 0;
+      uint32_t s = 0, ph = 1;  // ring slot and the parity of "slot free" (a fresh barrier passes a parity-1 wait)
       for (int tile = 0; tile < ntiles; ++tile)
-        for (int kc = 0; kc < nkc; ++kc, ++g) {
-          const uint32_t s = g % kF2A, u = g / kF2A;
-          if (u > 0) mbar_wait(&a_empty[s], (u - 1) & 1);
-          mbar_arrive_expect_tx(&a_full[s], kF2ABytes);
-          tma_load_2d(sA + s * kF2ABytes, &P.tmap, kc * 64, P0 + tile * 128, &a_full[s]);
+        for (int kc = 0; kc < nkc; ++kc) {
+          mbar_wait(&a_empty[s], ph);
+          if (a.dbg & 8) {
+            mbar_arrive(&a_full[s]);
+          } else {
+            mbar_arrive_expect_tx(&a_full[s], kF2ABytes);
+            tma_load_2d(sA + s * kF2ABytes, &P.tmap, kc * 64, P0 + tile * 128, &a_full[s]);
+          }
+          if (++s == NA) {
+            s = 0;
+            ph ^= 1;
+          }
         }
     }
   } else if (warp == 8) {
@@ -400,29 +413,61 @@ __global__ void __launch_bounds__(kF2Threads, 1) dense_fwd_tma_kernel(const __gr
         mbar_arrive_expect_tx(&w_full[s], wbytes);
         bulk_g2s(sW + s * kF2WBytes, a.wpk + (size_t)kc * kF2WBytes, wbytes, &w_full[s]);
       };
-      if (total > 0) issue_w(0);
-      if (total > 1) issue_w(1);
-      uint32_t g = 0;
+      if (wres) {  // the layer's whole weight matrix: loaded once, reused by every tile of this CTA
+        if (total > 0) {
+          uint32_t wbytes = 0;
+          for (int kc = 0; kc < nkc; ++kc) wbytes += (uint32_t)(min(64, a.Cin - kc * 64) / 8) * 144 * 16;
+          mbar_arrive_expect_tx(&w_full[0], wbytes);
+          for (int kc = 0; kc < nkc; ++kc)
+            bulk_g2s(sW + kc * kF2WBytes, a.wpk + (size_t)kc * kF2WBytes, (uint32_t)(min(64, a.Cin - kc * 64) / 8) * 144 * 16,
+                     &w_full[0]);
+          mbar_wait(&w_full[0], 0);
+        }
+      } else {
+        if (total > 0) issue_w(0);
+        if (total > 1) issue_w(1);
+      }
+      // The issuing thread is a serial instruction stream: everything per stage is kept to a handful of adds
+      // (descriptors advance by constants, ring slots and parities are carried, no divisions).
+      const uint64_t adesc0 = desc_sw128_kmajor(smem_u32(sA));
+      const uint64_t wdesc0 = desc_kmajor(smem_u32(sW), 144);
+      const int last_n16 = (a.Cin - (nkc - 1) * 64) / 16;
+      uint32_t sa = 0, pa = 0, sw = 0, pw = 0, g = 0;
       for (int tile = 0; tile < ntiles; ++tile) {
         const uint32_t buf = tile & 1;
+        const uint32_t dacc = tmem + buf * 256;
         if (tile >= 2) {
           mbar_wait(&acc_empty[buf], ((tile >> 1) - 1) & 1);  // the epilogue drained this accumulator
           tc_fence_after();
         }
         for (int kc = 0; kc < nkc; ++kc, ++g) {
-          if (g + 2 < total) issue_w(g + 2);
-          const uint32_t sa = g % kF2A, ua = g / kF2A, sw = g % kF2W, uw = g / kF2W;
-          const int ck = min(64, a.Cin - kc * 64);
-          mbar_wait(&a_ready[sa], ua & 1);
-          mbar_wait(&w_full[sw], uw & 1);
+          if (!wres && g + 2 < total) issue_w(g + 2);
+          const int n16 = (a.dbg & 2) ? 0 : (kc == nkc - 1 ? last_n16 : 4);
+          mbar_wait(&a_ready[sa], pa);
+          if (!wres) mbar_wait(&w_full[sw], pw);
           tc_fence_after();
-          const uint32_t aaddr = smem_u32(sA + sa * kF2ABytes), waddr = smem_u32(sW + sw * kF2WBytes);
-          for (int kk = 0; kk < ck / 16; ++kk)
-            umma_ss(tmem + buf * 256, desc_sw128_kmajor(aaddr + kk * 32), desc_kmajor(waddr + kk * 2 * 16 * 144, 144), idesc,
-                    (kc | kk) != 0);
-          umma_commit(&a_empty[sa]);
-          umma_commit(&w_empty[sw]);
-          if (kc == nkc - 1) umma_commit(&acc_full[buf]);
+          const uint64_t ad = adesc0 + (uint64_t)(sa * (kF2ABytes >> 4));
+          const uint64_t wd = wdesc0 + (uint64_t)((wres ? (uint32_t)kc : sw) * (kF2WBytes >> 4));
+          if (n16 > 0) umma_ss(dacc, ad, wd, idesc, kc != 0);
+          if (n16 > 1) umma_ss(dacc, ad + 2, wd + 288, idesc, 1);
+          if (n16 > 2) umma_ss(dacc, ad + 4, wd + 576, idesc, 1);
+          if (n16 > 3) umma_ss(dacc, ad + 6, wd + 864, idesc, 1);
+          if (a.dbg & 64) {
+            mbar_arrive(&a_empty[sa]);
+            if (kc == nkc - 1) mbar_arrive(&acc_full[buf]);
+          } else {
+            umma_commit(&a_empty[sa]);
+            if (!wres) umma_commit(&w_empty[sw]);
+            if (kc == nkc - 1) umma_commit(&acc_full[buf]);
+          }
+          if (++sa == NA) {
+            sa = 0;
+            pa ^= 1;
+          }
+          if (++sw == kF2W) {
+            sw = 0;
+            pw ^= 1;
+          }
         }
       }
     }
@@ -431,13 +476,12 @@ __global__ void __launch_bounds__(kF2Threads, 1) dense_fwd_tma_kernel(const __gr
     // physical 16-byte slot q = i*128 + tid of a stage: row = q >> 3, slot-in-row = q & 7, holding the logical
     // 8-channel group j = slot ^ (row & 7) -- the same j for every i
     const int j = (tid & 7) ^ ((tid >> 3) & 7);
-    uint32_t g = 0;
+    uint32_t s = 0, ph = 0;
     for (int tile = 0; tile < ntiles; ++tile)
-      for (int kc = 0; kc < nkc; ++kc, ++g) {
-        const uint32_t s = g % kF2A, u = g / kF2A;
+      for (int kc = 0; kc < nkc; ++kc) {
         const int ck = min(64, a.Cin - kc * 64);
-        mbar_wait(&a_full[s], u & 1);
-        if (8 * j < ck) {
+        mbar_wait(&a_full[s], ph);
+        if (8 * j < ck && !(a.dbg & 1)) {
           const float* sp = s_s + kc * 64 + 8 * j;
           const float* tp = s_t + kc * 64 + 8 * j;
           const float4 s0 = *reinterpret_cast<const float4*>(sp), s1 = *reinterpret_cast<const float4*>(sp + 4);
@@ -455,8 +499,13 @@ __global__ void __launch_bounds__(kF2Threads, 1) dense_fwd_tma_kernel(const __gr
             base[i * 128] = o;
           }
         }
-        fence_proxy_async();
-        mbar_arrive(&a_ready[s]);
+        if (!(a.dbg & 32)) fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&a_ready[s]);
+        if (++s == NA) {
+          s = 0;
+          ph ^= 1;
+        }
       }
   } else {
     // =============================================================== epilogue warps 4-7
@@ -479,33 +528,67 @@ __global__ void __launch_bounds__(kF2Threads, 1) dense_fwd_tma_kernel(const __gr
       }
       const int r = rin0 + rr, xx = cc;
       const int ri = r % a.H;
-#pragma unroll 1
-      for (int tap = 0; tap < 9; ++tap) {
-        const int dy = tap / 3 - 1, dx = tap % 3 - 1;
-        float v[16];
-        tmem_ld16(tmem + buf * 256 + ((uint32_t)(ew * 32) << 16) + tap * 16, v);
-        if (tap == 8) {
-          tc_fence_before();
-          mbar_arrive(&acc_empty[buf]);
-        }
-        const int qr = r - dy, qx = xx - dx, qi = ri - dy;
-        if (in_valid && qi >= 0 && qi < a.H && qr >= R0 && qr < R1 && qx >= 0 && qx < a.W) {
-          const int uidx = (t - dy * SW - dx + SW + 1) & (kRing - 1);
+      // Tap slots are packed dx-major, so one dx group = 48 consecutive accumulator columns = the three dy taps.
+      // Within a tile (128 consecutive pixels) two threads can only meet in a ring slot through different dx when
+      // SW >= 128 (a dy step moves the slot by SW): one barrier per dx group then suffices; narrower levels keep
+      // one barrier per tap.
+      const bool wide = SW >= 128;
+      const uint32_t tacc = tmem + buf * 256 + ((uint32_t)(ew * 32) << 16);
+      float v[48];
+      tmem_ld16_nowait(tacc, v);
+      tmem_ld16_nowait(tacc + 16, v + 16);
+      tmem_ld16_nowait(tacc + 32, v + 32);
+      tmem_wait_ld();
+      reg_fence16(v);
+      reg_fence16(v + 16);
+      reg_fence16(v + 32);
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            float4* p = reinterpret_cast<float4*>(zs + ((size_t)q * kRing + uidx) * 4);
-            float4 o = *p;
-            o.x += v[q * 4 + 0];
-            o.y += v[q * 4 + 1];
-            o.z += v[q * 4 + 2];
-            o.w += v[q * 4 + 3];
-            *p = o;
+      for (int dxi = 0; dxi < 3; ++dxi) {
+        const int dx = dxi - 1;
+        float vn[48];
+        if (dxi < 2) {  // next group's accumulator columns stream in behind this group's shift-add
+          tmem_ld16_nowait(tacc + (dxi + 1) * 48, vn);
+          tmem_ld16_nowait(tacc + (dxi + 1) * 48 + 16, vn + 16);
+          tmem_ld16_nowait(tacc + (dxi + 1) * 48 + 32, vn + 32);
+        }
+        const int qx = xx - dx;
+        const bool okx = in_valid && qx >= 0 && qx < a.W && !(a.dbg & 4);
+#pragma unroll
+        for (int dyi = 0; dyi < 3; ++dyi) {
+          const int dy = dyi - 1;
+          const int qr = r - dy, qi = ri - dy;
+          if (okx && qi >= 0 && qi < a.H && qr >= R0 && qr < R1) {
+            const int uidx = (t - dy * SW - dx + SW + 1) & (kRing - 1);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              float4* p = reinterpret_cast<float4*>(zs + ((size_t)q * kRing + uidx) * 4);
+              float4 o = *p;
+              o.x += v[dyi * 16 + q * 4 + 0];
+              o.y += v[dyi * 16 + q * 4 + 1];
+              o.z += v[dyi * 16 + q * 4 + 2];
+              o.w += v[dyi * 16 + q * 4 + 3];
+              *p = o;
+            }
+          }
+          if (!wide) epilogue_sync();
+        }
+        if (dxi < 2) {
+          tmem_wait_ld();
+          reg_fence16(vn);
+          reg_fence16(vn + 16);
+          reg_fence16(vn + 32);
+#pragma unroll
+          for (int i = 0; i < 48; ++i) v[i] = vn[i];
+          if (dxi == 1) {  // accumulator fully read by this thread: the MMAs two tiles ahead may overwrite it
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty[buf]);
           }
         }
-        epilogue_sync();
+        if (wide) epilogue_sync();
       }
       const int lim = (tile == ntiles - 1) ? n_in : max(0, min(t0 + 128 - SW - 1, n_in));
-      for (int e0 = emit_pos; e0 < lim; e0 += 128) {
+      for (int e0 = emit_pos; e0 < ((a.dbg & 16) ? 0 : lim); e0 += 128) {
         const int e = e0 + et;
         if (e < lim) {
           const int er = e / SW, ec = e - er * SW;
@@ -580,22 +663,29 @@ __global__ void __launch_bounds__(kF2Threads, 1) dense_fwd_tma_kernel(const __gr
   if (warp == 0) tmem_dealloc(tmem, 512);
 }
 
-size_t dense_fwd_tma_smem(int Cin) {
-  return 1024 + (size_t)kF2A * kF2ABytes + (size_t)kF2W * kF2WBytes + 4 * kRing * 16 + (size_t)Cin * 8;
-}
-
 int launch_dense_fwd_tma(const DenseFwdArgs& a, const void* tmap, int grid, cudaStream_t st) {
-  const size_t smem = dense_fwd_tma_smem(a.Cin);
+  constexpr size_t kCap = 224 * 1024;  // dynamic shared memory of the one resident CTA
   static bool configured = false;
   if (!configured) {
-    RL_CUDA(cudaFuncSetAttribute(dense_fwd_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    RL_CUDA(cudaFuncSetAttribute(dense_fwd_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCap));
     configured = true;
   }
-  if (smem > 200 * 1024) return rl_fail(RL_ERR_SHAPE, "dense_fwd_tma: smem %zu too large", smem);
   if (a.nstrips != 1 || a.W > 160) return rl_fail(RL_ERR_SHAPE, "dense_fwd_tma: needs a full-width strip");
   DenseFwdTmaArgs P;
   memcpy(&P.tmap, tmap, sizeof(CUtensorMap));
   P.a = a;
+  const int nkc = (a.Cin + 63) / 64;
+  const size_t fixed = 1024 + 4 * kRing * 16 + (size_t)a.Cin * 8;
+  const size_t wall = (size_t)nkc * kF2WBytes;
+  if (fixed + wall + 3 * kF2ABytes <= kCap) {
+    P.w_resident = 1;
+    P.na = (int)std::min<size_t>(kF2A, (kCap - fixed - wall) / kF2ABytes);
+  } else {
+    P.w_resident = 0;
+    P.na = kF2A;
+  }
+  const size_t smem = fixed + (P.w_resident ? wall : (size_t)kF2W * kF2WBytes) + (size_t)P.na * kF2ABytes;
+  if (smem > kCap) return rl_fail(RL_ERR_SHAPE, "dense_fwd_tma: smem %zu too large", smem);
   { ProfScope _ps(KC_DENSE_FWD, st);
   RL_CUDA(launch_pdl(dense_fwd_tma_kernel, dim3(grid), dim3(kF2Threads), smem, st, P)); }
   return RL_OK;

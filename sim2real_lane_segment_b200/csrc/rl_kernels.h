@@ -19,6 +19,7 @@ struct DenseFwdArgs {
   const float* mask;         // [B][16] dropout scale or null
   BnSrc bn;
   double* stats_out;         // level stats base (Σx at [c], Σx² at [Ct+c]) or null
+  int dbg;                   // triage switches (RL_FWD_DBG), 0 in production
 };
 int launch_dense_fwd(const DenseFwdArgs& a, int grid, cudaStream_t st);
 // TMA-fed variant (full-width strips only): tmap = the level arena's 128-byte CUtensorMap blob

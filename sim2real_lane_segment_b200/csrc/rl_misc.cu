@@ -27,9 +27,10 @@ __global__ void pack_weights_kernel(const PackEntry* tab, const float* __restric
     for (int k = 0; k < 8; ++k) v[k] = 0.f;
     const int C = e.cin;
     switch (e.kind) {
-      case 0: {  // dense fwd: [kc][jc][n=tap*16+co][8 c]
+      case 0: {  // dense fwd: [kc][jc][n=slot*16+co][8 c], tap slots ordered dx-major: slot = (dx+1)*3 + (dy+1)
         int kc = (int)(i / (8 * 144)), rem = (int)(i % (8 * 144)), jc = rem / 144, n = rem % 144;
-        int c0 = kc * 64 + jc * 8, tap = n / 16, co = n % 16;
+        int c0 = kc * 64 + jc * 8, slot = n / 16, co = n % 16;
+        int tap = (slot % 3) * 3 + slot / 3;  // reference tap index ky*3+kx
         if (c0 < C)
           for (int k = 0; k < 8; ++k) v[k] = w[((long)co * C + ref_channel(c0 + k, e.cs_perm)) * 9 + tap];
         break;

@@ -1,2 +1,2 @@
-timeout 900 python -m pytest tests -m gpu -q -x 2>&1 | grep -E "^E|FAILED|passed|failed" | head -12
-timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline 2>&1 | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['value'], d['ms_per_step'], d['e2e']['value'])"
+timeout 300 python -m pytest tests/test_forward_gpu.py tests/test_shapes_gpu.py -m gpu -q -x 2>&1 | tail -3
+for v in 0; do echo "dbg $v"; RL_FWD_DBG=$v timeout 120 python tools/per_launch.py dense_fwd 2>&1 | tail -1; done
