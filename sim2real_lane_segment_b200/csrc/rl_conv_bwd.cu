@@ -615,25 +615,44 @@ __global__ void __launch_bounds__(kWgThreads, 2) wgrad_kernel(WgradArgs a) {
       r.v[h] = (r.valid && j < a_nchunk) ? ldg128(src + j * 8) : make_uint4(0, 0, 0, 0);
     }
   };
+  // DenseLayer B tile: this thread's pixel row advances by 64 pixels per chunk; its position in the zero-padded dz planes
+  // is carried along (one division at the start, none in the loop).  The tap at (dy,dx) of pixel (b,y,x) sits at
+  // pos - dy*(W+2) - dx, always in range; the 5 (tap, half) column chunks of a thread are fixed, so their plane offsets are too.
+  long bpos = 0;   // plane position of pixel P0 + kc_next*64 + b_row
+  int bx = 0, by = 0;
+  long boff[5];
+  if (a.kind == WG_DENSE) {
+    const long P = P0 + b_row;
+    const long b = P / HW;
+    const int hw = (int)(P - b * HW);
+    by = hw / a.W;
+    bx = hw - by * a.W;
+    bpos = a.dz_guard + (b * (a.H + 1) + by) * (a.W + 2) + bx + 1;
+#pragma unroll
+    for (int q = 0; q < 5; ++q) {
+      const int j = b_j0 + 4 * q, tap = j >> 1, half = j & 1;
+      boff[q] = (long)half * a.dz_npos - (long)(tap / 3 - 1) * (a.W + 2) - (tap % 3 - 1);
+    }
+  }
   auto issue_b = [&](int kc, uint8_t* sB) {
     if (kc < nchunks) {
       const long P = P0 + (long)kc * 64 + b_row;
       const bool pv = P < P1;
       if (a.kind == WG_DENSE) {
-        // zero-padded planes: the tap at (dy,dx) of pixel (b,y,x) sits at position pos - dy*(W+2) - dx, always in range
-        long pos = a.dz_guard;
-        if (pv) {
-          const long b = P / HW;
-          const int hw = (int)(P - b * HW), y = hw / a.W, x = hw - y * a.W;
-          pos += (b * (a.H + 1) + y) * (a.W + 2) + x + 1;
-        }
 #pragma unroll
         for (int q = 0; q < 5; ++q) {
           const int j = b_j0 + 4 * q;
-          if (j < 18) {
-            const int tap = j >> 1, half = j & 1;
-            const long tp = pos - (long)(tap / 3 - 1) * (a.W + 2) - (tap % 3 - 1);
-            cp_async16(sB + ((size_t)j * 64 + b_row) * 16, a.Bm + ((long)half * a.dz_npos + tp) * 8, pv);
+          if (j < 18) cp_async16(sB + ((size_t)j * 64 + b_row) * 16, a.Bm + ((pv ? bpos : (long)a.dz_guard) + boff[q]) * 8, pv);
+        }
+        // advance to the next chunk (issue_b is called with consecutive kc)
+        bx += 64;
+        bpos += 64;
+        while (bx >= a.W) {
+          bx -= a.W;
+          bpos += 2;  // the two pad columns of a plane row
+          if (++by == a.H) {
+            by = 0;
+            bpos += a.W + 2;  // the pad row between images
           }
         }
       } else {
