@@ -112,6 +112,10 @@ int rl_profile_launches(float* ms, int* kernel_class, int max); /* per-launch ti
  * (0: the register-staged kernel that wider levels always use; both produce identical bits). */
 int rl_set_option(const char* name, int value);
 
+/* measurement hook: stream the channel window [c0, c0+nch) of an NHWC bf16 arena [npx][Ct] with 32-byte accesses
+ * (mode 0 read, 1 read+write back) -- what the memory system delivers for the access pattern of the concat arenas */
+int rl_selftest_stream(void* arena, long npx, int Ct, int c0, int nch, int mode, int grid, void* sink, void* stream);
+
 /* test hook: one 128 x N x K tcgen05 GEMM through the shared-memory operand conventions of csrc/rl_umma.cuh */
 int rl_selftest_umma(const void* A, int a_rows, int a_cols, int a_mn_major, int a_row_shift, const void* B, int b_rows,
                      int b_cols, int b_mn_major, int b_row_shift, int N, int K, float* D, int bulk_b, void* stream);

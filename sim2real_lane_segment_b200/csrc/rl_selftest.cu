@@ -94,3 +94,34 @@ extern "C" int rl_selftest_umma(const void* A, int a_rows, int a_cols, int a_mn_
   RL_CUDA(cudaGetLastError());
   return RL_OK;
 }
+
+// ------------------------------------------------------------------------------------------------
+// Measurement hook: stream a channel window [c0, c0+nch) of an NHWC bf16 arena ([npx][Ct]) with 32-byte accesses,
+// the access pattern of every consumer of the concat arenas.  mode 0: read only, 1: read + write back (RMW).
+// bench tools use it to measure what the memory system delivers for row-strided windows.
+// ------------------------------------------------------------------------------------------------
+namespace rl {
+__global__ void __launch_bounds__(256) stream_window_kernel(__nv_bfloat16* arena, long npx, int Ct, int c0, int nch, int mode,
+                                                            unsigned* sink) {
+  const int per_row = nch / 16;  // 32-byte pieces per pixel row
+  const long total = npx * per_row;
+  unsigned acc = 0;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const long p = i / per_row;
+    const int q = (int)(i - p * per_row);
+    __nv_bfloat16* ptr = arena + p * Ct + c0 + q * 16;
+    u32x8 v = ldg256_nc_nohint(ptr);
+    acc ^= v.lo.x ^ v.lo.y ^ v.lo.z ^ v.lo.w ^ v.hi.x ^ v.hi.y ^ v.hi.z ^ v.hi.w;
+    if (mode == 1) st256(ptr, v.lo, v.hi);
+  }
+  if (acc == 0x12345678u) *sink = acc;  // keeps the loads alive
+}
+}  // namespace rl
+
+extern "C" int rl_selftest_stream(void* arena, long npx, int Ct, int c0, int nch, int mode, int grid, void* sink, void* stream) {
+  using namespace rl;
+  if (nch % 16 || c0 % 16 || c0 + nch > Ct) return rl_fail(RL_ERR_ARG, "selftest_stream: bad window");
+  stream_window_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((__nv_bfloat16*)arena, npx, Ct, c0, nch, mode, (unsigned*)sink);
+  RL_CUDA(cudaGetLastError());
+  return RL_OK;
+}
