@@ -97,6 +97,15 @@ int rl_adamw_step(float* params, const float* grads, float* exp_avg, float* exp_
 int rl_sgd_nesterov_step(float* params, const float* grads, float* momentum_buf, long n, float lr, float momentum,
                          float weight_decay, int first_step, float grad_scale, void* stream);
 
+/* Input pipeline, deterministic part: MyTransform(width, height, gray, augment=False) of
+ * dataManagement/myTransforms.py:8-31 applied to a batch of cv2.imread frames (myDatasets.py:49-53) in one kernel.
+ * img_bgr: uint8 [B][Hs][Ws][3] (device), label: uint8 [B][Hs][Ws] or null.  x_out: float32 [B][3][H][W] =
+ * Normalize(cv2.resize(img, (W,H), INTER_LINEAR)) -- the resize is cv2's uint8 fixed-point algorithm, bit-exact --
+ * with ToGray applied in between when gray != 0; y_out: int64 [B][H][W] = cv2.resize(label, INTER_NEAREST), or null.
+ * The random augmentations (HueSaturationValue, RandomSizedCrop, MotionBlur, GaussNoise) are not part of this call. */
+int rl_preprocess(const unsigned char* img_bgr, const unsigned char* label, int B, int Hs, int Ws, int H, int W, int gray,
+                  float* x_out, long long* y_out, void* stream);
+
 /* launch accounting: number of kernels this library has launched (kernel_class < 0: all classes), and optional
  * per-class CUDA-event timing for bench.py's roofline (classes: 0 dense_fwd, 1 gemm_px, 2 dgrad_dense, 3 dgrad_td,
  * 4 wgrad, 5 head, 6 dz_prepare, 7 channel_stats, 8 first_fwd, 9 tu_col2im, 10 pack, 11 optimizer, 12 misc).

@@ -1,2 +1,1 @@
-timeout 300 python -m pytest tests/test_forward_gpu.py -m gpu -q -x 2>&1 | tail -2
-timeout 120 python tools/per_launch.py dense_fwd 2>&1 | tail -1
+RL_EXP_PLANAR=1 RL_FWD_DBG=128 timeout 120 python tools/per_launch.py dense_fwd 2>&1 | tail -1
