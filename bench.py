@@ -228,14 +228,21 @@ def run_b200(args, rank, world, local_rank):
         opt.step()
         return loss
 
-    xin = torch.empty(B, 3, H, W, device=dev)
-    yin = torch.empty(B, H, W, dtype=torch.int64, device=dev)
     loss_host = torch.empty(1, pin_memory=True)
+    # end to end: pinned HOST batches, each copied to the device inside the timed region (one H2D per step, issued by the
+    # package's DevicePrefetcher on a copy stream one step ahead), and the loss read back to the host every step
+    from sim2real_lane_segment_b200.prefetch import DevicePrefetcher
+
+    def host_batches():
+        i = 0
+        while True:
+            yield host[i % nb]
+            i += 1
+
+    feed = iter(DevicePrefetcher(host_batches(), dev))
 
     def step_e2e(i):
-        hx, hy = host[i % nb]
-        xin.copy_(hx, non_blocking=True)
-        yin.copy_(hy, non_blocking=True)
+        xin, yin = next(feed)
         opt.zero_grad()
         loss = model.training_step((xin, yin), i)
         loss.backward()

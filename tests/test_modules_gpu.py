@@ -107,3 +107,19 @@ def test_generic_autograd_path_matches_fused_loss():
     gb = rt.grads.clone()
     assert abs(float(loss_a) - float(loss_b)) < 1e-4
     assert float((ga - gb).norm() / gb.norm()) < 2e-2
+
+
+@pytest.mark.gpu
+def test_device_prefetcher_delivers_every_batch_in_order():
+    from sim2real_lane_segment_b200.prefetch import DevicePrefetcher
+    host = [(torch.randn(4, 3, 32, 32).pin_memory(), torch.randint(0, 4, (4, 32, 32)).pin_memory()) for _ in range(7)]
+    got = []
+    for x, y in DevicePrefetcher(host):
+        assert x.is_cuda and y.is_cuda
+        # consume on the current stream (a slow op keeps the buffer busy while the next copy is staged)
+        got.append(((x * 1.0).clone(), y.clone(), float((x @ x.transpose(-1, -2)).sum())))
+    torch.cuda.synchronize()
+    assert len(got) == 7
+    for (hx, hy), (dx, dy, _) in zip(host, got):
+        assert torch.equal(dx.cpu(), hx) and torch.equal(dy.cpu(), hy)
+    assert list(DevicePrefetcher([])) == []
