@@ -106,6 +106,12 @@ int rl_sgd_nesterov_step(float* params, const float* grads, float* momentum_buf,
 int rl_preprocess(const unsigned char* img_bgr, const unsigned char* label, int B, int Hs, int Ws, int H, int W, int gray,
                   float* x_out, long long* y_out, void* stream);
 
+/* Inference consumer (makeDemoVideo.py:36-42, comparison.py:44-58): out uint8 [B][H][W][3] = cv2.resize(frame, (W,H))
+ * (INTER_LINEAR, bit-exact) with the predicted classes painted over it in BGR: 1 -> (0,255,0), 2 -> (255,0,0),
+ * 3 -> (0,0,255).  mask: uint8 (rl_head's mask output) or int64 [B][H][W]. */
+int rl_overlay(const unsigned char* frames_bgr, int B, int Hs, int Ws, int H, int W, const void* mask, int mask_is_i64,
+               unsigned char* out, void* stream);
+
 /* launch accounting: number of kernels this library has launched (kernel_class < 0: all classes), and optional
  * per-class CUDA-event timing for bench.py's roofline (classes: 0 dense_fwd, 1 gemm_px, 2 dgrad_dense, 3 dgrad_td,
  * 4 wgrad, 5 head, 6 dz_prepare, 7 channel_stats, 8 first_fwd, 9 tu_col2im, 10 pack, 11 optimizer, 12 misc).

@@ -104,3 +104,13 @@ def my_transform(img_bgr, label=None, width=160, height=120, gray=False):
     if label is not None and label.ndim >= 2:
         y = resize_nearest_u8(label, height, width).squeeze().astype(np.int64)
     return x, y
+
+
+def overlay(frame_bgr, pred, width=160, height=120):
+    """makeDemoVideo.py:38-42: `cv2.resize(frame, framesize, cv2.INTER_LANCZOS4)` passes the flag in the *dst* position, so
+    the resize runs with the default INTER_LINEAR; then the three non-background classes are painted (BGR)."""
+    out = resize_linear_u8(frame_bgr, height, width)
+    out[pred == 1] = (0, 255, 0)
+    out[pred == 2] = (255, 0, 0)
+    out[pred == 3] = (0, 0, 255)
+    return out

@@ -25,6 +25,46 @@ __device__ __forceinline__ int cv_round_to_short(float v) {
   return max(-32768, min(32767, r));
 }
 
+// cv2.resize(src, (W, H)) with INTER_LINEAR (the default), uint8, 3 channels: one output pixel
+__device__ __forceinline__ void resize_linear_px(const uint8_t* src, int Hs, int Ws, int H, int W, double scale_x, double scale_y,
+                                                 int dx, int dy, int* v) {
+  if (Hs == H && Ws == W) {  // same size: copy
+    const uint8_t* p = src + ((size_t)dy * Ws + dx) * 3;
+    v[0] = p[0];
+    v[1] = p[1];
+    v[2] = p[2];
+    return;
+  }
+  float fx = (float)(((double)dx + 0.5) * scale_x - 0.5);
+  int sx = (int)floorf(fx);
+  fx -= (float)sx;
+  if (sx < 0) {
+    fx = 0.f;
+    sx = 0;
+  }
+  if (sx >= Ws - 1) {
+    fx = 0.f;
+    sx = Ws - 1;
+  }
+  const int a0 = cv_round_to_short((1.f - fx) * 2048.f), a1 = cv_round_to_short(fx * 2048.f);
+  const int sx1 = min(sx + 1, Ws - 1);
+  float fy = (float)(((double)dy + 0.5) * scale_y - 0.5);
+  const int sy = (int)floorf(fy);
+  fy -= (float)sy;
+  const int b0 = cv_round_to_short((1.f - fy) * 2048.f), b1 = cv_round_to_short(fy * 2048.f);
+  const int r0 = max(0, min(sy, Hs - 1)), r1 = max(0, min(sy + 1, Hs - 1));
+  const uint8_t* p00 = src + ((size_t)r0 * Ws + sx) * 3;
+  const uint8_t* p01 = src + ((size_t)r0 * Ws + sx1) * 3;
+  const uint8_t* p10 = src + ((size_t)r1 * Ws + sx) * 3;
+  const uint8_t* p11 = src + ((size_t)r1 * Ws + sx1) * 3;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const int S0 = p00[c] * a0 + p01[c] * a1, S1 = p10[c] * a0 + p11[c] * a1;
+    const int o = (((b0 * (S0 >> 4)) >> 16) + ((b1 * (S1 >> 4)) >> 16) + 2) >> 2;
+    v[c] = max(0, min(255, o));
+  }
+}
+
 __global__ void __launch_bounds__(256) preprocess_kernel(PrepArgs a) {
   const long n = (long)a.B * a.H * a.W;
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
@@ -33,41 +73,7 @@ __global__ void __launch_bounds__(256) preprocess_kernel(PrepArgs a) {
     const int b = (int)(i / ((long)a.W * a.H));
     const uint8_t* src = a.img + (size_t)b * a.Hs * a.Ws * 3;
     int v[3];
-    if (a.Hs == a.H && a.Ws == a.W) {  // cv2.resize to the same size is a copy
-      const uint8_t* p = src + ((size_t)dy * a.Ws + dx) * 3;
-      v[0] = p[0];
-      v[1] = p[1];
-      v[2] = p[2];
-    } else {
-      float fx = (float)(((double)dx + 0.5) * a.scale_x - 0.5);
-      int sx = (int)floorf(fx);
-      fx -= (float)sx;
-      if (sx < 0) {
-        fx = 0.f;
-        sx = 0;
-      }
-      if (sx >= a.Ws - 1) {
-        fx = 0.f;
-        sx = a.Ws - 1;
-      }
-      const int a0 = cv_round_to_short((1.f - fx) * 2048.f), a1 = cv_round_to_short(fx * 2048.f);
-      const int sx1 = min(sx + 1, a.Ws - 1);
-      float fy = (float)(((double)dy + 0.5) * a.scale_y - 0.5);
-      const int sy = (int)floorf(fy);
-      fy -= (float)sy;
-      const int b0 = cv_round_to_short((1.f - fy) * 2048.f), b1 = cv_round_to_short(fy * 2048.f);
-      const int r0 = max(0, min(sy, a.Hs - 1)), r1 = max(0, min(sy + 1, a.Hs - 1));
-      const uint8_t* p00 = src + ((size_t)r0 * a.Ws + sx) * 3;
-      const uint8_t* p01 = src + ((size_t)r0 * a.Ws + sx1) * 3;
-      const uint8_t* p10 = src + ((size_t)r1 * a.Ws + sx) * 3;
-      const uint8_t* p11 = src + ((size_t)r1 * a.Ws + sx1) * 3;
-#pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        const int S0 = p00[c] * a0 + p01[c] * a1, S1 = p10[c] * a0 + p11[c] * a1;
-        const int o = (((b0 * (S0 >> 4)) >> 16) + ((b1 * (S1 >> 4)) >> 16) + 2) >> 2;
-        v[c] = max(0, min(255, o));
-      }
-    }
+    resize_linear_px(src, a.Hs, a.Ws, a.H, a.W, a.scale_x, a.scale_y, dx, dy, v);
     if (a.gray) {  // cv2 COLOR_RGB2GRAY (15-bit weights) on the channels as they are, then GRAY2RGB
       const int g = (v[0] * 9798 + v[1] * 19235 + v[2] * 3735 + (1 << 14)) >> 15;
       v[0] = v[1] = v[2] = g;
@@ -86,7 +92,45 @@ __global__ void __launch_bounds__(256) preprocess_kernel(PrepArgs a) {
   }
 }
 
+// makeDemoVideo.py:38-42 / comparison.py: the frame resized to the network resolution with the predicted classes painted
+// over it (BGR): 1 right lane (0,255,0), 2 left lane (255,0,0), 3 obstacles (0,0,255); class 0 keeps the frame.
+__global__ void __launch_bounds__(256) overlay_kernel(const uint8_t* frames, int B, int Hs, int Ws, int H, int W, double scale_x,
+                                                      double scale_y, const uint8_t* mask8, const long long* mask64, uint8_t* out) {
+  const long n = (long)B * H * W;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    const int dx = (int)(i % W), dy = (int)((i / W) % H), b = (int)(i / ((long)W * H));
+    int v[3];
+    resize_linear_px(frames + (size_t)b * Hs * Ws * 3, Hs, Ws, H, W, scale_x, scale_y, dx, dy, v);
+    const int cls = mask8 ? (int)mask8[i] : (int)mask64[i];
+    if (cls == 1) {
+      v[0] = 0; v[1] = 255; v[2] = 0;
+    } else if (cls == 2) {
+      v[0] = 255; v[1] = 0; v[2] = 0;
+    } else if (cls == 3) {
+      v[0] = 0; v[1] = 0; v[2] = 255;
+    }
+    out[i * 3 + 0] = (uint8_t)v[0];
+    out[i * 3 + 1] = (uint8_t)v[1];
+    out[i * 3 + 2] = (uint8_t)v[2];
+  }
+}
+
 }  // namespace rl
+
+extern "C" int rl_overlay(const unsigned char* frames_bgr, int B, int Hs, int Ws, int H, int W, const void* mask, int mask_is_i64,
+                          unsigned char* out, void* stream) {
+  using namespace rl;
+  if (!frames_bgr || !mask || !out) return rl_fail(RL_ERR_ARG, "rl_overlay: null argument");
+  if (B < 1 || Hs < 1 || Ws < 1 || H < 1 || W < 1) return rl_fail(RL_ERR_SHAPE, "rl_overlay: bad shape");
+  const long n = (long)B * H * W;
+  const int grid = (int)std::min<long>((n + 255) / 256, 148L * 16);
+  { ProfScope _ps(KC_MISC, (cudaStream_t)stream);
+  overlay_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(frames_bgr, B, Hs, Ws, H, W, (double)Ws / W, (double)Hs / H,
+                                                         mask_is_i64 ? nullptr : (const uint8_t*)mask,
+                                                         mask_is_i64 ? (const long long*)mask : nullptr, out); }
+  RL_CUDA(cudaGetLastError());
+  return RL_OK;
+}
 
 extern "C" int rl_preprocess(const unsigned char* img_bgr, const unsigned char* label, int B, int Hs, int Ws, int H, int W,
                              int gray, float* x_out, long long* y_out, void* stream) {

@@ -83,6 +83,8 @@ class Trainer:
             train_dataloader = datamodule.train_dataloader()
             val_dataloaders = datamodule.val_dataloader() if hasattr(datamodule, "val_dataloader") else None
         model.trainer = self
+        self.model = model
+        self.current_epoch, self.global_step = 0, 0
         opts, scheds = model.configure_optimizers()
         dev = model.device
         for epoch in range(self.max_epochs):
@@ -96,8 +98,10 @@ class Trainer:
                     loss = model.training_step(batch, bi, oi) if len(opts) > 1 else model.training_step(batch, bi)
                     loss.backward()
                     opt.step()
+                self.global_step += 1
             for s in scheds:
                 s.step()
+            self.current_epoch = epoch + 1
             if val_dataloaders is not None:
                 model.eval()
                 outs = []
@@ -107,6 +111,24 @@ class Trainer:
                         outs.append(model.validation_step(batch, bi))
                 model.validation_epoch_end(outs)
         return model
+
+    def save_checkpoint(self, filepath, model=None):
+        """checkpoint file with the keys pytorch-lightning 1.2.1 writes and `load_from_checkpoint` reads (test.py:28-30,
+        makeDemoVideo.py:52-54): state_dict (434 entries, the reference's names), hyper_parameters, epoch, global_step"""
+        model = model if model is not None else getattr(self, "model", None)
+        if model is None:
+            raise ValueError("save_checkpoint: no model (call fit() first or pass model=)")
+        if hasattr(model, "runtime"):
+            torch.cuda.synchronize() if torch.cuda.is_available() else None
+        ckpt = {
+            "epoch": getattr(self, "current_epoch", 0),
+            "global_step": getattr(self, "global_step", 0),
+            "pytorch-lightning_version": "1.2.1",
+            "state_dict": {k: v.detach().cpu().clone() for k, v in model.state_dict().items()},
+            "hyper_parameters": dict(vars(model.hparams)) if hasattr(model, "hparams") else {},
+        }
+        torch.save(ckpt, filepath)
+        return filepath
 
     def test(self, model, test_dataloaders=None):
         model.eval()

@@ -86,3 +86,23 @@ def _worker(rank, world, port, n):
 def test_gradient_exchange_world_size_2_gloo():
     port = 29500 + os.getpid() % 2000
     mp.spawn(_worker, args=(2, port, 100003), nprocs=2, join=True)
+
+
+def test_checkpoint_roundtrip_has_lightning_121_layout(tmp_path):
+    """Trainer.save_checkpoint writes what `load_from_checkpoint(checkpoint_path=..., num_cls=4)` (test.py:28-30) reads:
+    state_dict under the reference's 434 names, hyper_parameters, epoch / global_step"""
+    import torch
+    from oracle import fcdensenet as net
+    from sim2real_lane_segment_b200.pl_shim import Trainer
+    from sim2real_lane_segment_b200.trainingModules import SimpleTrainModule
+    m = SimpleTrainModule(lr=2e-3, decay=1e-4, lrRatio=100, num_cls=4)
+    path = Trainer().save_checkpoint(str(tmp_path / "m.ckpt"), model=m)
+    ck = torch.load(path)
+    assert {"state_dict", "hyper_parameters", "epoch", "global_step", "pytorch-lightning_version"} <= set(ck)
+    assert list(ck["state_dict"].keys()) == list(net.init_state_dict(num_cls=4, seed=0).keys())
+    # the reference saves lr / decay / lrRatio only (TrainingBase.py:29): num_cls travels as a load_from_checkpoint kwarg
+    assert ck["hyper_parameters"] == {"lr": 2e-3, "decay": 1e-4, "lrRatio": 100}
+    m2 = SimpleTrainModule.load_from_checkpoint(checkpoint_path=path, num_cls=4)
+    assert m2.lr == 2e-3 and m2.lrRatio == 100
+    for (k1, v1), (k2, v2) in zip(m.state_dict().items(), m2.state_dict().items()):
+        assert k1 == k2 and torch.equal(v1, v2)

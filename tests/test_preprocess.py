@@ -65,3 +65,40 @@ def test_rl_preprocess_batch_and_ragged_sizes():
     assert y is None and x.shape == (3, 120, 160)
     with pytest.raises(NotImplementedError):
         MyTransform(augment=True)
+
+
+@pytest.mark.gpu
+def test_overlay_and_demo_frames_match_the_oracle():
+    """makeDemoVideo body: frame -> MyTransform -> forward -> argmax -> painted, resized frame.  The overlay is checked
+    bit-exactly against the oracle fed with OUR mask; the mask against the argmax of our own probabilities."""
+    import ctypes
+    from sim2real_lane_segment_b200 import _lib
+    from sim2real_lane_segment_b200.dataManagement.myTransforms import MyTransform
+    from sim2real_lane_segment_b200.makeDemoVideo import predictFrames
+    from sim2real_lane_segment_b200.trainingModules import SimpleTrainModule
+    rng = np.random.default_rng(5)
+    # kernel alone, both mask dtypes
+    L = _lib.lib()
+    frames = rng.integers(0, 256, (3, 90, 130, 3), dtype=np.uint8)
+    pred = rng.integers(0, 4, (3, 60, 80), dtype=np.uint8)
+    want = np.stack([pp.overlay(frames[b], pred[b], width=80, height=60) for b in range(3)])
+    fr = torch.from_numpy(frames).cuda()
+    for dt, flag in ((torch.uint8, 0), (torch.int64, 1)):
+        mk = torch.from_numpy(pred).to(dt).cuda()
+        out = torch.empty(3, 60, 80, 3, dtype=torch.uint8, device="cuda")
+        rc = L.rl_overlay(ctypes.c_void_p(fr.data_ptr()), 3, 90, 130, 60, 80, ctypes.c_void_p(mk.data_ptr()), flag,
+                          ctypes.c_void_p(out.data_ptr()), ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+        assert rc == 0
+        assert np.array_equal(out.cpu().numpy(), want)
+    # whole consumer path
+    torch.manual_seed(0)
+    model = SimpleTrainModule(num_cls=4).cuda().eval()
+    frames = rng.integers(0, 256, (2, 240, 320, 3), dtype=np.uint8)
+    tf = MyTransform(width=160, height=120)
+    out, mask = predictFrames(frames, model, tf)
+    x, _ = tf(frames)
+    with torch.no_grad():
+        _, ref_mask = torch.max(model.forward(x), 1)
+    assert torch.equal(mask.long(), ref_mask)
+    want = np.stack([pp.overlay(frames[b], mask[b].cpu().numpy(), width=160, height=120) for b in range(2)])
+    assert np.array_equal(out.cpu().numpy(), want)
