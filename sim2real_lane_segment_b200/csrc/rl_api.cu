@@ -154,7 +154,7 @@ int rl_plan_bind(rl_plan* h, void* workspace, void* stream) {
   // ---- tensor maps of the level arenas (activation tiles of the DenseLayer forward go through the TMA engine)
   p.tmap_ok = true;
   for (int l = 0; l < kLevels; ++l) {
-    int rc = encode_arena_tmap(p.tmap_act[l], act_of(&p, l), p.lv[l].px, p.lv[l].Ct);
+    int rc = encode_arena_tmap(p.tmap_act[l], act_of(&p, l), p.lv[l].px, p.lv[l].Ct, p.lv[l].W);
     if (rc) return rc;
   }
   if (p.training && !p.side_stream) {
@@ -220,9 +220,14 @@ int rl_forward(rl_plan* h, const float* params, const float* bnbuf, const float*
       a.H = li.H;
       a.W = li.W;
       a.rows_total = p->B * li.H;
-      a.strip_w = 160;
-      a.nstrips = (li.W + a.strip_w - 1) / a.strip_w;
-      const bool use_tma = g_fwd_tma && a.nstrips == 1 && p->tmap_ok;
+      const bool use_tma = g_fwd_tma && p->tmap_ok;
+      if (use_tma && li.W > 160) {  // strips whose 128-column input window (strip + 2 halo columns) is one TMA box row
+        a.nstrips = (li.W + 125) / 126;
+        a.strip_w = (li.W + a.nstrips - 1) / a.nstrips;
+      } else {
+        a.strip_w = 160;
+        a.nstrips = (li.W + a.strip_w - 1) / a.strip_w;
+      }
       int nruns = std::max(1, std::min(a.rows_total, ((use_tma ? 1 : 2) * sm) / a.nstrips));
       a.rows_per_cta = (a.rows_total + nruns - 1) / nruns;
       nruns = (a.rows_total + a.rows_per_cta - 1) / a.rows_per_cta;
@@ -233,7 +238,7 @@ int rl_forward(rl_plan* h, const float* params, const float* bnbuf, const float*
       a.stats_out = train ? stats_of(p, L.lvl_in) : nullptr;
       a.dbg = g_fwd_dbg;
       if (use_tma) {
-        if ((rc = launch_dense_fwd_tma(a, p->tmap_act[L.lvl_in], nruns, st))) return rc;
+        if ((rc = launch_dense_fwd_tma(a, p->tmap_act[L.lvl_in], nruns * a.nstrips, st))) return rc;
       } else if ((rc = launch_dense_fwd(a, nruns * a.nstrips, st))) return rc;
     } else if (L.type == L_TD) {
       GemmPxArgs a;

@@ -303,6 +303,7 @@ struct alignas(64) DenseFwdTmaArgs {
   DenseFwdArgs a;
   int na;          // activation ring depth (3..6 stages of 16 KB)
   int w_resident;  // all weight chunks stay in shared memory for the whole CTA (else a 3-deep streaming ring)
+  int strip_mode;  // 0: full-width rows through a 2-D map; 1: 128-column strips through a 3-D map (ch, x, row)
 };
 
 __device__ __forceinline__ void epilogue_sync() { asm volatile("bar.sync 2, 128;" ::: "memory"); }
@@ -312,6 +313,13 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* t
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
           smem_u32(smem_dst)),
       "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* tm, int c0, int c1, int c2, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
 // K-major operand in the canonical 128-byte-swizzle layout (rows of 64 bf16, 8-row atoms 1024 B apart)
@@ -344,9 +352,17 @@ __global__ void __launch_bounds__(kF2Threads, 1) dense_fwd_tma_kernel(const __gr
   __shared__ __align__(16) float s_bias16[16];
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int R0 = blockIdx.x * a.rows_per_cta, R1 = min(R0 + a.rows_per_cta, a.rows_total);
+  // work item: output rows [R0,R1) of the level (all images stacked) x output columns [x0,x1).  Full-width mode: the
+  // input window is the whole row (SW = W, 128 consecutive arena pixels per tile).  Strip mode (levels wider than 160):
+  // the input window of a strip is always the 128 columns [xs, xs+128) with xs = x0-1, one image row per tile, fetched
+  // through a 3-D tensor map whose out-of-range columns (x = -1, x >= W) arrive as zeros.
+  const bool strips = P.strip_mode != 0;
+  const int run = strips ? blockIdx.x / a.nstrips : blockIdx.x, strip = strips ? blockIdx.x % a.nstrips : 0;
+  const int R0 = run * a.rows_per_cta, R1 = min(R0 + a.rows_per_cta, a.rows_total);
   const int rin0 = max(R0 - 1, 0), rin1 = min(R1 + 1, a.rows_total);
-  const int SW = a.W;
+  const int x0 = strips ? strip * a.strip_w : 0, x1 = strips ? min(x0 + a.strip_w, a.W) : a.W;
+  const int xs = strips ? x0 - 1 : 0;
+  const int SW = strips ? 128 : a.W;
   const int n_in = (rin1 - rin0) * SW;
   const int ntiles = (n_in + 127) / 128;
   const uint32_t total = (uint32_t)ntiles * (uint32_t)nkc;
@@ -392,7 +408,8 @@ __global__ void __launch_bounds__(kF2Threads, 1) dense_fwd_tma_kernel(const __gr
             mbar_arrive(&a_full[s]);
           } else {
             mbar_arrive_expect_tx(&a_full[s], kF2ABytes);
-            tma_load_2d(sA + s * kF2ABytes, &P.tmap, kc * 64, P0 + tile * 128, &a_full[s]);
+            if (strips) tma_load_3d(sA + s * kF2ABytes, &P.tmap, kc * 64, xs, rin0 + tile, &a_full[s]);
+            else tma_load_2d(sA + s * kF2ABytes, &P.tmap, kc * 64, P0 + tile * 128, &a_full[s]);
           }
           if (++s == NA) {
             s = 0;
@@ -520,13 +537,14 @@ __global__ void __launch_bounds__(kF2Threads, 1) dense_fwd_tma_kernel(const __gr
       mbar_wait(&acc_full[buf], (tile >> 1) & 1);
       tc_fence_after();
       const int t = t0 + et;
-      const bool in_valid = t < n_in;
+      bool in_valid = t < n_in;
       int rr = 0, cc = 0;
       if (in_valid) {
         rr = t / SW;
         cc = t - rr * SW;
       }
-      const int r = rin0 + rr, xx = cc;
+      const int r = rin0 + rr, xx = xs + cc;
+      in_valid = in_valid && xx >= 0 && xx < a.W;  // strip mode: columns of the window that lie outside the image
       const int ri = r % a.H;
       // Tap slots are packed dx-major, so one dx group = 48 consecutive accumulator columns = the three dy taps.
       // Within a tile (128 consecutive pixels) two threads can only meet in a ring slot through different dx when
@@ -552,7 +570,7 @@ __global__ void __launch_bounds__(kF2Threads, 1) dense_fwd_tma_kernel(const __gr
           tmem_ld16_nowait(tacc + (dxi + 1) * 48 + 32, vn + 32);
         }
         const int qx = xx - dx;
-        const bool okx = in_valid && qx >= 0 && qx < a.W && !(a.dbg & 4);
+        const bool okx = in_valid && qx >= x0 && qx < x1 && !(a.dbg & 4);
 #pragma unroll
         for (int dyi = 0; dyi < 3; ++dyi) {
           const int dy = dyi - 1;
@@ -592,8 +610,8 @@ __global__ void __launch_bounds__(kF2Threads, 1) dense_fwd_tma_kernel(const __gr
         const int e = e0 + et;
         if (e < lim) {
           const int er = e / SW, ec = e - er * SW;
-          const int orow = rin0 + er, ox = ec;
-          if (orow >= R0 && orow < R1) {
+          const int orow = rin0 + er, ox = xs + ec;
+          if (orow >= R0 && orow < R1 && ox >= x0 && ox < x1) {
             const int uidx = (e + SW + 1) & (kRing - 1);
             const int img = orow / a.H;
             float o[16];
@@ -670,10 +688,13 @@ int launch_dense_fwd_tma(const DenseFwdArgs& a, const void* tmap, int grid, cuda
     RL_CUDA(cudaFuncSetAttribute(dense_fwd_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCap));
     configured = true;
   }
-  if (a.nstrips != 1 || a.W > 160) return rl_fail(RL_ERR_SHAPE, "dense_fwd_tma: needs a full-width strip");
+  const int strip_mode = a.W > 160;
+  if (!strip_mode && a.nstrips != 1) return rl_fail(RL_ERR_SHAPE, "dense_fwd_tma: a level up to 160 wide is one strip");
+  if (strip_mode && (a.strip_w < 1 || a.strip_w > 126)) return rl_fail(RL_ERR_SHAPE, "dense_fwd_tma: strips are at most 126 wide");
   DenseFwdTmaArgs P;
   memcpy(&P.tmap, tmap, sizeof(CUtensorMap));
   P.a = a;
+  P.strip_mode = strip_mode;
   const int nkc = (a.Cin + 63) / 64;
   const size_t fixed = 1024 + 4 * kRing * 16 + (size_t)a.Cin * 8;
   const size_t wall = (size_t)nkc * kF2WBytes;
@@ -691,7 +712,7 @@ int launch_dense_fwd_tma(const DenseFwdArgs& a, const void* tmap, int grid, cuda
   return RL_OK;
 }
 
-int encode_arena_tmap(void* tmap_out, const void* arena, long npx, int Ct) {
+int encode_arena_tmap(void* tmap_out, const void* arena, long npx, int Ct, int W) {
   typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -704,11 +725,13 @@ int encode_arena_tmap(void* tmap_out, const void* arena, long npx, int Ct) {
     fn = (EncodeFn)f;
   }
   CUtensorMap tm;
-  const cuuint64_t dims[2] = {(cuuint64_t)Ct, (cuuint64_t)npx};
-  const cuuint64_t strides[1] = {(cuuint64_t)Ct * 2};
-  const cuuint32_t box[2] = {64, 128};
-  const cuuint32_t estr[2] = {1, 1};
-  const CUresult r = fn(&tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(arena), dims, strides, box, estr,
+  // levels up to 160 wide: [pixels][Ct], box 128 px x 64 ch; wider levels: [rows][W][Ct], box 1 row x 128 columns x 64 ch
+  const bool three = W > 160;
+  const cuuint64_t dims[3] = {(cuuint64_t)Ct, (cuuint64_t)(three ? W : npx), (cuuint64_t)(three ? npx / W : 1)};
+  const cuuint64_t strides[2] = {(cuuint64_t)Ct * 2, (cuuint64_t)Ct * 2 * (cuuint64_t)W};
+  const cuuint32_t box[3] = {64, 128, 1};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  const CUresult r = fn(&tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, three ? 3 : 2, const_cast<void*>(arena), dims, strides, box, estr,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return rl_fail(RL_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) for [%ld][%d]", (int)r, npx, Ct);

@@ -22,10 +22,10 @@ struct DenseFwdArgs {
   int dbg;                   // triage switches (RL_FWD_DBG), 0 in production
 };
 int launch_dense_fwd(const DenseFwdArgs& a, int grid, cudaStream_t st);
-// TMA-fed variant (full-width strips only): tmap = the level arena's 128-byte CUtensorMap blob
+// TMA-fed variant (levels up to 160 wide: full rows; wider levels: strips of at most 126 columns): tmap = the level arena's 128-byte CUtensorMap blob
 int launch_dense_fwd_tma(const DenseFwdArgs& a, const void* tmap, int grid, cudaStream_t st);
 // host: encode a [pixels][Ct] bf16 arena as a 2-D tiled tensor map, box 128 px x 64 channels, SWIZZLE_128B
-int encode_arena_tmap(void* tmap_out, const void* arena, long npx, int Ct);
+int encode_arena_tmap(void* tmap_out, const void* arena, long npx, int Ct, int W);
 
 enum { GEMM_LINEAR = 0, GEMM_POOL = 1 };
 struct GemmPxArgs {

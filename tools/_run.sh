@@ -1,1 +1,2 @@
-RL_EXP_PLANAR=1 RL_FWD_DBG=128 timeout 120 python tools/per_launch.py dense_fwd 2>&1 | tail -1
+timeout 900 python -m pytest tests -m gpu -q -x 2>&1 | tail -3
+timeout 600 python tools/practical_bar.py > gpurun_out/practical_bar.json 2> gpurun_out/practical_bar.err; cat gpurun_out/practical_bar.json
