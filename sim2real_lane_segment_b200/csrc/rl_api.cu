@@ -192,6 +192,12 @@ static bool g_fwd_tma = []() {
   return !(e && e[0] == '0');
 }();
 
+// compact [px][16] side copies of DenseLayer outputs / output gradients for dz_prepare (RL_COMPACT16=0 disables)
+static const bool g_compact16 = []() {
+  const char* e = getenv("RL_COMPACT16");
+  return !(e && e[0] == '0');
+}();
+
 static const int g_fwd_dbg = []() {
   const char* e = getenv("RL_FWD_DBG");
   return e ? atoi(e) : 0;
@@ -237,6 +243,7 @@ int rl_forward(rl_plan* h, const float* params, const float* bnbuf, const float*
       a.bn = make_bn(p, L, params, bnbuf, train);
       a.stats_out = train ? stats_of(p, L.lvl_in) : nullptr;
       a.dbg = g_fwd_dbg;
+      a.x16 = (train && p->training && g_compact16 && L.x16_off) ? (__nv_bfloat16*)(wsb(p) + L.x16_off) : nullptr;
       if (use_tma) {
         if ((rc = launch_dense_fwd_tma(a, p->tmap_act[L.lvl_in], nruns * a.nstrips, st))) return rc;
       } else if ((rc = launch_dense_fwd(a, nruns * a.nstrips, st))) return rc;
@@ -471,6 +478,10 @@ extern "C" int rl_backward(rl_plan* h, const float* params, const float* x, floa
     if (L.type == L_DENSE) {
       z.kind = 0;
       z.mask = (const float*)(wsb(p) + L.mask_off);
+      if (g_compact16 && L.x16_off) {
+        z.x16c = (const __nv_bfloat16*)(wsb(p) + L.x16_off);
+        if (L.dx16_from_next) z.dx16c = (const __nv_bfloat16*)(wsb(p) + lin.dx16_off);
+      }
       const int q = dense_count++ & 1;  // dz buffer of this layer
       z.planes = 1;
       z.dz = (__nv_bfloat16*)(wsb(p) + lin.dzp_off + (size_t)q * lin.dzp_npos * 32);
@@ -489,6 +500,7 @@ extern "C" int rl_backward(rl_plan* h, const float* params, const float* x, floa
       d.dz_guard = lin.dzp_guard;
       d.Kdz = 16;
       d.wpk = wsb(p) + L.wpk_bwd;
+      if (g_compact16 && li > 0 && p->layers[li - 1].dx16_from_next) d.dx16_out = (__nv_bfloat16*)(wsb(p) + lin.dx16_off);
       d.act = act_of(p, L.lvl_in);
       d.dact = dact_of(p, L.lvl_in);
       d.Ct = lin.Ct;

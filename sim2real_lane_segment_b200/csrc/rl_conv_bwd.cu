@@ -164,7 +164,8 @@ __device__ __forceinline__ float warp_colsum8(float* sc, const float* gs, const 
 template <bool kSmemSums>
 __device__ __forceinline__ void dgrad_epilogue(uint32_t tmem_acc, int warp, int lane, const __nv_bfloat16* xrow,
                                                __nv_bfloat16* drow, int cbase, int nvalid, const DgradConsts* k,
-                                               const DgradArgs& a, float* S1, float* S2, DgradPre* pre, float* s_scr) {
+                                               const DgradArgs& a, float* S1, float* S2, DgradPre* pre, float* s_scr,
+                                               __nv_bfloat16* d16row = nullptr) {
   float* sc = kSmemSums ? s_scr + warp * kScrPerWarp : nullptr;
 #pragma unroll
   for (int gi = 0; gi < 8; ++gi) {
@@ -218,6 +219,9 @@ __device__ __forceinline__ void dgrad_epilogue(uint32_t tmem_acc, int warp, int 
           *reinterpret_cast<uint4*>(drow + c0) = dpk[0];
           *reinterpret_cast<uint4*>(drow + c0 + 8) = dpk[1];
         }
+        // the last 16 input channels are the previous DenseLayer's output and this is their final gradient: leave a
+        // dense copy for that layer's dz_prepare
+        if (d16row != nullptr && cbase + c0 == a.Cin - 16) st256(d16row, dpk[0], dpk[1]);
       }
       // lane (up, q, col) keeps quantity q (0: Σg, 1: Σg(x-mean)) of channel 8*up + col of this group
       S1[gi] += (lane & 16) ? rs[1] : rs[0];
@@ -367,6 +371,7 @@ __global__ void __launch_bounds__(128, 3) dgrad_dense_kernel(DgradArgs a) {
       }
       const __nv_bfloat16* xrow = P >= 0 ? a.act + (size_t)P * a.Ct + mb * 128 : nullptr;
       __nv_bfloat16* drow = P >= 0 ? a.dact + (size_t)P * a.Ct + mb * 128 : nullptr;
+      __nv_bfloat16* d16row = (P >= 0 && a.dx16_out != nullptr) ? a.dx16_out + (size_t)P * 16 : nullptr;
       DgradPre pre[2];
       dgrad_prefetch(pre[0], xrow, drow, 0, nvalid, (mb * 128) >= a.rmw_from, a.variant);
       dgrad_prefetch(pre[1], xrow, drow, 16, nvalid, (mb * 128 + 16) >= a.rmw_from, a.variant);
@@ -388,7 +393,7 @@ __global__ void __launch_bounds__(128, 3) dgrad_dense_kernel(DgradArgs a) {
       mbar_wait(&bar_mma, n_mma & 1);
       ++n_mma;
       tc_fence_after();
-      dgrad_epilogue<false>(tmem, warp, lane, xrow, drow, mb * 128, nvalid, kc, a, S1, S2, pre, nullptr);
+      dgrad_epilogue<false>(tmem, warp, lane, xrow, drow, mb * 128, nvalid, kc, a, S1, S2, pre, nullptr, d16row);
       tc_fence_before();
     }
     if (ntiles == 0 && tid == 0) mbar_wait(&bar_w, n_w & 1);

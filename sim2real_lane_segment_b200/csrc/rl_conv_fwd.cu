@@ -252,6 +252,9 @@ __global__ void __launch_bounds__(kFwdThreads, 2) dense_fwd_kernel(DenseFwdArgs 
             }
             st256(a.act_out + ((size_t)orow * a.W + ox) * a.Ct + a.Cin, make_uint4(pk[0], pk[1], pk[2], pk[3]),
                   make_uint4(pk[4], pk[5], pk[6], pk[7]));
+            if (a.x16 != nullptr)
+              st256(a.x16 + ((size_t)orow * a.W + ox) * 16, make_uint4(pk[0], pk[1], pk[2], pk[3]),
+                    make_uint4(pk[4], pk[5], pk[6], pk[7]));
           }
         }
       }
@@ -653,6 +656,9 @@ __global__ void __launch_bounds__(kF2Threads, 1) dense_fwd_tma_kernel(const __gr
             }
             st256(a.act_out + ((size_t)orow * a.W + ox) * a.Ct + a.Cin, make_uint4(pk[0], pk[1], pk[2], pk[3]),
                   make_uint4(pk[4], pk[5], pk[6], pk[7]));
+            if (a.x16 != nullptr)
+              st256(a.x16 + ((size_t)orow * a.W + ox) * 16, make_uint4(pk[0], pk[1], pk[2], pk[3]),
+                    make_uint4(pk[4], pk[5], pk[6], pk[7]));
           }
         }
       }

@@ -20,6 +20,7 @@ struct DenseFwdArgs {
   BnSrc bn;
   double* stats_out;         // level stats base (Σx at [c], Σx² at [Ct+c]) or null
   int dbg;                   // triage switches (RL_FWD_DBG), 0 in production
+  __nv_bfloat16* x16;        // training: compact copy [px][16] of the output slice for dz_prepare (or null)
 };
 int launch_dense_fwd(const DenseFwdArgs& a, int grid, cudaStream_t st);
 // TMA-fed variant (levels up to 160 wide: full rows; wider levels: strips of at most 126 columns): tmap = the level arena's 128-byte CUtensorMap blob
@@ -67,6 +68,7 @@ struct DgradArgs {
   int vrows_per_cta, nstrips, strip_w;  // dense work decomposition (virtual rows: H+1 per image)
   long ntiles;                           // td: 128-pixel tiles
   int variant;                           // tuning switches (env RL_VARIANT): bit0 L2::128B hint, bit1 256-bit accesses
+  __nv_bfloat16* dx16_out;               // dense: compact [px][16] copy of the final dX of channels [Cin-16, Cin) (or null)
 };
 int launch_dgrad(const DgradArgs& a, int grid, cudaStream_t st);
 
@@ -143,6 +145,8 @@ struct DzArgs {
   long dz_npos, dz_guard;
   float* g_bias;              // Σ dz per channel -> conv bias gradient (fp32 atomics)
   // TD: output arena is the pooled level; dz is written at the input resolution [px_in][nch]
+  const __nv_bfloat16* x16c;  // kind 0, nch 16: compact [px][16] copies of act / dact slices (or null: read the arenas)
+  const __nv_bfloat16* dx16c;
   const uint8_t* amax;
   int H, W, Hp, Wp, B;        // TD: input H,W and pooled Hp,Wp.  TU: input (low-res) h=Hp,w=Wp and output H,W
 };

@@ -685,8 +685,8 @@ __global__ void __launch_bounds__(256) dz_dense16_kernel(DzArgs a) {
   for (long P = blockIdx.x * (long)blockDim.x + threadIdx.x; P < a.npx_out; P += (long)gridDim.x * blockDim.x) {
     const int img = (int)(P / a.HW_out);
     const int hw = (int)(P - (long)img * a.HW_out), y = hw / a.W, x = hw - y * a.W;
-    const u32x8 dv = ld256_nohint(a.dact + P * a.Ct + a.c_off);
-    const u32x8 xv = ldg256_nc_nohint(a.act + P * a.Ct + a.c_off);
+    const u32x8 dv = a.dx16c ? ld256_nohint(a.dx16c + P * 16) : ld256_nohint(a.dact + P * a.Ct + a.c_off);
+    const u32x8 xv = a.x16c ? ldg256_nc_nohint(a.x16c + P * 16) : ldg256_nc_nohint(a.act + P * a.Ct + a.c_off);
     float dx[16], xx[16], mk[16], o[16];
     unpack8(dv.lo, dx);
     unpack8(dv.hi, dx + 8);

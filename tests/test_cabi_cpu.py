@@ -78,7 +78,8 @@ def test_workspace_size_is_dominated_by_the_arenas(lib):
     px = [64 * (120 >> l) * (160 >> l) for l in range(6)]
     ct = [288, 368, 448, 528, 608, 528]
     arenas = sum(2 * p * c for p, c in zip(px, ct))
-    assert 2 * arenas < ws < 2 * arenas + (3 << 29)     # activations + gradients + < 1.5 GiB of scratch (dz planes, double-buffered TD/TU scratch)
+    # activations + gradients + < 2.25 GiB of scratch (dz planes, double-buffered TD/TU scratch, compact x16 / dX16 copies)
+    assert 2 * arenas < ws < 2 * arenas + (9 << 28)
     rc2, h2 = _plan(lib, 64, 120, 160, 4, training=0)
     assert lib.rl_plan_workspace_bytes(h2) < ws // 2 + (1 << 29)
     lib.rl_plan_destroy(h)
