@@ -892,11 +892,13 @@ __global__ void __launch_bounds__(128, 2) gemm_px_kernel(GemmPxArgs a) {
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
           const float y = (v[i] + s_bias[c0 + i]) * s_mask[c0 + i];
-          float m = fmaxf(y, __shfl_xor_sync(0xffffffffu, y, 1));
-          m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 2));
-          // arg-max inside the 2x2 window = first lane of the quad holding the maximum (torch scans row-major)
-          const unsigned bal = __ballot_sync(0xffffffffu, y == m);
-          const int bq = __ffs((bal >> (lane & 28)) & 0xFu) - 1;
+          // the three other pixels of the 2x2 window sit in the other lanes of the quad: three independent exchanges.
+          // Only lane q == 0 stores, and for it (y, y1, y2, y3) are the window in torch's row-major scan order; the
+          // arg-max is the first position holding the maximum.
+          const float y1 = __shfl_xor_sync(0xffffffffu, y, 1), y2 = __shfl_xor_sync(0xffffffffu, y, 2),
+                      y3 = __shfl_xor_sync(0xffffffffu, y, 3);
+          const float m = fmaxf(fmaxf(y, y1), fmaxf(y2, y3));
+          const int bq = (y == m) ? 0 : (y1 == m) ? 1 : (y2 == m) ? 2 : 3;
           v[i] = m;
           am[i >> 2] |= (uint32_t)bq << (8 * (i & 3));
         }
