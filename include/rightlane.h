@@ -127,6 +127,12 @@ int rl_profile_launches(float* ms, int* kernel_class, int max); /* per-launch ti
  * (0: the register-staged kernel that wider levels always use; both produce identical bits). */
 int rl_set_option(const char* name, int value);
 
+/* test hook: one tcgen05 GEMM (M = 128) from caller-supplied shared-memory images of A and B and the upper bits of both
+ * matrix descriptors (start address filled in by the kernel, advanced by *_kstep_bytes per K = 16 step) */
+int rl_selftest_umma_raw(const void* a_img, int a_bytes, unsigned long long a_desc_tmpl, int a_kstep_bytes,
+                         const void* b_img, int b_bytes, unsigned long long b_desc_tmpl, int b_kstep_bytes, unsigned idesc,
+                         int nk, int N, float* D, void* stream);
+
 /* measurement hook: stream the channel window [c0, c0+nch) of an NHWC bf16 arena [npx][Ct] with 32-byte accesses
  * (mode 0 read, 1 read+write back) -- what the memory system delivers for the access pattern of the concat arenas */
 int rl_selftest_stream(void* arena, long npx, int Ct, int c0, int nch, int mode, int grid, void* sink, void* stream);

@@ -311,31 +311,6 @@ struct alignas(64) DenseFwdTmaArgs {
 
 __device__ __forceinline__ void epilogue_sync() { asm volatile("bar.sync 2, 128;" ::: "memory"); }
 
-__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* tm, int c0, int c1, uint64_t* bar) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
-          smem_u32(smem_dst)),
-      "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
-      : "memory");
-}
-__device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* tm, int c0, int c1, int c2, uint64_t* bar) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
-          smem_u32(smem_dst)),
-      "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
-      : "memory");
-}
-// K-major operand in the canonical 128-byte-swizzle layout (rows of 64 bf16, 8-row atoms 1024 B apart)
-__device__ __forceinline__ uint64_t desc_sw128_kmajor(uint32_t saddr) {
-  uint64_t d = 0;
-  d |= (uint64_t)((saddr >> 4) & 0x3FFFu);
-  d |= (uint64_t)1 << 16;             // LBO: unused for swizzled K-major
-  d |= (uint64_t)(1024u >> 4) << 32;  // SBO
-  d |= (uint64_t)1 << 46;             // descriptor version
-  d |= (uint64_t)2 << 61;             // SWIZZLE_128B
-  return d;
-}
-
 __global__ void __launch_bounds__(kF2Threads, 1) dense_fwd_tma_kernel(const __grid_constant__ DenseFwdTmaArgs P) {
   const DenseFwdArgs& a = P.a;
   extern __shared__ uint8_t smem_raw[];

@@ -125,3 +125,69 @@ extern "C" int rl_selftest_stream(void* arena, long npx, int Ct, int c0, int nch
   RL_CUDA(cudaGetLastError());
   return RL_OK;
 }
+
+// ------------------------------------------------------------------------------------------------
+// Raw descriptor probe: the caller supplies the exact shared-memory images of A and B and the upper bits of both
+// matrix descriptors (everything except the start address), so a layout / descriptor hypothesis (swizzle modes,
+// LBO / SBO meaning, K-step advance) can be checked against a reference product without recompiling.
+// ------------------------------------------------------------------------------------------------
+namespace rl {
+__global__ void __launch_bounds__(128, 1)
+umma_raw_kernel(const uint8_t* a_img, int a_bytes, unsigned long long a_tmpl, int a_kstep, const uint8_t* b_img, int b_bytes,
+                unsigned long long b_tmpl, int b_kstep, uint32_t idesc, int nk, int N, float* D) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + (((size_t)a_bytes + 1023) & ~(size_t)1023);
+  __shared__ uint64_t bar_mma;
+  __shared__ uint32_t tmem_base_s;
+  const int warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) {
+    mbar_init(&bar_mma, 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) tmem_alloc(&tmem_base_s, 256);
+  for (int i = threadIdx.x; i < a_bytes / 16; i += blockDim.x)
+    reinterpret_cast<uint4*>(sA)[i] = reinterpret_cast<const uint4*>(a_img)[i];
+  for (int i = threadIdx.x; i < b_bytes / 16; i += blockDim.x)
+    reinterpret_cast<uint4*>(sB)[i] = reinterpret_cast<const uint4*>(b_img)[i];
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_s;
+  if (threadIdx.x == 0) {
+    for (int kk = 0; kk < nk; ++kk) {
+      const uint64_t ad = a_tmpl | (uint64_t)(((smem_u32(sA) + (uint32_t)(kk * a_kstep)) >> 4) & 0x3FFFu);
+      const uint64_t bd = b_tmpl | (uint64_t)(((smem_u32(sB) + (uint32_t)(kk * b_kstep)) >> 4) & 0x3FFFu);
+      umma_ss(tmem, ad, bd, idesc, kk > 0);
+    }
+    umma_commit(&bar_mma);
+  }
+  mbar_wait(&bar_mma, 0);
+  tc_fence_after();
+  for (int c0 = 0; c0 < N; c0 += 16) {
+    float v[16];
+    tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16) + c0, v);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) D[(size_t)threadIdx.x * N + c0 + i] = v[i];
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 256);
+}
+}  // namespace rl
+
+extern "C" int rl_selftest_umma_raw(const void* a_img, int a_bytes, unsigned long long a_desc_tmpl, int a_kstep_bytes,
+                                    const void* b_img, int b_bytes, unsigned long long b_desc_tmpl, int b_kstep_bytes,
+                                    unsigned idesc, int nk, int N, float* D, void* stream) {
+  using namespace rl;
+  if (a_bytes % 16 || b_bytes % 16 || N % 16 || N < 16 || N > 256) return rl_fail(RL_ERR_ARG, "selftest_raw: bad sizes");
+  const size_t smem = 1024 + (((size_t)a_bytes + 1023) & ~(size_t)1023) + (size_t)b_bytes;
+  if (smem > 200 * 1024) return rl_fail(RL_ERR_ARG, "selftest_raw: images too large");
+  RL_CUDA(cudaFuncSetAttribute(umma_raw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  umma_raw_kernel<<<1, 128, smem, (cudaStream_t)stream>>>((const uint8_t*)a_img, a_bytes, a_desc_tmpl, a_kstep_bytes,
+                                                          (const uint8_t*)b_img, b_bytes, b_desc_tmpl, b_kstep_bytes, idesc, nk, N, D);
+  RL_CUDA(cudaGetLastError());
+  return RL_OK;
+}

@@ -136,6 +136,45 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16(uint32_t N, uint32_t a_mn
          | ((N >> 3) << 17)      // N
          | ((M >> 4) << 24);     // M
 }
+// ----------------------------------------------------------------------------------------------
+// Tensor-map TMA (cp.async.bulk.tensor): tm points to a CUtensorMap in kernel-parameter (__grid_constant__) space.
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const void* tm, int c0, int c1, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* smem_dst, const void* tm, int c0, int c1, int c2, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+// Operands in the 128-byte-swizzle layout a [rows][64 bf16] tensor-map box lands in (8-row atoms of 1024 B):
+//   K-major  (rows = M/N index, the 64 elements of a row = K): SBO = 1024, K step of 16 elements = +32 B
+//   MN-major (rows = K index, the 64 elements of a row = M/N): SBO = 1024 between 8-row K groups, LBO = byte distance of
+//            the next 64-element M/N atom (the next box), K step of 16 rows = +2048 B      (tests/test_umma_selftest.py)
+__device__ __forceinline__ uint64_t desc_sw128_kmajor(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFFu);
+  d |= (uint64_t)1 << 16;             // LBO: unused for swizzled K-major
+  d |= (uint64_t)(1024u >> 4) << 32;  // SBO
+  d |= (uint64_t)1 << 46;             // descriptor version
+  d |= (uint64_t)2 << 61;             // SWIZZLE_128B
+  return d;
+}
+__device__ __forceinline__ uint64_t desc_sw128_mnmajor(uint32_t saddr, uint32_t atom_stride_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFFu);
+  d |= (uint64_t)((atom_stride_bytes >> 4) & 0x3FFFu) << 16;
+  d |= (uint64_t)(1024u >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
 // D[tmem] (+)= A[smem] · B[smem]; one thread issues on behalf of the CTA. K = 16 per instruction.
 __device__ __forceinline__ void umma_ss(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
                                         uint32_t accumulate) {

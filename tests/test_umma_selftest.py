@@ -82,3 +82,41 @@ def test_mixed_major():
     b = torch.randn(K, N, device="cuda", generator=g).bfloat16()
     D = _run(a, 0, 0, b, 1, 0, N, K)
     torch.testing.assert_close(D, a.float() @ b.float(), rtol=1e-4, atol=1e-3)
+
+
+@pytest.mark.gpu
+def test_sw128_mnmajor_a_operand_from_tensor_map_box_layout():
+    """MN-major A in the 128-byte-swizzle layout a [rows = K][64 elements = M] tensor-map box lands in: SBO = 1024 between
+    8-row K groups, LBO = distance of the next 64-element M atom (the next box), K step of 16 rows = +2048 B
+    (desc_sw128_mnmajor in csrc/rl_umma.cuh); B = the un-swizzled chunk layout read MN-major."""
+    import ctypes
+    import numpy as np
+    L = _lib.lib()
+    L.rl_selftest_umma_raw.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_ulonglong, ctypes.c_int, ctypes.c_void_p,
+                                       ctypes.c_int, ctypes.c_ulonglong, ctypes.c_int, ctypes.c_uint, ctypes.c_int, ctypes.c_int,
+                                       ctypes.c_void_p, ctypes.c_void_p]
+
+    def desc(lbo, sbo, layout):
+        return ((lbo >> 4) & 0x3FFF) << 16 | ((sbo >> 4) & 0x3FFF) << 32 | 1 << 46 | layout << 61
+
+    torch.manual_seed(0)
+    K, M, N = 64, 128, 16
+    A = torch.randn(K, M).bfloat16()
+    B = torch.randn(K, N).bfloat16()
+    ref = A.float().t() @ B.float()
+    a16 = A.view(torch.int16).numpy()
+    img = np.zeros((2, K, 64), dtype=np.int16)
+    for atom in range(2):
+        for p in range(K):
+            for j in range(8):
+                jj = j ^ (p & 7)
+                img[atom, p, jj * 8:jj * 8 + 8] = a16[p, atom * 64 + j * 8: atom * 64 + j * 8 + 8]
+    a_img = torch.from_numpy(img.reshape(-1).copy()).cuda()
+    b_img = B.view(torch.int16).reshape(K, 2, 8).permute(1, 0, 2).contiguous().cuda()
+    idesc = (1 << 4) | (1 << 7) | (1 << 10) | (1 << 15) | (1 << 16) | ((N >> 3) << 17) | ((128 >> 4) << 24)
+    D = torch.full((128, N), float("nan"), device="cuda")
+    rc = L.rl_selftest_umma_raw(a_img.data_ptr(), a_img.numel() * 2, desc(K * 128, 1024, 2), 2048, b_img.data_ptr(),
+                                b_img.numel() * 2, desc(128, 16 * K, 0), 256, idesc, K // 16, N, D.data_ptr(), _lib.cur_stream())
+    _lib.check(rc)
+    torch.cuda.synchronize()
+    torch.testing.assert_close(D.cpu(), ref, rtol=1e-4, atol=1e-3)
