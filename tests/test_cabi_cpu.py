@@ -100,3 +100,26 @@ def test_errors_are_reported_not_thrown(lib):
     lib.rl_forward.argtypes = [ctypes.c_void_p] * 4 + [ctypes.c_int, ctypes.c_void_p]
     assert lib.rl_forward(h, None, None, None, 0, None) == -4
     lib.rl_plan_destroy(h)
+
+
+def test_argument_errors_of_the_stateless_entry_points(lib):
+    """null pointers / impossible shapes are rejected with an error code and a message before any device work"""
+    lib.rl_last_error.restype = ctypes.c_char_p
+    vp = ctypes.c_void_p
+    lib.rl_preprocess.argtypes = [vp, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                  vp, vp, vp]
+    assert lib.rl_preprocess(None, None, 1, 4, 4, 4, 4, 0, None, None, None) == -1
+    assert b"rl_preprocess" in lib.rl_last_error()
+    assert lib.rl_preprocess(vp(16), None, 1, 4, 4, 4, 4, 0, vp(16), vp(16), None) == -1      # y_out without a label
+    assert lib.rl_preprocess(vp(16), None, 0, 4, 4, 4, 4, 0, vp(16), None, None) == -2        # empty batch
+    lib.rl_overlay.argtypes = [vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp, ctypes.c_int, vp, vp]
+    assert lib.rl_overlay(None, 1, 4, 4, 4, 4, None, 0, None, None) == -1
+    assert lib.rl_overlay(vp(16), 1, 4, 4, 0, 4, vp(16), 0, vp(16), None) == -2
+    assert lib.rl_set_option(b"no_such_option", 1) == -1
+    assert lib.rl_set_option(b"overlap", 1) == 0 and lib.rl_set_option(b"fwd_tma", 1) == 0
+    rc, h = _plan(lib, 1, 64, 64, 4)
+    lib.rl_forward.argtypes = [vp, vp, vp, vp, ctypes.c_int, vp]
+    assert lib.rl_forward(h, vp(16), vp(16), vp(16), 1, None) != 0                              # plan not bound
+    assert b"not bound" in lib.rl_last_error()
+    lib.rl_plan_destroy.argtypes = [vp]
+    lib.rl_plan_destroy(h)
