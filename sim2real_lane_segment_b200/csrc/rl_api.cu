@@ -480,7 +480,6 @@ extern "C" int rl_backward(rl_plan* h, const float* params, const float* x, floa
       z.mask = (const float*)(wsb(p) + L.mask_off);
       if (g_compact16 && L.x16_off) {
         z.x16c = (const __nv_bfloat16*)(wsb(p) + L.x16_off);
-        if (L.dx16_from_next) z.dx16c = (const __nv_bfloat16*)(wsb(p) + lin.dx16_off);
       }
       const int q = dense_count++ & 1;  // dz buffer of this layer
       z.planes = 1;
@@ -499,8 +498,8 @@ extern "C" int rl_backward(rl_plan* h, const float* params, const float* x, floa
       d.dz_npos = lin.dzp_npos;
       d.dz_guard = lin.dzp_guard;
       d.Kdz = 16;
+      d.npx = lin.px;
       d.wpk = wsb(p) + L.wpk_bwd;
-      if (g_compact16 && li > 0 && p->layers[li - 1].dx16_from_next) d.dx16_out = (__nv_bfloat16*)(wsb(p) + lin.dx16_off);
       d.act = act_of(p, L.lvl_in);
       d.dact = dact_of(p, L.lvl_in);
       d.Ct = lin.Ct;
@@ -562,6 +561,7 @@ extern "C" int rl_backward(rl_plan* h, const float* params, const float* x, floa
       DgradArgs d;
       memset(&d, 0, sizeof(d));
       d.dense = 0;
+      d.npx = lin.px;
       d.dz = tmp;
       d.Kdz = L.cout;
       d.wpk = wsb(p) + L.wpk_bwd;
@@ -627,6 +627,7 @@ extern "C" int rl_backward(rl_plan* h, const float* params, const float* x, floa
       a.out = dact_of(p, L.lvl_in);
       a.ldo = lin.Ct;
       a.o_off = L.in_off;
+      a.out_planar_npx = lin.px;
       int gx = (int)std::max(1L, std::min(a.ntiles, (long)2 * sm));
       if ((rc = launch_gemm_px(a, gx, 1, st))) return rc;
       WgradArgs w;

@@ -103,8 +103,10 @@ __device__ __forceinline__ float warp_reduce8(float* v, int lane) {
 struct DgradPre {
   uint4 x0, x1, d0, d1;
 };
-__device__ __forceinline__ void dgrad_prefetch(DgradPre& p, const __nv_bfloat16* xrow, const __nv_bfloat16* drow, int c0,
-                                               int nvalid, bool rmw, int variant = 3) {
+// drow: this pixel's slot in the first 16-channel group plane of the channel block; dgs: elements between group planes
+__device__ __forceinline__ void dgrad_prefetch(DgradPre& p, const __nv_bfloat16* xrow, const __nv_bfloat16* drow_, int c0,
+                                               int nvalid, bool rmw, int variant, long dgs) {
+  const __nv_bfloat16* drow = drow_ + (long)(c0 >> 4) * dgs - c0;  // so that drow + c0 addresses group c0/16
   if (xrow != nullptr && c0 < nvalid) {
     if (variant & 32) {
       p.x0 = p.x1 = make_uint4(0x3f803f80u, 0x3f803f80u, 0x3f803f80u, 0x3f803f80u);
@@ -164,8 +166,7 @@ __device__ __forceinline__ float warp_colsum8(float* sc, const float* gs, const 
 template <bool kSmemSums>
 __device__ __forceinline__ void dgrad_epilogue(uint32_t tmem_acc, int warp, int lane, const __nv_bfloat16* xrow,
                                                __nv_bfloat16* drow, int cbase, int nvalid, const DgradConsts* k,
-                                               const DgradArgs& a, float* S1, float* S2, DgradPre* pre, float* s_scr,
-                                               __nv_bfloat16* d16row = nullptr) {
+                                               const DgradArgs& a, float* S1, float* S2, DgradPre* pre, float* s_scr) {
   float* sc = kSmemSums ? s_scr + warp * kScrPerWarp : nullptr;
 #pragma unroll
   for (int gi = 0; gi < 8; ++gi) {
@@ -174,7 +175,7 @@ __device__ __forceinline__ void dgrad_epilogue(uint32_t tmem_acc, int warp, int 
       float g[16];
       tmem_ld16(tmem_acc + ((uint32_t)(warp * 32) << 16) + c0, g);
       const DgradPre cur = pre[gi & 1];
-      if (gi + 2 < 8) dgrad_prefetch(pre[gi & 1], xrow, drow, c0 + 32, nvalid, (cbase + c0 + 32) >= a.rmw_from, a.variant);
+      if (gi + 2 < 8) dgrad_prefetch(pre[gi & 1], xrow, drow, c0 + 32, nvalid, (cbase + c0 + 32) >= a.rmw_from, a.variant, 16 * a.npx);
       // two halves of 8 channels keep the fp32 temporaries small (register budget: 4 CTAs per SM)
       uint4 dpk[2];
       float rs[2];
@@ -213,15 +214,13 @@ __device__ __forceinline__ void dgrad_epilogue(uint32_t tmem_acc, int warp, int 
         }
       }
       if (xrow != nullptr && !(a.variant & 8)) {
+        __nv_bfloat16* dg = drow + (long)(c0 >> 4) * 16 * a.npx;
         if (a.variant & 2) {
-          st256(drow + c0, dpk[0], dpk[1]);
+          st256(dg, dpk[0], dpk[1]);
         } else {
-          *reinterpret_cast<uint4*>(drow + c0) = dpk[0];
-          *reinterpret_cast<uint4*>(drow + c0 + 8) = dpk[1];
+          *reinterpret_cast<uint4*>(dg) = dpk[0];
+          *reinterpret_cast<uint4*>(dg + 8) = dpk[1];
         }
-        // the last 16 input channels are the previous DenseLayer's output and this is their final gradient: leave a
-        // dense copy for that layer's dz_prepare
-        if (d16row != nullptr && cbase + c0 == a.Cin - 16) st256(d16row, dpk[0], dpk[1]);
       }
       // lane (up, q, col) keeps quantity q (0: Σg, 1: Σg(x-mean)) of channel 8*up + col of this group
       S1[gi] += (lane & 16) ? rs[1] : rs[0];
@@ -370,11 +369,10 @@ __global__ void __launch_bounds__(128, 3) dgrad_dense_kernel(DgradArgs a) {
         }
       }
       const __nv_bfloat16* xrow = P >= 0 ? a.act + (size_t)P * a.Ct + mb * 128 : nullptr;
-      __nv_bfloat16* drow = P >= 0 ? a.dact + (size_t)P * a.Ct + mb * 128 : nullptr;
-      __nv_bfloat16* d16row = (P >= 0 && a.dx16_out != nullptr) ? a.dx16_out + (size_t)P * 16 : nullptr;
+      __nv_bfloat16* drow = P >= 0 ? a.dact + dact_index(a.npx, P, mb * 128) : nullptr;
       DgradPre pre[2];
-      dgrad_prefetch(pre[0], xrow, drow, 0, nvalid, (mb * 128) >= a.rmw_from, a.variant);
-      dgrad_prefetch(pre[1], xrow, drow, 16, nvalid, (mb * 128 + 16) >= a.rmw_from, a.variant);
+      dgrad_prefetch(pre[0], xrow, drow, 0, nvalid, (mb * 128) >= a.rmw_from, a.variant, 16 * a.npx);
+      dgrad_prefetch(pre[1], xrow, drow, 16, nvalid, (mb * 128 + 16) >= a.rmw_from, a.variant, 16 * a.npx);
       load_dz(tile);           // previous tile's MMAs were waited for before its epilogue: the buffer is free
       fence_proxy_async();
       __syncthreads();         // also: every thread is past the epilogue of tile-1 -> TMEM reusable
@@ -393,7 +391,7 @@ __global__ void __launch_bounds__(128, 3) dgrad_dense_kernel(DgradArgs a) {
       mbar_wait(&bar_mma, n_mma & 1);
       ++n_mma;
       tc_fence_after();
-      dgrad_epilogue<false>(tmem, warp, lane, xrow, drow, mb * 128, nvalid, kc, a, S1, S2, pre, nullptr, d16row);
+      dgrad_epilogue<false>(tmem, warp, lane, xrow, drow, mb * 128, nvalid, kc, a, S1, S2, pre, nullptr);
       tc_fence_before();
     }
     if (ntiles == 0 && tid == 0) mbar_wait(&bar_w, n_w & 1);
@@ -458,10 +456,10 @@ __global__ void __launch_bounds__(128, 3) dgrad_td_kernel(DgradArgs a) {
       const long Pl = tile * 128 + tid;
       const int P = Pl < npx ? (int)Pl : -1;
       const __nv_bfloat16* xrow = P >= 0 ? a.act + (size_t)P * a.Ct + mb * 128 : nullptr;
-      __nv_bfloat16* drow = P >= 0 ? a.dact + (size_t)P * a.Ct + mb * 128 : nullptr;
+      __nv_bfloat16* drow = P >= 0 ? a.dact + dact_index(a.npx, P, mb * 128) : nullptr;
       DgradPre pre[2];
-      dgrad_prefetch(pre[0], xrow, drow, 0, nvalid, (mb * 128) >= a.rmw_from, a.variant);
-      dgrad_prefetch(pre[1], xrow, drow, 16, nvalid, (mb * 128 + 16) >= a.rmw_from, a.variant);
+      dgrad_prefetch(pre[0], xrow, drow, 0, nvalid, (mb * 128) >= a.rmw_from, a.variant, 16 * a.npx);
+      dgrad_prefetch(pre[1], xrow, drow, 16, nvalid, (mb * 128 + 16) >= a.rmw_from, a.variant, 16 * a.npx);
       ld.load(rowptr, min(8, a.Kdz / 8));
       for (int kc = 0; kc < nkc; ++kc) {
         const int ck = min(64, a.Kdz - kc * 64);

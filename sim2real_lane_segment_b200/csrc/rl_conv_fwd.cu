@@ -894,7 +894,8 @@ __global__ void __launch_bounds__(128, 2) gemm_px_kernel(GemmPxArgs a) {
           uint32_t pk[8];
 #pragma unroll
           for (int i = 0; i < 8; ++i) pk[i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
-          uint4* dst = reinterpret_cast<uint4*>(a.out + (size_t)P * a.ldo + a.o_off + n0 + c0);
+          uint4* dst = reinterpret_cast<uint4*>(a.out_planar_npx > 0 ? a.out + dact_index(a.out_planar_npx, P, a.o_off + n0 + c0)
+                                                                      : a.out + (size_t)P * a.ldo + a.o_off + n0 + c0);
           dst[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
           dst[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
         }

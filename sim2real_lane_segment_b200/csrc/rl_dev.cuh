@@ -44,6 +44,14 @@ __device__ __forceinline__ BnCoef bn_coef(const BnSrc& b, int c) {
   return k;
 }
 
+// Gradient arenas are planar by 16-channel group: [Ct/16][pixels][16] bf16.  A pixel's 16 channels of a group are 32
+// contiguous bytes and consecutive pixels are contiguous, so the lane = pixel accesses of the input-gradient epilogues
+// touch 8 lines per warp instead of 32 and every channel window is a contiguous stream.  Element index of channel c
+// (a multiple of 8) of pixel P in an arena of npx pixels:
+__host__ __device__ __forceinline__ size_t dact_index(long npx, long P, int c) {
+  return ((size_t)(c >> 4) * (size_t)npx + (size_t)P) * 16 + (size_t)(c & 8);
+}
+
 __device__ __forceinline__ uint4 ldg128(const void* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
 
 // relu(x*s+t) on 8 packed bf16 with per-channel s,t taken from shared memory

@@ -45,6 +45,7 @@ struct GemmPxArgs {
   const float* mask;
   __nv_bfloat16* out;
   int ldo, o_off;
+  long out_planar_npx;  // > 0: out is a planar gradient arena of that many pixels (LINEAR mode), ldo unused
   uint8_t* amax;
 };
 int launch_gemm_px(const GemmPxArgs& a, int grid_x, int nparts, cudaStream_t st);
@@ -58,7 +59,7 @@ struct DgradArgs {
   int Kdz;
   const uint8_t* wpk;        // dense: per M-block [18][128][8]; td: per M-block, per K chunk [8][128][8]
   const __nv_bfloat16* act;  // level arena
-  __nv_bfloat16* dact;       // gradient arena (same geometry)
+  __nv_bfloat16* dact;       // gradient arena, planar by 16-channel group (rl_dev.cuh: dact_index)
   int Ct, Cin, H, W, B;
   int rmw_from;
   BnSrc bn;
@@ -68,7 +69,7 @@ struct DgradArgs {
   int vrows_per_cta, nstrips, strip_w;  // dense work decomposition (virtual rows: H+1 per image)
   long ntiles;                           // td: 128-pixel tiles
   int variant;                           // tuning switches (env RL_VARIANT): bit0 L2::128B hint, bit1 256-bit accesses
-  __nv_bfloat16* dx16_out;               // dense: compact [px][16] copy of the final dX of channels [Cin-16, Cin) (or null)
+  long npx;                              // pixels of the level (group stride of the planar gradient arena = 16 * npx)
 };
 int launch_dgrad(const DgradArgs& a, int grid, cudaStream_t st);
 
@@ -145,8 +146,7 @@ struct DzArgs {
   long dz_npos, dz_guard;
   float* g_bias;              // Σ dz per channel -> conv bias gradient (fp32 atomics)
   // TD: output arena is the pooled level; dz is written at the input resolution [px_in][nch]
-  const __nv_bfloat16* x16c;  // kind 0, nch 16: compact [px][16] copies of act / dact slices (or null: read the arenas)
-  const __nv_bfloat16* dx16c;
+  const __nv_bfloat16* x16c;  // kind 0, nch 16: compact [px][16] copy of the act slice (or null: read the arena)
   const uint8_t* amax;
   int H, W, Hp, Wp, B;        // TD: input H,W and pooled Hp,Wp.  TU: input (low-res) h=Hp,w=Wp and output H,W
 };

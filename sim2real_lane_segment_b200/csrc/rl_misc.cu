@@ -467,7 +467,7 @@ __global__ void __launch_bounds__(256, 2) head_kernel(HeadArgs a) {
             o[2 * h] = g0 * a.feat_grad_sign;
             o[2 * h + 1] = g1 * a.feat_grad_sign;
           }
-          *reinterpret_cast<uint4*>(a.dact + P * a.Ct + j * 8) = pack8(o);
+          *reinterpret_cast<uint4*>(a.dact + dact_index(a.npx, P, j * 8)) = pack8(o);
         }
       }
     }
@@ -546,7 +546,7 @@ __global__ void __launch_bounds__(256) dz_prepare_kernel(DzArgs a) {
   // j is always this thread's own chunk (jown)
   auto corrected = [&](long Pout, int j, int img, float* o) {
     float dx[8], xv[8];
-    unpack8(ldg128(a.dact + Pout * a.Ct + a.c_off + j * 8), dx);
+    unpack8(ldg128(a.dact + dact_index(a.npx_out, Pout, a.c_off + j * 8)), dx);
     unpack8(ldg128(a.act + Pout * a.Ct + a.c_off + j * 8), xv);
     if (a.mask != nullptr && img != mk_img) {
       const float4* mp = reinterpret_cast<const float4*>(a.mask + (long)img * a.nch + j * 8);
@@ -685,7 +685,7 @@ __global__ void __launch_bounds__(256) dz_dense16_kernel(DzArgs a) {
   for (long P = blockIdx.x * (long)blockDim.x + threadIdx.x; P < a.npx_out; P += (long)gridDim.x * blockDim.x) {
     const int img = (int)(P / a.HW_out);
     const int hw = (int)(P - (long)img * a.HW_out), y = hw / a.W, x = hw - y * a.W;
-    const u32x8 dv = a.dx16c ? ld256_nohint(a.dx16c + P * 16) : ld256_nohint(a.dact + P * a.Ct + a.c_off);
+    const u32x8 dv = ld256_nohint(a.dact + dact_index(a.npx_out, P, a.c_off));
     const u32x8 xv = a.x16c ? ldg256_nc_nohint(a.x16c + P * 16) : ldg256_nc_nohint(a.act + P * a.Ct + a.c_off);
     float dx[16], xx[16], mk[16], o[16];
     unpack8(dv.lo, dx);
@@ -758,7 +758,7 @@ __global__ void __launch_bounds__(256) dz_td_kernel(DzArgs a) {
         mk_img = b;
       }
       float dx[8], xv[8], c8[8];
-      unpack8(ldg128(a.dact + Pp * a.Ct + a.c_off + j * 8), dx);
+      unpack8(ldg128(a.dact + dact_index(a.npx_out, Pp, a.c_off + j * 8)), dx);
       unpack8(ldg128(a.act + Pp * a.Ct + a.c_off + j * 8), xv);
       const uint2 am = *reinterpret_cast<const uint2*>(a.amax + Pp * a.nch + j * 8);
 #pragma unroll
@@ -833,7 +833,7 @@ __global__ void __launch_bounds__(250) dz_tu_kernel(DzArgs a) {
   for (long P = (long)blockIdx.x * 25 + pl; P < nout; P += (long)gridDim.x * 25) {
     const int X = (int)(P % a.W), Y = (int)((P / a.W) % a.H), b = (int)(P / ((long)a.W * a.H));
     float dx[8], xv[8], o[8];
-    unpack8(ldg128(a.dact + P * a.Ct + a.c_off + j * 8), dx);
+    unpack8(ldg128(a.dact + dact_index(a.npx_out, P, a.c_off + j * 8)), dx);
     unpack8(ldg128(a.act + P * a.Ct + a.c_off + j * 8), xv);
 #pragma unroll
     for (int c = 0; c < 8; ++c) {

@@ -200,22 +200,15 @@ int build_plan(Plan* p, int B, int H, int W, int num_cls, int training) {
     L.dzp_off = training ? carve((size_t)L.dzp_npos * 32 * 2) : 0;
   }
   p->dzp_bytes = ws - p->dzp_off_all;
-  // compact side copies for dz_prepare of the DenseLayers: a 16-channel slice of a concat arena is 32 bytes out of every
-  // 2*Ct-byte row (1.0 TB/s on B200, profiles/r01_stream_probe.txt); the producers also leave those 32 bytes in a dense
-  // [px][16] buffer -- the forward kernel its output x16 (one buffer per layer, it lives until the backward pass), the
-  // next layer's input-gradient kernel the final dX16 (one buffer per level, consumed immediately)
+  // compact side copy for dz_prepare of the DenseLayers: a 16-channel slice of a concat arena is 32 bytes out of every
+  // 2*Ct-byte row (1.0 TB/s on B200, profiles/r01_stream_probe.txt); the forward kernel also leaves its output x16 in a
+  // dense [px][16] buffer (one per layer, it lives until the backward pass).  The gradient arenas are planar already.
   for (size_t i = 0; i < p->layers.size(); ++i) {
     Layer& L = p->layers[i];
     L.x16_off = 0;
-    L.dx16_from_next = 0;
     if (L.type != L_DENSE || !training) continue;
     L.x16_off = carve((size_t)p->lv[L.lvl_in].px * 32);
-    if (i + 1 < p->layers.size()) {
-      const Layer& N = p->layers[i + 1];
-      L.dx16_from_next = (N.type == L_DENSE && N.lvl_in == L.lvl_in && N.cin == L.cin + 16) ? 1 : 0;
-    }
   }
-  for (int l = 0; l < kLevels; ++l) p->lv[l].dx16_off = training ? carve((size_t)p->lv[l].px * 32) : 0;
   p->dl_bytes = training ? (size_t)p->lv[0].px * 16 * 2 : 0;
   p->dl_off = carve(p->dl_bytes);
   p->ws_bytes = ws;

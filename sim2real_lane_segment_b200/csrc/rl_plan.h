@@ -34,12 +34,11 @@ constexpr int kTaps = 9;
 struct Level {
   int H, W, Ct;
   int Cskip;  // channels of the down-path block output at this level (level 5: input channels 448)
-  size_t act_off, dact_off;      // bytes into workspace
+  size_t act_off, dact_off;      // bytes into workspace (act: NHWC [px][Ct]; dact: planar [Ct/16][px][16], rl_dev.cuh)
   size_t stats_off, acc_off;     // bytes into workspace: double[2][Ct] each
   long px;                       // B*H*W
   // zero-padded planes of the 16-channel output gradient of a DenseLayer (training):
   // two planes [npos][8] bf16; position(b,y,x) = guard + (b*(H+1)+y)*(W+2) + x+1; pads are never written
-  size_t dx16_off;               // training: compact [px][16] bf16 final output gradient of the DenseLayer handled next
   size_t dzp_off;                // two buffers of 2 planes each (alternate DenseLayers of the level use alternate buffers,
   long dzp_npos, dzp_guard;      // so a layer's weight gradient can still read its dz while the next layer's is written)
 };
@@ -56,8 +55,6 @@ struct Layer {
   size_t mask_off;                 // byte offset into workspace: float[B][cout] dropout scale (0 or 1/(1-p))
   size_t amax_off;                 // TD only: byte offset of uint8 argmax [pooled px][C]
   size_t x16_off;                  // DenseLayer, training: compact copy [px][16] bf16 of the layer's output (0: none)
-  int dx16_from_next;              // the next layer (same block) is a DenseLayer reading this one's output as its last 16
-                                   // input channels: its dgrad leaves the final dX of them in the level's dx16 buffer
   int rmw_from;                    // backward: input-gradient channels below this are overwritten, not accumulated
   int bn_index;                    // 0..59 or -1
 };

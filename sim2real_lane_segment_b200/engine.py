@@ -94,11 +94,15 @@ class Engine:
         return out.value
 
     def level_view(self, level, grad=False):
-        """[B, H_l, W_l, Ct_l] bf16 view of a concat arena (physical channel order: skip | up | new)."""
+        """[B, H_l, W_l, Ct_l] bf16 view of a concat arena (physical channel order: skip | up | new); grad=True: a copy of
+        the level's gradient arena in the same NHWC form."""
         off = self.query(Q_DACT_OFF if grad else Q_ACT_OFF, level)
         Ct, H, W = self.query(Q_CT, level), self.query(Q_H, level), self.query(Q_W, level)
         n = self.B * H * W * Ct
-        return self._ws_view[off:off + 2 * n].view(torch.bfloat16).view(self.B, H, W, Ct)
+        flat = self._ws_view[off:off + 2 * n].view(torch.bfloat16)
+        if grad:   # gradient arenas are planar by 16-channel group, [Ct/16][px][16]: return an NHWC copy
+            return flat.view(Ct // 16, self.B, H, W, 16).permute(1, 2, 3, 0, 4).reshape(self.B, H, W, Ct)
+        return flat.view(self.B, H, W, Ct)
 
     def level_stats(self, level):
         off, Ct = self.query(Q_STATS_OFF, level), self.query(Q_CT, level)
