@@ -22,6 +22,14 @@ int td_parts(int C, int* n0, int* np);
 static inline uint8_t* wsb(const Plan* p) { return (uint8_t*)p->ws; }
 static inline __nv_bfloat16* act_of(const Plan* p, int l) { return (__nv_bfloat16*)(wsb(p) + p->lv[l].act_off); }
 static inline __nv_bfloat16* dact_of(const Plan* p, int l) { return (__nv_bfloat16*)(wsb(p) + p->lv[l].dact_off); }
+// planar mirror of a level's activations (training plans only; RL_XP=0 keeps every reader on the NHWC arena)
+static const bool g_xp = []() {
+  const char* e = getenv("RL_XP");
+  return !(e && e[0] == '0');
+}();
+static inline __nv_bfloat16* xp_of(const Plan* p, int l) {
+  return (p->training && g_xp) ? (__nv_bfloat16*)(wsb(p) + p->lv[l].xp_off) : nullptr;
+}
 static inline double* stats_of(const Plan* p, int l) { return (double*)(wsb(p) + p->lv[l].stats_off); }
 static inline double* acc_of(const Plan* p, int l) { return (double*)(wsb(p) + p->lv[l].acc_off); }
 static inline Scalars* scal_of(const Plan* p) { return (Scalars*)(wsb(p) + p->scal_off); }
@@ -192,12 +200,6 @@ static bool g_fwd_tma = []() {
   return !(e && e[0] == '0');
 }();
 
-// compact [px][16] side copies of DenseLayer outputs / output gradients for dz_prepare (RL_COMPACT16=0 disables)
-static const bool g_compact16 = []() {
-  const char* e = getenv("RL_COMPACT16");
-  return !(e && e[0] == '0');
-}();
-
 static const int g_fwd_dbg = []() {
   const char* e = getenv("RL_FWD_DBG");
   return e ? atoi(e) : 0;
@@ -215,7 +217,7 @@ int rl_forward(rl_plan* h, const float* params, const float* bnbuf, const float*
     const Level& li = p->lv[L.lvl_in];
     const Level& lo = p->lv[L.lvl_out];
     if (L.type == L_FIRST) {
-      if ((rc = launch_first_fwd(p, x, params, st))) return rc;
+      if ((rc = launch_first_fwd(p, x, params, train && g_xp, st))) return rc;
       if (train && (rc = launch_channel_stats(act_of(p, 0), lo.px, lo.Ct, 0, kFirst, stats_of(p, 0), sm, st))) return rc;
     } else if (L.type == L_DENSE) {
       DenseFwdArgs a;
@@ -243,7 +245,7 @@ int rl_forward(rl_plan* h, const float* params, const float* bnbuf, const float*
       a.bn = make_bn(p, L, params, bnbuf, train);
       a.stats_out = train ? stats_of(p, L.lvl_in) : nullptr;
       a.dbg = g_fwd_dbg;
-      a.x16 = (train && p->training && g_compact16 && L.x16_off) ? (__nv_bfloat16*)(wsb(p) + L.x16_off) : nullptr;
+      a.x16 = (train && xp_of(p, L.lvl_in)) ? xp_of(p, L.lvl_in) + (size_t)(L.cin / 16) * li.px * 16 : nullptr;
       if (use_tma) {
         if ((rc = launch_dense_fwd_tma(a, p->tmap_act[L.lvl_in], nruns * a.nstrips, st))) return rc;
       } else if ((rc = launch_dense_fwd(a, nruns * a.nstrips, st))) return rc;
@@ -272,6 +274,8 @@ int rl_forward(rl_plan* h, const float* params, const float* bnbuf, const float*
       a.ldo = lo.Ct;
       a.o_off = 0;
       a.amax = (train && p->training) ? wsb(p) + L.amax_off : nullptr;
+      a.out_xp = train ? xp_of(p, L.lvl_out) : nullptr;
+      a.out_xp_npx = lo.px;
       int gx = (int)std::max(1L, std::min(a.ntiles, (long)(2 * sm) / nparts));
       if ((rc = launch_gemm_px(a, gx, nparts, st))) return rc;
       if (train && (rc = launch_channel_stats(act_of(p, L.lvl_out), lo.px, lo.Ct, 0, L.cout, stats_of(p, L.lvl_out), sm, st)))
@@ -298,7 +302,8 @@ int rl_forward(rl_plan* h, const float* params, const float* bnbuf, const float*
       a.o_off = 0;
       int gx = (int)std::max(1L, std::min(a.ntiles, (long)(2 * sm) / 3));
       if ((rc = launch_gemm_px(a, gx, 3, st))) return rc;
-      if ((rc = launch_tu_col2im((const __nv_bfloat16*)(wsb(p) + p->tmp_off), act_of(p, L.lvl_out), params + L.p_b, p->B, li.H,
+      if ((rc = launch_tu_col2im((const __nv_bfloat16*)(wsb(p) + p->tmp_off), act_of(p, L.lvl_out),
+                                 train ? xp_of(p, L.lvl_out) : nullptr, params + L.p_b, p->B, li.H,
                                  li.W, lo.H, lo.W, lo.Ct, L.out_off, st)))
         return rc;
       if (train && (rc = launch_channel_stats(act_of(p, L.lvl_out), lo.px, lo.Ct, L.out_off, kUpCh, stats_of(p, L.lvl_out), sm, st)))
@@ -475,12 +480,12 @@ extern "C" int rl_backward(rl_plan* h, const float* params, const float* x, floa
     z.dz = tmp;
     z.g_bias = grads + L.p_b;
     z.B = p->B;
+    // only the one-thread-per-pixel DenseLayer kernel reads x from the planar mirror; the chunk-per-thread TD / TU / first
+    // conv kernels are coalesced on the NHWC arena
+    z.xp = L.type == L_DENSE ? xp_of(p, L.lvl_out) : nullptr;
     if (L.type == L_DENSE) {
       z.kind = 0;
       z.mask = (const float*)(wsb(p) + L.mask_off);
-      if (g_compact16 && L.x16_off) {
-        z.x16c = (const __nv_bfloat16*)(wsb(p) + L.x16_off);
-      }
       const int q = dense_count++ & 1;  // dz buffer of this layer
       z.planes = 1;
       z.dz = (__nv_bfloat16*)(wsb(p) + lin.dzp_off + (size_t)q * lin.dzp_npos * 32);
@@ -499,6 +504,7 @@ extern "C" int rl_backward(rl_plan* h, const float* params, const float* x, floa
       d.dz_guard = lin.dzp_guard;
       d.Kdz = 16;
       d.npx = lin.px;
+      d.xp = xp_of(p, L.lvl_in);
       d.wpk = wsb(p) + L.wpk_bwd;
       d.act = act_of(p, L.lvl_in);
       d.dact = dact_of(p, L.lvl_in);
@@ -562,6 +568,7 @@ extern "C" int rl_backward(rl_plan* h, const float* params, const float* x, floa
       memset(&d, 0, sizeof(d));
       d.dense = 0;
       d.npx = lin.px;
+      d.xp = xp_of(p, L.lvl_in);
       d.dz = tmp;
       d.Kdz = L.cout;
       d.wpk = wsb(p) + L.wpk_bwd;

@@ -105,8 +105,9 @@ struct DgradPre {
 };
 // drow: this pixel's slot in the first 16-channel group plane of the channel block; dgs: elements between group planes
 __device__ __forceinline__ void dgrad_prefetch(DgradPre& p, const __nv_bfloat16* xrow, const __nv_bfloat16* drow_, int c0,
-                                               int nvalid, bool rmw, int variant, long dgs) {
+                                               int nvalid, bool rmw, int variant, long dgs, long xgs = 0) {
   const __nv_bfloat16* drow = drow_ + (long)(c0 >> 4) * dgs - c0;  // so that drow + c0 addresses group c0/16
+  if (xgs != 0 && xrow != nullptr) xrow += (long)(c0 >> 4) * xgs - c0;  // planar activation mirror: same addressing
   if (xrow != nullptr && c0 < nvalid) {
     if (variant & 32) {
       p.x0 = p.x1 = make_uint4(0x3f803f80u, 0x3f803f80u, 0x3f803f80u, 0x3f803f80u);
@@ -175,7 +176,7 @@ __device__ __forceinline__ void dgrad_epilogue(uint32_t tmem_acc, int warp, int 
       float g[16];
       tmem_ld16(tmem_acc + ((uint32_t)(warp * 32) << 16) + c0, g);
       const DgradPre cur = pre[gi & 1];
-      if (gi + 2 < 8) dgrad_prefetch(pre[gi & 1], xrow, drow, c0 + 32, nvalid, (cbase + c0 + 32) >= a.rmw_from, a.variant, 16 * a.npx);
+      if (gi + 2 < 8) dgrad_prefetch(pre[gi & 1], xrow, drow, c0 + 32, nvalid, (cbase + c0 + 32) >= a.rmw_from, a.variant, 16 * a.npx, a.xp ? 16 * a.npx : 0);
       // two halves of 8 channels keep the fp32 temporaries small (register budget: 4 CTAs per SM)
       uint4 dpk[2];
       float rs[2];
@@ -368,11 +369,11 @@ __global__ void __launch_bounds__(128, 3) dgrad_dense_kernel(DgradArgs a) {
           if (ri < a.H && xc >= x0 && xc < x1) P = (img * a.H + ri) * a.W + xc;
         }
       }
-      const __nv_bfloat16* xrow = P >= 0 ? a.act + (size_t)P * a.Ct + mb * 128 : nullptr;
+      const __nv_bfloat16* xrow = P < 0 ? nullptr : (a.xp ? a.xp + dact_index(a.npx, P, mb * 128) : a.act + (size_t)P * a.Ct + mb * 128);
       __nv_bfloat16* drow = P >= 0 ? a.dact + dact_index(a.npx, P, mb * 128) : nullptr;
       DgradPre pre[2];
-      dgrad_prefetch(pre[0], xrow, drow, 0, nvalid, (mb * 128) >= a.rmw_from, a.variant, 16 * a.npx);
-      dgrad_prefetch(pre[1], xrow, drow, 16, nvalid, (mb * 128 + 16) >= a.rmw_from, a.variant, 16 * a.npx);
+      dgrad_prefetch(pre[0], xrow, drow, 0, nvalid, (mb * 128) >= a.rmw_from, a.variant, 16 * a.npx, a.xp ? 16 * a.npx : 0);
+      dgrad_prefetch(pre[1], xrow, drow, 16, nvalid, (mb * 128 + 16) >= a.rmw_from, a.variant, 16 * a.npx, a.xp ? 16 * a.npx : 0);
       load_dz(tile);           // previous tile's MMAs were waited for before its epilogue: the buffer is free
       fence_proxy_async();
       __syncthreads();         // also: every thread is past the epilogue of tile-1 -> TMEM reusable
@@ -455,11 +456,11 @@ __global__ void __launch_bounds__(128, 3) dgrad_td_kernel(DgradArgs a) {
       }
       const long Pl = tile * 128 + tid;
       const int P = Pl < npx ? (int)Pl : -1;
-      const __nv_bfloat16* xrow = P >= 0 ? a.act + (size_t)P * a.Ct + mb * 128 : nullptr;
+      const __nv_bfloat16* xrow = P < 0 ? nullptr : (a.xp ? a.xp + dact_index(a.npx, P, mb * 128) : a.act + (size_t)P * a.Ct + mb * 128);
       __nv_bfloat16* drow = P >= 0 ? a.dact + dact_index(a.npx, P, mb * 128) : nullptr;
       DgradPre pre[2];
-      dgrad_prefetch(pre[0], xrow, drow, 0, nvalid, (mb * 128) >= a.rmw_from, a.variant, 16 * a.npx);
-      dgrad_prefetch(pre[1], xrow, drow, 16, nvalid, (mb * 128 + 16) >= a.rmw_from, a.variant, 16 * a.npx);
+      dgrad_prefetch(pre[0], xrow, drow, 0, nvalid, (mb * 128) >= a.rmw_from, a.variant, 16 * a.npx, a.xp ? 16 * a.npx : 0);
+      dgrad_prefetch(pre[1], xrow, drow, 16, nvalid, (mb * 128 + 16) >= a.rmw_from, a.variant, 16 * a.npx, a.xp ? 16 * a.npx : 0);
       ld.load(rowptr, min(8, a.Kdz / 8));
       for (int kc = 0; kc < nkc; ++kc) {
         const int ck = min(64, a.Kdz - kc * 64);

@@ -883,6 +883,11 @@ __global__ void __launch_bounds__(128, 2) gemm_px_kernel(GemmPxArgs a) {
           uint4* dst = reinterpret_cast<uint4*>(a.out + opx * a.ldo + a.o_off + n0 + c0);
           dst[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
           dst[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+          if (a.out_xp != nullptr) {
+            uint4* d2 = reinterpret_cast<uint4*>(a.out_xp + dact_index(a.out_xp_npx, (long)opx, a.o_off + n0 + c0));
+            d2[0] = dst[0];
+            d2[1] = dst[1];
+          }
           if (a.amax) *reinterpret_cast<uint4*>(a.amax + opx * a.N + n0 + c0) = make_uint4(am[0], am[1], am[2], am[3]);
         }
       }

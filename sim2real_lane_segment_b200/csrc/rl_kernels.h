@@ -20,7 +20,7 @@ struct DenseFwdArgs {
   BnSrc bn;
   double* stats_out;         // level stats base (Σx at [c], Σx² at [Ct+c]) or null
   int dbg;                   // triage switches (RL_FWD_DBG), 0 in production
-  __nv_bfloat16* x16;        // training: compact copy [px][16] of the output slice for dz_prepare (or null)
+  __nv_bfloat16* x16;        // training: the output's 16-channel group plane [px][16] of the planar mirror (or null)
 };
 int launch_dense_fwd(const DenseFwdArgs& a, int grid, cudaStream_t st);
 // TMA-fed variant (levels up to 160 wide: full rows; wider levels: strips of at most 126 columns): tmap = the level arena's 128-byte CUtensorMap blob
@@ -46,6 +46,8 @@ struct GemmPxArgs {
   __nv_bfloat16* out;
   int ldo, o_off;
   long out_planar_npx;  // > 0: out is a planar gradient arena of that many pixels (LINEAR mode), ldo unused
+  __nv_bfloat16* out_xp;  // POOL mode, training: planar mirror of the pooled level (written besides out) or null
+  long out_xp_npx;
   uint8_t* amax;
 };
 int launch_gemm_px(const GemmPxArgs& a, int grid_x, int nparts, cudaStream_t st);
@@ -70,6 +72,7 @@ struct DgradArgs {
   long ntiles;                           // td: 128-pixel tiles
   int variant;                           // tuning switches (env RL_VARIANT): bit0 L2::128B hint, bit1 256-bit accesses
   long npx;                              // pixels of the level (group stride of the planar gradient arena = 16 * npx)
+  const __nv_bfloat16* xp;               // planar mirror of the activation arena (same layout as dact) or null
 };
 int launch_dgrad(const DgradArgs& a, int grid, cudaStream_t st);
 
@@ -98,11 +101,11 @@ int launch_wgrad(const WgradArgs& a, int nruns, int nmb, int nparts, cudaStream_
 
 // ---------------------------------------------------------------- CUDA-core kernels (rl_misc.cu)
 int launch_pack_weights(const Plan* p, const float* params, cudaStream_t st);
-int launch_first_fwd(const Plan* p, const float* x, const float* params, cudaStream_t st);
+int launch_first_fwd(const Plan* p, const float* x, const float* params, int train, cudaStream_t st);
 int launch_channel_stats(const __nv_bfloat16* arena, long npx, int Ct, int c_off, int nch, double* stats, int sm,
                          cudaStream_t st);
-int launch_tu_col2im(const __nv_bfloat16* ycol, __nv_bfloat16* out, const float* bias, int B, int h, int w, int H,
-                     int W, int Ct, int o_off, cudaStream_t st);
+int launch_tu_col2im(const __nv_bfloat16* ycol, __nv_bfloat16* out, __nv_bfloat16* out_xp, const float* bias, int B, int h,
+                     int w, int H, int W, int Ct, int o_off, cudaStream_t st);
 int launch_label_hist(const void* y, int y_is_i64, long n, int num_cls, Scalars* sc, cudaStream_t st);
 
 struct HeadArgs {
@@ -146,7 +149,7 @@ struct DzArgs {
   long dz_npos, dz_guard;
   float* g_bias;              // Σ dz per channel -> conv bias gradient (fp32 atomics)
   // TD: output arena is the pooled level; dz is written at the input resolution [px_in][nch]
-  const __nv_bfloat16* x16c;  // kind 0, nch 16: compact [px][16] copy of the act slice (or null: read the arena)
+  const __nv_bfloat16* xp;    // planar mirror of act (training; same indexing as dact) or null: read the NHWC arena
   const uint8_t* amax;
   int H, W, Hp, Wp, B;        // TD: input H,W and pooled Hp,Wp.  TU: input (low-res) h=Hp,w=Wp and output H,W
 };

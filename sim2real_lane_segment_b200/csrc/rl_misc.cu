@@ -102,7 +102,7 @@ int launch_pack_weights(const Plan* p, const float* params, cudaStream_t st) {
 // ================================================================================================
 __global__ void __launch_bounds__(256) first_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                         const float* __restrict__ bias, __nv_bfloat16* act, int Ct, int B,
-                                                        int H, int W, __nv_bfloat16* xcol) {
+                                                        int H, int W, __nv_bfloat16* xcol, __nv_bfloat16* xp) {
   __shared__ float sw[48 * 27 + 48];
   for (int i = threadIdx.x; i < 48 * 27; i += blockDim.x) sw[i] = w[i];
   for (int i = threadIdx.x; i < 48; i += blockDim.x) sw[48 * 27 + i] = bias[i];
@@ -143,17 +143,19 @@ __global__ void __launch_bounds__(256) first_fwd_kernel(const float* __restrict_
         o[k] = acc;
       }
       dst[g] = pack8(o);
+      if (xp != nullptr) *reinterpret_cast<uint4*>(xp + dact_index(npx, P, g * 8)) = dst[g];
     }
   }
 }
 
-int launch_first_fwd(const Plan* p, const float* x, const float* params, cudaStream_t st) {
+int launch_first_fwd(const Plan* p, const float* x, const float* params, int train, cudaStream_t st) {
   const Layer& L = p->layers[0];
   __nv_bfloat16* act = (__nv_bfloat16*)((uint8_t*)p->ws + p->lv[0].act_off);
   __nv_bfloat16* xcol = p->training ? (__nv_bfloat16*)((uint8_t*)p->ws + p->xcol_off) : nullptr;
   { ProfScope _ps(KC_FIRST_FWD, st);
+  __nv_bfloat16* xp = (p->training && train) ? (__nv_bfloat16*)((uint8_t*)p->ws + p->lv[0].xp_off) : nullptr;
   first_fwd_kernel<<<p->sm_count * 4, 256, 0, st>>>(x, params + L.p_w, params + L.p_b, act, p->lv[0].Ct, p->B, p->H, p->W,
-                                                    xcol); }
+                                                    xcol, xp); }
   RL_CUDA(cudaGetLastError());
   return RL_OK;
 }
@@ -213,7 +215,7 @@ int launch_channel_stats(const __nv_bfloat16* arena, long npx, int Ct, int c_off
 // ycol[p_in][tap*80+co] holds in[p_in,:] · W[:,co,tap]   (reference layers.py:61-68, 82-86)
 // ================================================================================================
 __global__ void __launch_bounds__(256) tu_col2im_kernel(const __nv_bfloat16* __restrict__ ycol, __nv_bfloat16* out,
-                                                        const float* __restrict__ bias, int B, int h, int w, int H, int W,
+                                                        __nv_bfloat16* out_xp, const float* __restrict__ bias, int B, int h, int w, int H, int W,
                                                         int Ct, int o_off) {
   pdl_trigger();
   pdl_wait();
@@ -243,16 +245,18 @@ __global__ void __launch_bounds__(256) tu_col2im_kernel(const __nv_bfloat16* __r
         acc[7] += d.y;
       }
     }
-    *reinterpret_cast<uint4*>(out + P * Ct + o_off + j * 8) = pack8(acc);
+    const uint4 pk = pack8(acc);
+    *reinterpret_cast<uint4*>(out + P * Ct + o_off + j * 8) = pk;
+    if (out_xp != nullptr) *reinterpret_cast<uint4*>(out_xp + dact_index((long)B * H * W, P, o_off + j * 8)) = pk;
   }
 }
 
-int launch_tu_col2im(const __nv_bfloat16* ycol, __nv_bfloat16* out, const float* bias, int B, int h, int w, int H,
-                     int W, int Ct, int o_off, cudaStream_t st) {
+int launch_tu_col2im(const __nv_bfloat16* ycol, __nv_bfloat16* out, __nv_bfloat16* out_xp, const float* bias, int B, int h,
+                     int w, int H, int W, int Ct, int o_off, cudaStream_t st) {
   long total = (long)B * H * W * 10;
   int grid = (int)std::min<long>((total + 255) / 256, 148L * 16);
   { ProfScope _ps(KC_TU_COL2IM, st);
-  RL_CUDA(launch_pdl(tu_col2im_kernel, dim3(grid), dim3(256), 0, st, ycol, out, bias, B, h, w, H, W, Ct, o_off)); }
+  RL_CUDA(launch_pdl(tu_col2im_kernel, dim3(grid), dim3(256), 0, st, ycol, out, out_xp, bias, B, h, w, H, W, Ct, o_off)); }
   return RL_OK;
 }
 
@@ -547,7 +551,7 @@ __global__ void __launch_bounds__(256) dz_prepare_kernel(DzArgs a) {
   auto corrected = [&](long Pout, int j, int img, float* o) {
     float dx[8], xv[8];
     unpack8(ldg128(a.dact + dact_index(a.npx_out, Pout, a.c_off + j * 8)), dx);
-    unpack8(ldg128(a.act + Pout * a.Ct + a.c_off + j * 8), xv);
+    unpack8(ldg128(a.xp ? a.xp + dact_index(a.npx_out, Pout, a.c_off + j * 8) : a.act + Pout * a.Ct + a.c_off + j * 8), xv);
     if (a.mask != nullptr && img != mk_img) {
       const float4* mp = reinterpret_cast<const float4*>(a.mask + (long)img * a.nch + j * 8);
       const float4 m0 = __ldg(mp), m1 = __ldg(mp + 1);
@@ -686,7 +690,7 @@ __global__ void __launch_bounds__(256) dz_dense16_kernel(DzArgs a) {
     const int img = (int)(P / a.HW_out);
     const int hw = (int)(P - (long)img * a.HW_out), y = hw / a.W, x = hw - y * a.W;
     const u32x8 dv = ld256_nohint(a.dact + dact_index(a.npx_out, P, a.c_off));
-    const u32x8 xv = a.x16c ? ldg256_nc_nohint(a.x16c + P * 16) : ldg256_nc_nohint(a.act + P * a.Ct + a.c_off);
+    const u32x8 xv = ldg256_nc_nohint(a.xp ? a.xp + dact_index(a.npx_out, P, a.c_off) : a.act + P * a.Ct + a.c_off);
     float dx[16], xx[16], mk[16], o[16];
     unpack8(dv.lo, dx);
     unpack8(dv.hi, dx + 8);
@@ -759,7 +763,7 @@ __global__ void __launch_bounds__(256) dz_td_kernel(DzArgs a) {
       }
       float dx[8], xv[8], c8[8];
       unpack8(ldg128(a.dact + dact_index(a.npx_out, Pp, a.c_off + j * 8)), dx);
-      unpack8(ldg128(a.act + Pp * a.Ct + a.c_off + j * 8), xv);
+      unpack8(ldg128(a.xp ? a.xp + dact_index(a.npx_out, Pp, a.c_off + j * 8) : a.act + Pp * a.Ct + a.c_off + j * 8), xv);
       const uint2 am = *reinterpret_cast<const uint2*>(a.amax + Pp * a.nch + j * 8);
 #pragma unroll
       for (int c = 0; c < 8; ++c) {
@@ -834,7 +838,7 @@ __global__ void __launch_bounds__(250) dz_tu_kernel(DzArgs a) {
     const int X = (int)(P % a.W), Y = (int)((P / a.W) % a.H), b = (int)(P / ((long)a.W * a.H));
     float dx[8], xv[8], o[8];
     unpack8(ldg128(a.dact + dact_index(a.npx_out, P, a.c_off + j * 8)), dx);
-    unpack8(ldg128(a.act + P * a.Ct + a.c_off + j * 8), xv);
+    unpack8(ldg128(a.xp ? a.xp + dact_index(a.npx_out, P, a.c_off + j * 8) : a.act + P * a.Ct + a.c_off + j * 8), xv);
 #pragma unroll
     for (int c = 0; c < 8; ++c) {
       const float xh = (xv[c] - k[c].mean) * k[c].rstd;

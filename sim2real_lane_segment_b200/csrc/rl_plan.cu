@@ -200,15 +200,11 @@ int build_plan(Plan* p, int B, int H, int W, int num_cls, int training) {
     L.dzp_off = training ? carve((size_t)L.dzp_npos * 32 * 2) : 0;
   }
   p->dzp_bytes = ws - p->dzp_off_all;
-  // compact side copy for dz_prepare of the DenseLayers: a 16-channel slice of a concat arena is 32 bytes out of every
-  // 2*Ct-byte row (1.0 TB/s on B200, profiles/r01_stream_probe.txt); the forward kernel also leaves its output x16 in a
-  // dense [px][16] buffer (one per layer, it lives until the backward pass).  The gradient arenas are planar already.
-  for (size_t i = 0; i < p->layers.size(); ++i) {
-    Layer& L = p->layers[i];
-    L.x16_off = 0;
-    if (L.type != L_DENSE || !training) continue;
-    L.x16_off = carve((size_t)p->lv[L.lvl_in].px * 32);
-  }
+  // Planar mirror of the activation arenas (training): [Ct/16][px][16] like the gradient arenas.  Every producer writes
+  // its channels to both; the backward's lane = pixel readers (input-gradient epilogues, dz_prepare) use the mirror,
+  // where a pixel's 16-channel group is 32 contiguous bytes next to its neighbours' (a 16-channel slice of the NHWC
+  // arena streams at 1.0 TB/s, profiles/r01_stream_probe.txt, and costs 32 L1 lines per warp access).
+  for (int l = 0; l < kLevels; ++l) p->lv[l].xp_off = training ? carve((size_t)p->lv[l].px * p->lv[l].Ct * 2) : 0;
   p->dl_bytes = training ? (size_t)p->lv[0].px * 16 * 2 : 0;
   p->dl_off = carve(p->dl_bytes);
   p->ws_bytes = ws;

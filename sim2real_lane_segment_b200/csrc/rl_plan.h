@@ -35,6 +35,7 @@ struct Level {
   int H, W, Ct;
   int Cskip;  // channels of the down-path block output at this level (level 5: input channels 448)
   size_t act_off, dact_off;      // bytes into workspace (act: NHWC [px][Ct]; dact: planar [Ct/16][px][16], rl_dev.cuh)
+  size_t xp_off;                 // training: planar mirror of act (same layout as dact) for the backward's lane = pixel reads
   size_t stats_off, acc_off;     // bytes into workspace: double[2][Ct] each
   long px;                       // B*H*W
   // zero-padded planes of the 16-channel output gradient of a DenseLayer (training):
@@ -54,7 +55,6 @@ struct Layer {
   size_t wpk_fwd, wpk_bwd;         // byte offsets into workspace (packed bf16 weights)
   size_t mask_off;                 // byte offset into workspace: float[B][cout] dropout scale (0 or 1/(1-p))
   size_t amax_off;                 // TD only: byte offset of uint8 argmax [pooled px][C]
-  size_t x16_off;                  // DenseLayer, training: compact copy [px][16] bf16 of the layer's output (0: none)
   int rmw_from;                    // backward: input-gradient channels below this are overwritten, not accumulated
   int bn_index;                    // 0..59 or -1
 };
