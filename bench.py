@@ -326,7 +326,7 @@ def run_b200(args, rank, world, local_rank):
             try:
                 tj = json.load(open(ncu_traffic))
                 roof["traffic"] = tj.get(top)
-                roof["traffic_note"] = tj.get("note")
+                roof["traffic_note"] = tj.get(top + "_note", tj.get("note"))
             except Exception:
                 pass
 
