@@ -864,18 +864,29 @@ __global__ void __launch_bounds__(128, 2) gemm_px_kernel(GemmPxArgs a) {
         tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16) + c0, v);
         uint32_t pk[8];
         uint32_t am[4] = {0, 0, 0, 0};
+        // 2x2 max-pool over the four lanes of a quad, on the raw accumulators (+bias and the non-negative Dropout2d scale
+        // are the same for the four pixels of a window, so they commute with the max and are applied to the pooled value
+        // only).  The window position rides in the two lowest mantissa bits (3 - q, so that the first position wins a
+        // tie): one max butterfly yields value and arg-max together; the 2-bit perturbation is far below bf16 rounding.
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
-          const float y = (v[i] + s_bias[c0 + i]) * s_mask[c0 + i];
-          // the three other pixels of the 2x2 window sit in the other lanes of the quad: three independent exchanges.
-          // Only lane q == 0 stores, and for it (y, y1, y2, y3) are the window in torch's row-major scan order; the
-          // arg-max is the first position holding the maximum.
-          const float y1 = __shfl_xor_sync(0xffffffffu, y, 1), y2 = __shfl_xor_sync(0xffffffffu, y, 2),
-                      y3 = __shfl_xor_sync(0xffffffffu, y, 3);
-          const float m = fmaxf(fmaxf(y, y1), fmaxf(y2, y3));
-          const int bq = (y == m) ? 0 : (y1 == m) ? 1 : (y2 == m) ? 2 : 3;
-          v[i] = m;
-          am[i >> 2] |= (uint32_t)bq << (8 * (i & 3));
+          float t = __int_as_float((__float_as_int(v[i]) & ~3) | (3 - q));
+          t = fmaxf(t, __shfl_xor_sync(0xffffffffu, t, 1));
+          t = fmaxf(t, __shfl_xor_sync(0xffffffffu, t, 2));
+          am[i >> 2] |= (uint32_t)(3 - (__float_as_int(t) & 3)) << (8 * (i & 3));
+          v[i] = t;
+        }
+        {
+          const float4* bp = reinterpret_cast<const float4*>(s_bias + c0);
+          const float4* mp = reinterpret_cast<const float4*>(s_mask + c0);
+#pragma unroll
+          for (int i4 = 0; i4 < 4; ++i4) {
+            const float4 b4 = bp[i4], m4 = mp[i4];
+            v[4 * i4 + 0] = (v[4 * i4 + 0] + b4.x) * m4.x;
+            v[4 * i4 + 1] = (v[4 * i4 + 1] + b4.y) * m4.y;
+            v[4 * i4 + 2] = (v[4 * i4 + 2] + b4.z) * m4.z;
+            v[4 * i4 + 3] = (v[4 * i4 + 3] + b4.w) * m4.w;
+          }
         }
         if (valid && q == 0) {
 #pragma unroll
