@@ -675,22 +675,29 @@ __device__ __forceinline__ DzConst dz_const(const DzArgs& a, int c) {
 // DenseLayer output (16 channels): one thread per pixel, 32-byte accesses, zero-padded two-plane result
 __global__ void __launch_bounds__(256) dz_dense16_kernel(DzArgs a) {
   __shared__ float s_red[8][16];
-  __shared__ DzConst s_k[16];
+  __shared__ float2 s_k[16];  // dz = mask * (dX - A' - x * B'),  B' = rstd * B,  A' = A - mean * B'
   pdl_trigger();
   pdl_wait();
-  if (threadIdx.x < 16) s_k[threadIdx.x] = dz_const(a, threadIdx.x);
+  if (threadIdx.x < 16) {
+    const DzConst k = dz_const(a, threadIdx.x);
+    const float b2 = k.rstd * k.B;
+    s_k[threadIdx.x] = make_float2(k.A - k.mean * b2, b2);
+  }
   __syncthreads();
-  DzConst k[16];
+  float2 k[16];
 #pragma unroll
   for (int c = 0; c < 16; ++c) k[c] = s_k[c];
   float bsum[16];
 #pragma unroll
   for (int c = 0; c < 16; ++c) bsum[c] = 0.f;
-  for (long P = blockIdx.x * (long)blockDim.x + threadIdx.x; P < a.npx_out; P += (long)gridDim.x * blockDim.x) {
-    const int img = (int)(P / a.HW_out);
-    const int hw = (int)(P - (long)img * a.HW_out), y = hw / a.W, x = hw - y * a.W;
-    const u32x8 dv = ld256_nohint(a.dact + dact_index(a.npx_out, P, a.c_off));
-    const u32x8 xv = ldg256_nc_nohint(a.xp ? a.xp + dact_index(a.npx_out, P, a.c_off) : a.act + P * a.Ct + a.c_off);
+  const int npx = (int)a.npx_out;  // < 2^31: 32-bit index arithmetic
+  const __nv_bfloat16* dplane = a.dact + (size_t)(a.c_off >> 4) * (size_t)a.npx_out * 16;
+  const __nv_bfloat16* xplane = a.xp ? a.xp + (size_t)(a.c_off >> 4) * (size_t)a.npx_out * 16 : nullptr;
+  for (int P = blockIdx.x * blockDim.x + threadIdx.x; P < npx; P += gridDim.x * blockDim.x) {
+    const int img = P / a.HW_out;
+    const int hw = P - img * a.HW_out, y = hw / a.W, x = hw - y * a.W;
+    const u32x8 dv = ld256_nohint(dplane + (size_t)P * 16);
+    const u32x8 xv = ldg256_nc_nohint(xplane ? xplane + (size_t)P * 16 : a.act + (size_t)P * a.Ct + a.c_off);
     float dx[16], xx[16], mk[16], o[16];
     unpack8(dv.lo, dx);
     unpack8(dv.hi, dx + 8);
@@ -709,8 +716,7 @@ __global__ void __launch_bounds__(256) dz_dense16_kernel(DzArgs a) {
     }
 #pragma unroll
     for (int c = 0; c < 16; ++c) {
-      const float xh = (xx[c] - k[c].mean) * k[c].rstd;
-      o[c] = mk[c] * (dx[c] - k[c].A - xh * k[c].B);
+      o[c] = mk[c] * (dx[c] - fmaf(xx[c], k[c].y, k[c].x));
       bsum[c] += o[c];
     }
     const long pos = a.dz_guard + ((long)img * (a.H + 1) + y) * (a.W + 2) + x + 1;
