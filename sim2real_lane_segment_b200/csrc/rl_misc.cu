@@ -221,9 +221,9 @@ __global__ void __launch_bounds__(256) tu_col2im_kernel(const __nv_bfloat16* __r
   pdl_wait();
   const long total = (long)B * H * W * 10;
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
-    const int j = (int)(i % 10);
-    const long P = i / 10;
-    const int X = (int)(P % W), Y = (int)((P / W) % H), b = (int)(P / ((long)W * H));
+    const int i32 = (int)i, P32 = i32 / 10, j = i32 - P32 * 10;   // < 2^31 work items: 32-bit index arithmetic
+    const long P = P32;
+    const int b = P32 / (W * H), rem = P32 - b * (W * H), Y = rem / W, X = rem - Y * W;
     float acc[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) acc[k] = bias[j * 8 + k];
@@ -760,7 +760,7 @@ __global__ void __launch_bounds__(256) dz_td_kernel(DzArgs a) {
   const long npool = (long)a.B * a.Hp * a.Wp;
   if (pl < ppb)
     for (long Pp = (long)blockIdx.x * ppb + pl; Pp < npool; Pp += (long)gridDim.x * ppb) {
-      const int px = (int)(Pp % a.Wp), py = (int)((Pp / a.Wp) % a.Hp), b = (int)(Pp / ((long)a.Wp * a.Hp));
+      const int Pp32 = (int)Pp, b = Pp32 / (a.Wp * a.Hp), rem = Pp32 - b * (a.Wp * a.Hp), py = rem / a.Wp, px = rem - py * a.Wp;
       if (a.mask != nullptr && b != mk_img) {
         const float4* mp = reinterpret_cast<const float4*>(a.mask + (long)b * a.nch + j * 8);
         const float4 m0 = __ldg(mp), m1 = __ldg(mp + 1);
@@ -841,7 +841,7 @@ __global__ void __launch_bounds__(250) dz_tu_kernel(DzArgs a) {
   for (int c = 0; c < 8; ++c) bsum[c] = 0.f;
   const long nout = (long)a.B * a.H * a.W;
   for (long P = (long)blockIdx.x * 25 + pl; P < nout; P += (long)gridDim.x * 25) {
-    const int X = (int)(P % a.W), Y = (int)((P / a.W) % a.H), b = (int)(P / ((long)a.W * a.H));
+    const int P32 = (int)P, b = P32 / (a.W * a.H), rem = P32 - b * (a.W * a.H), Y = rem / a.W, X = rem - Y * a.W;
     float dx[8], xv[8], o[8];
     unpack8(ldg128(a.dact + dact_index(a.npx_out, P, a.c_off + j * 8)), dx);
     unpack8(ldg128(a.xp ? a.xp + dact_index(a.npx_out, P, a.c_off + j * 8) : a.act + P * a.Ct + a.c_off + j * 8), xv);

@@ -36,9 +36,10 @@ int build_plan(Plan* p, int B, int H, int W, int num_cls, int training) {
     p->ev_wg_used[i] = false;
   }
   p->err[0] = 0;
-  if (B < 1 || H < 32 || W < 32 || num_cls < 2 || num_cls > 4) {
-    snprintf(p->err, sizeof(p->err), "unsupported shape B=%d H=%d W=%d num_cls=%d (need H,W>=32, 2<=C<=4)", B, H, W,
-             num_cls);
+  // B*H*W*16 < 2^31: the elementwise kernels index pixels (and pixel x chunk work items) with 32-bit arithmetic
+  if (B < 1 || H < 32 || W < 32 || num_cls < 2 || num_cls > 4 || (long)B * H * W >= (1L << 27)) {
+    snprintf(p->err, sizeof(p->err), "unsupported shape B=%d H=%d W=%d num_cls=%d (need H,W>=32, 2<=C<=4, B*H*W < 2^27)", B, H,
+             W, num_cls);
     return -1;
   }
   // ---- levels
