@@ -110,7 +110,7 @@ __global__ void __launch_bounds__(256) first_fwd_kernel(const float* __restrict_
   const long npx = (long)B * H * W;
   const long HW = (long)H * W;
   for (long P = blockIdx.x * (long)blockDim.x + threadIdx.x; P < npx; P += (long)gridDim.x * blockDim.x) {
-    const int b = (int)(P / HW), hw = (int)(P % HW), y = hw / W, xx = hw % W;
+    const int P32 = (int)P, iHW = (int)HW, b = P32 / iHW, hw = P32 - b * iHW, y = hw / W, xx = hw - y * W;
     float in[27];
 #pragma unroll
     for (int ci = 0; ci < 3; ++ci)
@@ -386,7 +386,7 @@ __global__ void __launch_bounds__(256, 2) head_kernel(HeadArgs a) {
         pred = k;
       }
     }
-    const int b = valid ? (int)(P / a.HW) : 0, hw = valid ? (int)(P % a.HW) : 0;
+    const int b = valid ? (int)P / a.HW : 0, hw = valid ? (int)P - b * a.HW : 0;
     if (valid && q == 0) {
       if (a.probs)
 #pragma unroll
@@ -573,7 +573,7 @@ __global__ void __launch_bounds__(256) dz_prepare_kernel(DzArgs a) {
     if (pl < ppb)
       for (long P = (long)blockIdx.x * ppb + pl; P < a.npx_out; P += (long)gridDim.x * ppb) {
         float o[8];
-        const int img = (int)(P / a.HW_out);
+        const int img = (int)P / a.HW_out;
         corrected(P, j, img, o);
         if (a.planes) {
           const int hw = (int)(P - (long)img * a.HW_out), y = hw / a.W, x = hw - y * a.W;
