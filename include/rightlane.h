@@ -124,7 +124,9 @@ int rl_profile_launches(float* ms, int* kernel_class, int max); /* per-launch ti
 /* runtime switches: "overlap" (default 1) runs the DenseLayer weight-gradient kernels of rl_backward on a plan-owned
  * side stream concurrently with the input-gradient chain (joined before rl_backward returns control of the stream);
  * "fwd_tma" (default 1) runs the DenseLayer forward of levels up to 160 pixels wide through the tensor-map TMA kernel
- * (0: the register-staged kernel that wider levels always use; both produce identical bits). */
+ * (0: the register-staged kernel; same GEMMs, the fp32 shift-add order differs); "xp" (default 1): training forward
+ * passes also write the planar mirror of the activation arenas that the input-gradient kernels read (0: they read the
+ * NHWC arenas; set it before rl_forward). */
 int rl_set_option(const char* name, int value);
 
 /* test hook: one tcgen05 GEMM (M = 128) from caller-supplied shared-memory images of A and B and the upper bits of both

@@ -23,7 +23,7 @@ static inline uint8_t* wsb(const Plan* p) { return (uint8_t*)p->ws; }
 static inline __nv_bfloat16* act_of(const Plan* p, int l) { return (__nv_bfloat16*)(wsb(p) + p->lv[l].act_off); }
 static inline __nv_bfloat16* dact_of(const Plan* p, int l) { return (__nv_bfloat16*)(wsb(p) + p->lv[l].dact_off); }
 // planar mirror of a level's activations (training plans only; RL_XP=0 keeps every reader on the NHWC arena)
-static const bool g_xp = []() {
+static bool g_xp = []() {
   const char* e = getenv("RL_XP");
   return !(e && e[0] == '0');
 }();
@@ -692,6 +692,10 @@ extern "C" int rl_backward(rl_plan* h, const float* params, const float* x, floa
 extern "C" int rl_set_option(const char* name, int value) {
   if (name && strcmp(name, "overlap") == 0) {
     g_overlap = value ? 1 : 0;
+    return RL_OK;
+  }
+  if (name && strcmp(name, "xp") == 0) {  // takes effect with the next rl_forward (the mirror is written by the forward pass)
+    g_xp = value != 0;
     return RL_OK;
   }
   if (name && strcmp(name, "fwd_tma") == 0) {
