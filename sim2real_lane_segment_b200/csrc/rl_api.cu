@@ -438,6 +438,7 @@ extern "C" int rl_backward(rl_plan* h, const float* params, const float* x, floa
     memset(&w, 0, sizeof(w));
     w.kind = WG_HEAD;
     w.A = act_of(p, 0);
+    w.Axp = xp_of(p, 0);
     w.lda = p->lv[0].Ct;
     w.a_off = 0;
     w.Ca = 288;
@@ -532,6 +533,7 @@ extern "C" int rl_backward(rl_plan* h, const float* params, const float* x, floa
       memset(&w, 0, sizeof(w));
       w.kind = WG_DENSE;
       w.A = act_of(p, L.lvl_in);
+      w.Axp = xp_of(p, L.lvl_in);
       w.lda = lin.Ct;
       w.Ca = L.cin;
       w.transform = 1;
@@ -591,6 +593,7 @@ extern "C" int rl_backward(rl_plan* h, const float* params, const float* x, floa
       memset(&w, 0, sizeof(w));
       w.kind = WG_TD;
       w.A = act_of(p, L.lvl_in);
+      w.Axp = xp_of(p, L.lvl_in);
       w.lda = lin.Ct;
       w.Ca = L.cin;
       w.transform = 1;
@@ -641,6 +644,7 @@ extern "C" int rl_backward(rl_plan* h, const float* params, const float* x, floa
       memset(&w, 0, sizeof(w));
       w.kind = WG_TU;
       w.A = act_of(p, L.lvl_in);
+      w.Axp = xp_of(p, L.lvl_in);
       w.lda = lin.Ct;
       w.a_off = L.in_off;
       w.Ca = kUpCh;

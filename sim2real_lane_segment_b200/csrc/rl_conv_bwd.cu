@@ -612,11 +612,13 @@ __global__ void __launch_bounds__(kWgThreads, 2) wgrad_kernel(WgradArgs a) {
   auto load_a = [&](int kc, ARegs& r) {
     const long P = P0 + (long)kc * 64 + a_row;
     r.valid = kc < nchunks && P < P1;
-    const __nv_bfloat16* src = a.A + (size_t)(r.valid ? P : P0) * a.lda + a.a_off + mb * 128;
+    const long Pv = r.valid ? P : P0;
+    const __nv_bfloat16* src = a.A + (size_t)Pv * a.lda + a.a_off + mb * 128;
 #pragma unroll
     for (int h = 0; h < 4; ++h) {
       const int j = a_j0 + 4 * h;
-      r.v[h] = (r.valid && j < a_nchunk) ? ldg128(src + j * 8) : make_uint4(0, 0, 0, 0);
+      const __nv_bfloat16* pj = a.Axp ? a.Axp + dact_index(a.npx, Pv, a.a_off + mb * 128 + j * 8) : src + j * 8;
+      r.v[h] = (r.valid && j < a_nchunk) ? ldg128(pj) : make_uint4(0, 0, 0, 0);
     }
   };
   // DenseLayer B tile: this thread's pixel row advances by 64 pixels per chunk; its position in the zero-padded dz planes

@@ -81,6 +81,7 @@ struct WgradArgs {
   // dW^T[c, n] = Σ_p A[p, c] · Bm[p, n]   (A optionally relu(bn(.)))
   int kind;
   const __nv_bfloat16* A;    // arena
+  const __nv_bfloat16* Axp;  // planar mirror of the arena (rl_dev.cuh dact_index) or null: A is read through it
   int lda, a_off, Ca;        // Ca = valid A channels
   int transform;
   BnSrc bn;
