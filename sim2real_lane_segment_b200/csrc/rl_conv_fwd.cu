@@ -775,6 +775,32 @@ __global__ void __launch_bounds__(128, 2) gemm_px_kernel(GemmPxArgs a) {
   TileLoader<128> ld;
   const __nv_bfloat16* rowptr[4];
 
+  // row m of tile t -> arena pixel (or -1): POOL mode orders the rows window-major (4 pixels of a 2x2 window adjacent)
+  auto pixel_of = [&](long t, int m) -> long {
+    if (a.mode == GEMM_POOL) {
+      const int pr_ = (int)(t / a.wblocks), wb_ = (int)(t - (long)pr_ * a.wblocks);
+      const int win = m >> 2, q = m & 3;
+      const int wi = wb_ * 32 + win;
+      if (wi >= a.Wp) return -1;
+      const int img = pr_ / a.Hp, py = pr_ - img * a.Hp;
+      return ((long)img * a.H + 2 * py + (q >> 1)) * a.W + 2 * wi + (q & 1);
+    } else {
+      const long P = t * 128 + m;
+      return P < a.M ? P : -1;
+    }
+  };
+  auto set_rowptrs = [&](long t) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const long P = pixel_of(t, TileLoader<128>::row_of(i));
+      rowptr[i] = P >= 0 ? a.A + (size_t)P * a.lda + a.a_off : nullptr;
+    }
+  };
+  // the first K chunk of a tile is fetched before the previous tile's epilogue, so its latency hides behind it
+  if ((long)blockIdx.x < a.ntiles) {
+    set_rowptrs(blockIdx.x);
+    ld.load(rowptr, min(8, a.K / 8));
+  }
   for (long tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
     // ---- row -> pixel mapping
     int pr = 0, wb = 0;
@@ -787,24 +813,7 @@ __global__ void __launch_bounds__(128, 2) gemm_px_kernel(GemmPxArgs a) {
         mask_img = img;
       }
     }
-    auto pixel_of_row = [&](int m) -> long {
-      if (a.mode == GEMM_POOL) {
-        const int win = m >> 2, q = m & 3;
-        const int wi = wb * 32 + win;
-        if (wi >= a.Wp) return -1;
-        const int img = pr / a.Hp, py = pr % a.Hp;
-        return ((long)img * a.H + 2 * py + (q >> 1)) * a.W + 2 * wi + (q & 1);
-      } else {
-        const long P = tile * 128 + m;
-        return P < a.M ? P : -1;
-      }
-    };
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const long P = pixel_of_row(TileLoader<128>::row_of(i));
-      rowptr[i] = P >= 0 ? a.A + (size_t)P * a.lda + a.a_off : nullptr;
-    }
-    ld.load(rowptr, min(8, a.K / 8));
+    auto pixel_of_row = [&](int m) -> long { return pixel_of(tile, m); };
     for (int kc = 0; kc < nkc; ++kc) {
       const int ck = min(64, a.K - kc * 64);
       const uint32_t s = g & 1, u = g >> 1;
@@ -846,6 +855,10 @@ __global__ void __launch_bounds__(128, 2) gemm_px_kernel(GemmPxArgs a) {
       }
       w_issued = true;
       ++g;
+    }
+    if (tile + gridDim.x < a.ntiles) {  // next tile's first chunk streams in behind this tile's epilogue
+      set_rowptrs(tile + gridDim.x);
+      ld.load(rowptr, min(8, a.K / 8));
     }
     {
       const uint32_t s = (g - 1) & 1, u = (g - 1) >> 1;
