@@ -162,8 +162,8 @@ __device__ __forceinline__ float warp_colsum8(float* sc, const float* gs, const 
   return acc;
 }
 
-// kSmemSums: cross-pixel sums through the shared-memory scratch (fewer instructions; used by the 1x1 kernel) or by
-// shuffle butterflies (no scratch: the 3x3 kernel prefers the shared memory as L1 for its overlapping halo tiles).
+// kSmemSums: cross-pixel sums through a shared-memory scratch or (false, what both kernels use) by shuffle butterflies:
+// the scratch variant's column reads were the hottest lines of the 1x1 kernel and its 12.8 KB cost a resident CTA.
 template <bool kSmemSums>
 __device__ __forceinline__ void dgrad_epilogue(uint32_t tmem_acc, int warp, int lane, const __nv_bfloat16* xrow,
                                                __nv_bfloat16* drow, int cbase, int nvalid, const DgradConsts* k,
@@ -498,7 +498,7 @@ __global__ void __launch_bounds__(128, 3) dgrad_td_kernel(DgradArgs a) {
         mbar_wait(&bar_done[s], u & 1);
         tc_fence_after();
       }
-      dgrad_epilogue<true>(tmem, warp, lane, xrow, drow, mb * 128, nvalid, kcs, a, S1, S2, pre, s_scr);
+      dgrad_epilogue<false>(tmem, warp, lane, xrow, drow, mb * 128, nvalid, kcs, a, S1, S2, pre, nullptr);
       tc_fence_before();
       __syncthreads();
     }
@@ -532,7 +532,7 @@ int launch_dgrad(const DgradArgs& a_in, int grid, cudaStream_t st) {
     { ProfScope _ps(KC_DGRAD_DENSE, st);
     RL_CUDA(launch_pdl(dgrad_dense_kernel, dim3(grid, split ? nmb : 1), dim3(128), smem, st, a)); }
   } else {
-    size_t smem = 2 * 32768 + sizeof(DgradConsts) + (384 + 4 * kScrPerWarp) * sizeof(float);
+    size_t smem = 2 * 32768 + sizeof(DgradConsts) + 384 * sizeof(float);
     { ProfScope _ps(KC_DGRAD_TD, st);
     RL_CUDA(launch_pdl(dgrad_td_kernel, dim3(grid), dim3(128), smem, st, a)); }
   }
