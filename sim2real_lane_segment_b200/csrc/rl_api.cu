@@ -276,7 +276,9 @@ int rl_forward(rl_plan* h, const float* params, const float* bnbuf, const float*
       a.amax = (train && p->training) ? wsb(p) + L.amax_off : nullptr;
       a.out_xp = train ? xp_of(p, L.lvl_out) : nullptr;
       a.out_xp_npx = lo.px;
-      int gx = (int)std::max(1L, std::min(a.ntiles, (long)(2 * sm) / nparts));
+      int npmax = 0;
+      for (int q = 0; q < nparts; ++q) npmax = std::max(npmax, a.part_np[q]);
+      int gx = (int)std::max(1L, std::min(a.ntiles, (long)((npmax <= 128 ? 3 : 2) * sm) / nparts));
       if ((rc = launch_gemm_px(a, gx, nparts, st))) return rc;
       if (train && (rc = launch_channel_stats(act_of(p, L.lvl_out), lo.px, lo.Ct, 0, L.cout, stats_of(p, L.lvl_out), sm, st)))
         return rc;
@@ -638,7 +640,7 @@ extern "C" int rl_backward(rl_plan* h, const float* params, const float* x, floa
       a.ldo = lin.Ct;
       a.o_off = L.in_off;
       a.out_planar_npx = lin.px;
-      int gx = (int)std::max(1L, std::min(a.ntiles, (long)2 * sm));
+      int gx = (int)std::max(1L, std::min(a.ntiles, (long)3 * sm));  // N = 80: three CTAs per SM
       if ((rc = launch_gemm_px(a, gx, 1, st))) return rc;
       WgradArgs w;
       memset(&w, 0, sizeof(w));

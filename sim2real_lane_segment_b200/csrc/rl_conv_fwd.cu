@@ -750,7 +750,8 @@ __global__ void __launch_bounds__(128, 2) gemm_px_kernel(GemmPxArgs a) {
     mbar_init(&bar_done[1], 1);
     fence_mbar_init();
   }
-  if (warp == 0) tmem_alloc(&tmem_base_s, 256);
+  const uint32_t tmem_cols = np <= 128 ? 128u : 256u;  // accumulator columns of this part: 3 CTAs per SM fit when <= 128
+  if (warp == 0) tmem_alloc(&tmem_base_s, tmem_cols);
   pdl_trigger();
   pdl_wait();
   if (a.transform)
@@ -935,7 +936,7 @@ __global__ void __launch_bounds__(128, 2) gemm_px_kernel(GemmPxArgs a) {
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem, 256);
+  if (warp == 0) tmem_dealloc(tmem, tmem_cols);
 }
 
 size_t gemm_px_smem(int K, int np_max) { return (((size_t)K * 8 + 127) & ~(size_t)127) + 2048 + 2 * (16384 + (size_t)8 * np_max * 16); }
