@@ -389,6 +389,13 @@ __global__ void __launch_bounds__(128, 3) dgrad_dense_kernel(DgradArgs a) {
         }
         umma_commit(&bar_mma);
       }
+      // the 128 positions the next tile's halo adds (the rest is this tile's, still in L1): pull them into L1 now so
+      // that the next load_dz does not start with an exposed L2 round trip
+      if (SW == PW && tile + 1 < ntiles) {
+        const long pn = a.dz_guard + (long)(V0 - 1) * PW + (t0 + 128 - SW - 1) + (nrows - 128) + tid;
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(plane0 + pn));
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(plane1 + pn));
+      }
       mbar_wait(&bar_mma, n_mma & 1);
       ++n_mma;
       tc_fence_after();
