@@ -605,7 +605,8 @@ __global__ void __launch_bounds__(kWgThreads, 2) wgrad_kernel(WgradArgs a) {
   const int a_nchunk = (ca + 7) / 8;
   const long HW = (long)a.H * a.W;
   const int nj = (a.kind == WG_DENSE) ? 18 : np / 8;  // 16-byte column chunks of the B tile
-  // A tile: 64 pixel rows x 16 channel chunks -> 4 items per thread: row = 8*warp + (lane&7), chunk = (lane>>3) + 4h
+  // A tile: 64 pixel rows x 16 channel chunks -> two 32-byte items (= 2 adjacent chunks = one 16-channel group) per thread:
+  // row = 8*warp + (lane&7), group = (lane>>3) + 4*(h>>1), chunk = 2*group + (h&1)
   const int a_row = warp * 8 + (lane & 7), a_j0 = lane >> 3;
   // B tile: row = tid & 63, column chunks j = (tid >> 6) + 4q
   const int b_row = tid & 63, b_j0 = tid >> 6;
@@ -622,10 +623,16 @@ __global__ void __launch_bounds__(kWgThreads, 2) wgrad_kernel(WgradArgs a) {
     const long Pv = r.valid ? P : P0;
     const __nv_bfloat16* src = a.A + (size_t)Pv * a.lda + a.a_off + mb * 128;
 #pragma unroll
-    for (int h = 0; h < 4; ++h) {
-      const int j = a_j0 + 4 * h;
+    for (int hh = 0; hh < 2; ++hh) {
+      const int j = 2 * (a_j0 + 4 * hh);  // even chunk of the group; the odd one follows in both layouts
       const __nv_bfloat16* pj = a.Axp ? a.Axp + dact_index(a.npx, Pv, a.a_off + mb * 128 + j * 8) : src + j * 8;
-      r.v[h] = (r.valid && j < a_nchunk) ? ldg128(pj) : make_uint4(0, 0, 0, 0);
+      if (r.valid && j < a_nchunk) {
+        const u32x8 v = ldg256_nc_nohint(pj);
+        r.v[2 * hh] = v.lo;
+        r.v[2 * hh + 1] = v.hi;
+      } else {
+        r.v[2 * hh] = r.v[2 * hh + 1] = make_uint4(0, 0, 0, 0);
+      }
     }
   };
   // DenseLayer B tile: this thread's pixel row advances by 64 pixels per chunk; its position in the zero-padded dz planes
@@ -683,7 +690,7 @@ __global__ void __launch_bounds__(kWgThreads, 2) wgrad_kernel(WgradArgs a) {
     uint8_t* sA = stage_base + s * kStageBytes;
 #pragma unroll
     for (int h = 0; h < 4; ++h) {
-      const int j = a_j0 + 4 * h;
+      const int j = 2 * (a_j0 + 4 * (h >> 1)) + (h & 1);
       if (j < a_nchunk) {
         uint4 o = r.v[h];
         if (a.transform && r.valid) o = bn_relu8(o, s_s + j * 8, s_t + j * 8);
