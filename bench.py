@@ -21,7 +21,8 @@ sys.path.insert(0, ROOT)
 
 METRIC = "train images/sec (whole box)"
 KCLASS = ["dense_fwd", "gemm_px", "dgrad_dense", "dgrad_td", "wgrad", "head", "dz_prepare", "channel_stats", "first_fwd",
-          "tu_col2im", "pack_weights", "optimizer", "misc"]
+          "tu_col2im", "pack_weights", "optimizer", "misc", "dgrad_bulk", "wgrad_dense"]
+NK = len(KCLASS)
 
 
 def parse():
@@ -291,16 +292,18 @@ def run_b200(args, rank, world, local_rank):
     # ---- per-class CUDA-event timing of our kernels on the launching stream (2 profiled steps)
     roof, shares = None, None
     if rank == 0:
-        msb = (ctypes.c_double * 13)()
-        lnb = (ctypes.c_long * 13)()
-        L.rl_set_option(b"overlap", 0)   # time every kernel alone (the side-stream overlap would smear the class times)
+        msb = (ctypes.c_double * NK)()
+        lnb = (ctypes.c_long * NK)()
+        for eng in rt.engines.values():   # time every kernel alone (the side-stream overlap would smear the class times)
+            eng.set_option("overlap", 0)
         L.rl_profile_begin()
         nprof = 2
         for i in range(nprof):
             step_local(i)
         L.rl_profile_end(msb, lnb)
-        L.rl_set_option(b"overlap", 1)
-        per = {KCLASS[i]: (msb[i] / nprof, lnb[i] // nprof) for i in range(13)}
+        for eng in rt.engines.values():
+            eng.set_option("overlap", 1)
+        per = {KCLASS[i]: (msb[i] / nprof, lnb[i] // nprof) for i in range(NK)}
         tot = sum(v[0] for v in per.values())
         shares = {k: round(v[0] / tot, 4) for k, v in per.items() if v[1]}
         algo = algorithmic_bytes(B, H, W)

@@ -54,7 +54,22 @@ enum {
   RL_Q_LAYER_MASK_OFF = 9,  /* byte offset of float[B][cout] dropout keep-scale (dense / transition-down layers) */
   RL_Q_LAYER_COUT = 10,
   RL_Q_LAYER_PARAM_W = 11,  /* float offset of the layer's conv weight in the parameter arena */
-  RL_Q_LEVEL_STATS_OFF = 12 /* byte offset of double[2][Ct]: per-channel sum, sum of squares */
+  RL_Q_LEVEL_STATS_OFF = 12, /* byte offset of double[2][Ct]: per-channel sum, sum of squares */
+  RL_Q_GSTAGE_OFF = 13,      /* byte offset of float[num_params]: raw gradients of the current backward pass */
+  RL_Q_LEVEL_XP_OFF = 14,    /* byte offset of the planar mirror [Ct/16][pixels][16] bf16 of a level's activations */
+  RL_Q_LEVEL_ACC_OFF = 15,   /* byte offset of double[2][Ct]: BatchNorm-backward mean terms A_c, B_c (sums, not yet / N) */
+  RL_Q_LAYER_LEVEL_IN = 16,
+  RL_Q_LAYER_LEVEL_OUT = 17,
+  RL_Q_LAYER_CIN = 18,
+  RL_Q_LAYER_IN_OFF = 19,    /* first input channel in the input level's arena (TransitionUp) */
+  RL_Q_LAYER_OUT_OFF = 20,   /* first output channel in the output level's arena */
+  RL_Q_LAYER_CS_PERM = 21,   /* > 0: up-path layer, C_skip of its level (reference [up|skip|new] <-> physical [skip|up|new]) */
+  RL_Q_LAYER_AMAX_OFF = 22,  /* TransitionDown: byte offset of the uint8 arg-max [pooled pixels][C] */
+  RL_Q_LAYER_RMW_FROM = 23,
+  RL_Q_LAYER_PARAM_GAMMA = 24, /* float offsets in the parameter arena (-1: absent): BatchNorm weight (bias follows, then conv weight) */
+  RL_Q_LAYER_PARAM_B = 25,     /* conv bias */
+  RL_Q_LAYER_BN_RM = 26,       /* float offset of running_mean in the BN-buffer arena (running_var follows) */
+  RL_Q_DL_OFF = 27             /* byte offset of bf16 [pixels][16]: d(logits)/||f|| written by rl_head(backward) */
 };
 int rl_plan_query(const rl_plan* p, int what, int index, long* out);
 
@@ -70,22 +85,33 @@ int rl_set_dropout(rl_plan* p, float p_drop, unsigned long long seed, unsigned l
  * level-0 arena (288 channels).  train != 0: BatchNorm uses batch statistics (and they are retained for
  * rl_bn_running_update / rl_backward); else running statistics from bn_buffers. */
 int rl_forward(rl_plan* p, const float* params, const float* bn_buffers, const float* x, int train, void* stream);
+/* the same for layers layer_lo..layer_hi of the plan's forward order only (0 = first conv; RL_Q_LAYER_TYPE), on whatever
+ * the arenas hold: the per-layer entry point the parity tests use (models/FCDenseNet/layers.py:5-69, one module at a
+ * time).  Does not clear the batch statistics. */
+int rl_forward_range(rl_plan* p, const float* params, const float* bn_buffers, const float* x, int train, int layer_lo,
+                     int layer_hi, void* stream);
 
 /* F.normalize (tiramisu.py:105) + FCDenseNetClassifier.forward (tiramisu.py:120-125) + cross_entropy on the
  * probabilities + argmax + confusion counts (SimpleTrain.py:15-20, TrainingBase.py:84-93, test.py:93-100).
  *   y: labels uint8 or int64 [B,H,W] or NULL; weighted: class weights 1/count as getClassWeight (TrainingBase.py:12-23)
  *   probs (fp32 [B,C,H,W]) / mask (uint8 [B,H,W]) may be NULL.  Loss sums and counts land in the scalars block.
- *   backward: 0 = forward only; 1 = also start the backward pass with the fused CE gradient times grad_scale
- *   (times *grad_scale_dev if that device pointer is non-NULL: the loss's grad_output, read without a host sync);
- *   2 = backward from an external d(loss)/d(probs) (dprobs fp32 [B,C,H,W]).  feat_grad_sign = -1 realises
- *   GradReverse (tiramisu.py:7-18).  Classifier gradients are accumulated into grads. */
+ *   backward: 0 = forward only; 1 = the same launch also starts the backward pass with the fused CE gradient
+ *   d(loss)/d(features) for loss grad_output 1 (rl_backward applies the real grad_output); 2 = backward from an external
+ *   d(loss)/d(probs) (dprobs fp32 [B,C,H,W]).  feat_grad_sign = -1 realises GradReverse (tiramisu.py:7-18).
+ *   backward != 0 clears the plan's gradient stage (RL_Q_GSTAGE_OFF) and adds the classifier-bias gradient to it. */
 int rl_head(rl_plan* p, const float* params, const void* y, int y_is_i64, int weighted, float* probs, uint8_t* mask,
-            int backward, const float* dprobs, float grad_scale, const float* grad_scale_dev, float feat_grad_sign,
-            float* grads, void* stream);
+            int backward, const float* dprobs, float feat_grad_sign, void* stream);
 
-/* loss.backward() for everything below the head (SimpleTrain.py:25 + autograd): accumulates into grads (fp32 arena,
- * same layout as params).  Requires rl_forward(train=1) and rl_head(backward != 0) on the same plan. */
-int rl_backward(rl_plan* p, const float* params, const float* x, float* grads, void* stream);
+/* loss.backward() for everything below the head (SimpleTrain.py:25 + autograd).  The pass's raw gradients are staged in
+ * the workspace and added to grads (fp32 arena, same layout as params) at the end:
+ *   grads += grad_scale * (grad_scale_dev ? *grad_scale_dev : 1) * stage
+ * (grad_scale_dev: the loss's grad_output as a device scalar, read without a host sync).
+ * Requires rl_forward(train=1) and rl_head(backward != 0) on the same plan. */
+int rl_backward(rl_plan* p, const float* params, float* grads, float grad_scale, const float* grad_scale_dev, void* stream);
+/* backward of layers layer_hi..layer_lo only (descending; layer_hi = RL_Q_NUM_LAYERS adds the classifier weight
+ * gradient), from whatever the gradient arenas hold, into the gradient stage; no clearing, no final scaling: the
+ * per-layer / per-DenseBlock entry point the parity tests use (autograd of layers.py:5-69 one module at a time). */
+int rl_backward_range(rl_plan* p, const float* params, int layer_hi, int layer_lo, void* stream);
 
 /* running_mean / running_var momentum update of all 60 BatchNorm2d layers from the last training forward */
 int rl_bn_running_update(rl_plan* p, float* bn_buffers, float momentum, void* stream);
@@ -114,20 +140,22 @@ int rl_overlay(const unsigned char* frames_bgr, int B, int Hs, int Ws, int H, in
 
 /* launch accounting: number of kernels this library has launched (kernel_class < 0: all classes), and optional
  * per-class CUDA-event timing for bench.py's roofline (classes: 0 dense_fwd, 1 gemm_px, 2 dgrad_dense, 3 dgrad_td,
- * 4 wgrad, 5 head, 6 dz_prepare, 7 channel_stats, 8 first_fwd, 9 tu_col2im, 10 pack, 11 optimizer, 12 misc).
- * rl_profile_end synchronises the device and fills ms[13], launches[13] (host pointers). */
+ * 4 wgrad, 5 head, 6 dz_prepare, 7 channel_stats, 8 first_fwd, 9 tu_col2im, 10 pack, 11 optimizer, 12 misc,
+ * 13 dgrad_bulk, 14 wgrad_dense).  rl_profile_end synchronises the device and fills ms[RL_NUM_KERNEL_CLASSES],
+ * launches[RL_NUM_KERNEL_CLASSES] (host pointers). */
+enum { RL_NUM_KERNEL_CLASSES = 15 };
 long rl_launch_count(int kernel_class);
 int rl_profile_begin(void);
 int rl_profile_end(double* ms, long* launches);
 int rl_profile_launches(float* ms, int* kernel_class, int max); /* per-launch times of the last profiled region */
 
-/* runtime switches: "overlap" (default 1) runs the DenseLayer weight-gradient kernels of rl_backward on a plan-owned
- * side stream concurrently with the input-gradient chain (joined before rl_backward returns control of the stream);
- * "fwd_tma" (default 1) runs the DenseLayer forward of levels up to 160 pixels wide through the tensor-map TMA kernel
- * (0: the register-staged kernel; same GEMMs, the fp32 shift-add order differs); "xp" (default 1): training forward
- * passes also write the planar mirror of the activation arenas that the input-gradient kernels read (0: they read the
- * NHWC arenas; set it before rl_forward). */
-int rl_set_option(const char* name, int value);
+/* per-plan switches (all default 1): "overlap": weight-gradient kernels of rl_backward run on a plan-owned side stream
+ * concurrently with the input-gradient chain (joined before rl_backward returns control of the stream); "fwd_tma": the
+ * DenseLayer forward goes through the tensor-map TMA kernel (0: the register-staged kernel; same GEMMs, the fp32
+ * shift-add order differs); "xp": training forward passes also write the planar mirror of the activation arenas that the
+ * backward kernels read (0: they read the NHWC arenas; set it before rl_forward); "bwd_fused": DenseBlocks run their
+ * backward through the block-fused kernels (0: five per-layer input-gradient and weight-gradient launches). */
+int rl_plan_set_option(rl_plan* p, const char* name, int value);
 
 /* test hook: one tcgen05 GEMM (M = 128) from caller-supplied shared-memory images of A and B and the upper bits of both
  * matrix descriptors (start address filled in by the kernel, advanced by *_kstep_bytes per K = 16 step) */

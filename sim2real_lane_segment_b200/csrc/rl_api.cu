@@ -17,19 +17,25 @@ struct rl_plan {
 
 namespace rl {
 int td_parts(int C, int* n0, int* np);
+int configure_fwd_kernels();
+int configure_bwd_kernels();
+int configure_fused_kernels();
+int configure_kernels() {
+  int rc;
+  if ((rc = configure_fwd_kernels())) return rc;
+  if ((rc = configure_bwd_kernels())) return rc;
+  return configure_fused_kernels();
+}
 }
 
 static inline uint8_t* wsb(const Plan* p) { return (uint8_t*)p->ws; }
 static inline __nv_bfloat16* act_of(const Plan* p, int l) { return (__nv_bfloat16*)(wsb(p) + p->lv[l].act_off); }
 static inline __nv_bfloat16* dact_of(const Plan* p, int l) { return (__nv_bfloat16*)(wsb(p) + p->lv[l].dact_off); }
-// planar mirror of a level's activations (training plans only; RL_XP=0 keeps every reader on the NHWC arena)
-static bool g_xp = []() {
-  const char* e = getenv("RL_XP");
-  return !(e && e[0] == '0');
-}();
+// planar mirror of a level's activations (training plans only; option "xp" = 0 keeps every reader on the NHWC arena)
 static inline __nv_bfloat16* xp_of(const Plan* p, int l) {
-  return (p->training && g_xp) ? (__nv_bfloat16*)(wsb(p) + p->lv[l].xp_off) : nullptr;
+  return (p->training && p->opt_xp) ? (__nv_bfloat16*)(wsb(p) + p->lv[l].xp_off) : nullptr;
 }
+static inline float* gstage_of(const Plan* p) { return (float*)(wsb(p) + p->gstage_off); }
 static inline double* stats_of(const Plan* p, int l) { return (double*)(wsb(p) + p->lv[l].stats_off); }
 static inline double* acc_of(const Plan* p, int l) { return (double*)(wsb(p) + p->lv[l].acc_off); }
 static inline Scalars* scal_of(const Plan* p) { return (Scalars*)(wsb(p) + p->scal_off); }
@@ -78,6 +84,8 @@ void rl_plan_destroy(rl_plan* h) {
     if (p.ev_dz[i]) cudaEventDestroy((cudaEvent_t)p.ev_dz[i]);
     if (p.ev_wg[i]) cudaEventDestroy((cudaEvent_t)p.ev_wg[i]);
   }
+  for (int i = 0; i < kLevels; ++i)
+    if (p.ev_blk[i]) cudaEventDestroy((cudaEvent_t)p.ev_blk[i]);
   if (p.side_stream) cudaStreamDestroy((cudaStream_t)p.side_stream);
   delete h;
 }
@@ -103,6 +111,21 @@ int rl_plan_query(const rl_plan* h, int what, int index, long* out) {
     case 10: if (!lay_ok) break; *out = p.layers[index].cout; return RL_OK;
     case 11: if (!lay_ok) break; *out = p.layers[index].p_w; return RL_OK;
     case 12: if (!lvl_ok) break; *out = (long)p.lv[index].stats_off; return RL_OK;
+    case 13: *out = (long)p.gstage_off; return RL_OK;
+    case 14: if (!lvl_ok) break; *out = (long)p.lv[index].xp_off; return RL_OK;
+    case 15: if (!lvl_ok) break; *out = (long)p.lv[index].acc_off; return RL_OK;
+    case 16: if (!lay_ok) break; *out = p.layers[index].lvl_in; return RL_OK;
+    case 17: if (!lay_ok) break; *out = p.layers[index].lvl_out; return RL_OK;
+    case 18: if (!lay_ok) break; *out = p.layers[index].cin; return RL_OK;
+    case 19: if (!lay_ok) break; *out = p.layers[index].in_off; return RL_OK;
+    case 20: if (!lay_ok) break; *out = p.layers[index].out_off; return RL_OK;
+    case 21: if (!lay_ok) break; *out = p.layers[index].cs_perm; return RL_OK;
+    case 22: if (!lay_ok) break; *out = (long)p.layers[index].amax_off; return RL_OK;
+    case 23: if (!lay_ok) break; *out = p.layers[index].rmw_from; return RL_OK;
+    case 24: if (!lay_ok) break; *out = p.layers[index].p_gamma; return RL_OK;
+    case 25: if (!lay_ok) break; *out = p.layers[index].p_b; return RL_OK;
+    case 26: if (!lay_ok) break; *out = p.layers[index].b_rm; return RL_OK;
+    case 27: *out = (long)p.dl_off; return RL_OK;
     default: return rl_fail(RL_ERR_ARG, "rl_plan_query: unknown selector %d", what);
   }
   return rl_fail(RL_ERR_ARG, "rl_plan_query: index %d out of range for selector %d", index, what);
@@ -137,7 +160,15 @@ int rl_plan_bind(rl_plan* h, void* workspace, void* stream) {
       e.kind = 4; e.dst_off = (long)L.wpk_fwd; e.n16 = 3L * 2 * 8 * 240; pk.push_back(e);
       e.kind = 5; e.dst_off = (long)L.wpk_bwd; e.n16 = 12L * 8 * 80; pk.push_back(e);
     }
+    if (L.type == L_DENSE && p.training) {
+      const Block& b = p.blocks[L.blk];
+      if (L.jblk > 0) {
+        e.kind = 6; e.dst_off = (long)L.wpk_chain; e.n16 = 18L * 128; e.c_lo = b.C0; e.nch = kGrowth * L.jblk; pk.push_back(e);
+      }
+      e.kind = 7; e.dst_off = (long)L.wpk_bulk; e.n16 = (long)b.ncb * 18 * kBulkCb; e.c_lo = b.C0; e.nch = b.cbs; pk.push_back(e);
+    }
   }
+  if (pk.size() > 256) return rl_fail(RL_ERR_STATE, "rl_plan_bind: pack table overflow");
   p.n_pack = (int)pk.size();
   RL_CUDA(cudaMemcpyAsync(wsb(&p) + p.packtab_off, pk.data(), pk.size() * sizeof(PackEntry), cudaMemcpyHostToDevice, st));
   // ---- BN table
@@ -165,6 +196,10 @@ int rl_plan_bind(rl_plan* h, void* workspace, void* stream) {
     int rc = encode_arena_tmap(p.tmap_act[l], act_of(&p, l), p.lv[l].px, p.lv[l].Ct, p.lv[l].W);
     if (rc) return rc;
   }
+  {
+    int rc = configure_kernels();  // per device: a process may bind plans on several GPUs
+    if (rc) return rc;
+  }
   if (p.training && !p.side_stream) {
     cudaStream_t s2;
     RL_CUDA(cudaStreamCreateWithFlags(&s2, cudaStreamNonBlocking));
@@ -175,6 +210,11 @@ int rl_plan_bind(rl_plan* h, void* workspace, void* stream) {
       p.ev_dz[i] = e;
       RL_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
       p.ev_wg[i] = e;
+    }
+    for (int i = 0; i < kLevels; ++i) {
+      cudaEvent_t e;
+      RL_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+      p.ev_blk[i] = e;
     }
   }
   RL_CUDA(cudaStreamSynchronize(st));  // host vectors go out of scope
@@ -194,137 +234,152 @@ int rl_set_dropout(rl_plan* h, float p_drop, unsigned long long seed, unsigned l
                            step, (cudaStream_t)stream);
 }
 
-// DenseLayer forward through the tensor-map TMA kernel (RL_FWD_TMA=0 selects the register-staged kernel)
-static bool g_fwd_tma = []() {
-  const char* e = getenv("RL_FWD_TMA");
-  return !(e && e[0] == '0');
-}();
+}  // extern "C"
 
-static const int g_fwd_dbg = []() {
-  const char* e = getenv("RL_FWD_DBG");
-  return e ? atoi(e) : 0;
-}();
-
-int rl_forward(rl_plan* h, const float* params, const float* bnbuf, const float* x, int train, void* stream) {
-  if (!h || !h->p.ws) return rl_fail(RL_ERR_STATE, "rl_forward: plan not bound");
-  if (!params || !x || (!train && !bnbuf)) return rl_fail(RL_ERR_ARG, "rl_forward: null argument");
-  Plan* p = &h->p;
-  cudaStream_t st = (cudaStream_t)stream;
+// ------------------------------------------------------------------------------------------------
+// forward schedule: one call per layer of Plan::layers (forward order)
+// ------------------------------------------------------------------------------------------------
+static int forward_layer(Plan* p, int li, const float* params, const float* bnbuf, const float* x, int train, cudaStream_t st) {
+  const Layer& L = p->layers[li];
+  const Level& lin = p->lv[L.lvl_in];
+  const Level& lo = p->lv[L.lvl_out];
   const int sm = p->sm_count;
-  if (train) RL_CUDA(cudaMemsetAsync(wsb(p) + p->stats_off_all, 0, p->stats_bytes, st));
   int rc;
-  for (const Layer& L : p->layers) {
-    const Level& li = p->lv[L.lvl_in];
-    const Level& lo = p->lv[L.lvl_out];
-    if (L.type == L_FIRST) {
-      if ((rc = launch_first_fwd(p, x, params, train && g_xp, st))) return rc;
-      if (train && (rc = launch_channel_stats(act_of(p, 0), lo.px, lo.Ct, 0, kFirst, stats_of(p, 0), sm, st))) return rc;
-    } else if (L.type == L_DENSE) {
-      DenseFwdArgs a;
-      a.act = act_of(p, L.lvl_in);
-      a.act_out = act_of(p, L.lvl_in);
-      a.Ct = li.Ct;
-      a.Cin = L.cin;
-      a.H = li.H;
-      a.W = li.W;
-      a.rows_total = p->B * li.H;
-      const bool use_tma = g_fwd_tma && p->tmap_ok;
-      if (use_tma && li.W > 160) {  // strips whose 128-column input window (strip + 2 halo columns) is one TMA box row
-        a.nstrips = (li.W + 125) / 126;
-        a.strip_w = (li.W + a.nstrips - 1) / a.nstrips;
-      } else {
-        a.strip_w = 160;
-        a.nstrips = (li.W + a.strip_w - 1) / a.strip_w;
-      }
-      int nruns = std::max(1, std::min(a.rows_total, ((use_tma ? 1 : 2) * sm) / a.nstrips));
-      a.rows_per_cta = (a.rows_total + nruns - 1) / nruns;
-      nruns = (a.rows_total + a.rows_per_cta - 1) / a.rows_per_cta;
-      a.wpk = wsb(p) + L.wpk_fwd;
-      a.bias = params + L.p_b;
-      a.mask = train ? (const float*)(wsb(p) + L.mask_off) : nullptr;
-      a.bn = make_bn(p, L, params, bnbuf, train);
-      a.stats_out = train ? stats_of(p, L.lvl_in) : nullptr;
-      a.dbg = g_fwd_dbg;
-      a.x16 = (train && xp_of(p, L.lvl_in)) ? xp_of(p, L.lvl_in) + (size_t)(L.cin / 16) * li.px * 16 : nullptr;
-      if (use_tma) {
-        if ((rc = launch_dense_fwd_tma(a, p->tmap_act[L.lvl_in], nruns * a.nstrips, st))) return rc;
-      } else if ((rc = launch_dense_fwd(a, nruns * a.nstrips, st))) return rc;
-    } else if (L.type == L_TD) {
-      GemmPxArgs a;
-      memset(&a, 0, sizeof(a));
-      a.A = act_of(p, L.lvl_in);
-      a.lda = li.Ct;
-      a.a_off = 0;
-      a.K = L.cin;
-      a.mode = GEMM_POOL;
-      a.H = li.H;
-      a.W = li.W;
-      a.Hp = lo.H;
-      a.Wp = lo.W;
-      a.wblocks = (lo.W + 31) / 32;
-      a.ntiles = (long)p->B * lo.H * a.wblocks;
-      a.transform = 1;
-      a.bn = make_bn(p, L, params, bnbuf, train);
-      a.wpk = wsb(p) + L.wpk_fwd;
-      a.N = L.cout;
-      int nparts = td_parts(L.cout, a.part_n0, a.part_np);
-      a.bias = params + L.p_b;
-      a.mask = train ? (const float*)(wsb(p) + L.mask_off) : nullptr;
-      a.out = act_of(p, L.lvl_out);
-      a.ldo = lo.Ct;
-      a.o_off = 0;
-      a.amax = (train && p->training) ? wsb(p) + L.amax_off : nullptr;
-      a.out_xp = train ? xp_of(p, L.lvl_out) : nullptr;
-      a.out_xp_npx = lo.px;
-      int npmax = 0;
-      for (int q = 0; q < nparts; ++q) npmax = std::max(npmax, a.part_np[q]);
-      int gx = (int)std::max(1L, std::min(a.ntiles, (long)((npmax <= 128 ? 3 : 2) * sm) / nparts));
-      if ((rc = launch_gemm_px(a, gx, nparts, st))) return rc;
-      if (train && (rc = launch_channel_stats(act_of(p, L.lvl_out), lo.px, lo.Ct, 0, L.cout, stats_of(p, L.lvl_out), sm, st)))
-        return rc;
-    } else {  // L_TU
-      GemmPxArgs a;
-      memset(&a, 0, sizeof(a));
-      a.A = act_of(p, L.lvl_in);
-      a.lda = li.Ct;
-      a.a_off = L.in_off;
-      a.K = kUpCh;
-      a.M = li.px;
-      a.ntiles = (li.px + 127) / 128;
-      a.mode = GEMM_LINEAR;
-      a.transform = 0;
-      a.wpk = wsb(p) + L.wpk_fwd;
-      a.N = 720;
-      for (int q = 0; q < 3; ++q) {
-        a.part_n0[q] = q * 240;
-        a.part_np[q] = 240;
-      }
-      a.out = (__nv_bfloat16*)(wsb(p) + p->tmp_off);
-      a.ldo = 720;
-      a.o_off = 0;
-      int gx = (int)std::max(1L, std::min(a.ntiles, (long)(2 * sm) / 3));
-      if ((rc = launch_gemm_px(a, gx, 3, st))) return rc;
-      if ((rc = launch_tu_col2im((const __nv_bfloat16*)(wsb(p) + p->tmp_off), act_of(p, L.lvl_out),
-                                 train ? xp_of(p, L.lvl_out) : nullptr, params + L.p_b, p->B, li.H,
-                                 li.W, lo.H, lo.W, lo.Ct, L.out_off, st)))
-        return rc;
-      if (train && (rc = launch_channel_stats(act_of(p, L.lvl_out), lo.px, lo.Ct, L.out_off, kUpCh, stats_of(p, L.lvl_out), sm, st)))
-        return rc;
+  if (L.type == L_FIRST) {
+    if ((rc = launch_first_fwd(p, x, params, train && p->opt_xp, st))) return rc;
+    if (train && (rc = launch_channel_stats(act_of(p, 0), lo.px, lo.Ct, 0, kFirst, stats_of(p, 0), sm, st))) return rc;
+  } else if (L.type == L_DENSE) {
+    DenseFwdArgs a;
+    memset(&a, 0, sizeof(a));
+    a.act = act_of(p, L.lvl_in);
+    a.act_out = act_of(p, L.lvl_in);
+    a.Ct = lin.Ct;
+    a.Cin = L.cin;
+    a.H = lin.H;
+    a.W = lin.W;
+    a.rows_total = p->B * lin.H;
+    const bool use_tma = p->opt_fwd_tma && p->tmap_ok;
+    if (use_tma && lin.W > 160) {  // strips whose 128-column input window (strip + 2 halo columns) is one TMA box row
+      a.nstrips = (lin.W + 125) / 126;
+      a.strip_w = (lin.W + a.nstrips - 1) / a.nstrips;
+    } else {
+      a.strip_w = 160;
+      a.nstrips = (lin.W + a.strip_w - 1) / a.strip_w;
     }
+    int nruns = std::max(1, std::min(a.rows_total, ((use_tma ? 1 : 2) * sm) / a.nstrips));
+    a.rows_per_cta = (a.rows_total + nruns - 1) / nruns;
+    nruns = (a.rows_total + a.rows_per_cta - 1) / a.rows_per_cta;
+    a.wpk = wsb(p) + L.wpk_fwd;
+    a.bias = params + L.p_b;
+    a.mask = train ? (const float*)(wsb(p) + L.mask_off) : nullptr;
+    a.bn = make_bn(p, L, params, bnbuf, train);
+    a.stats_out = train ? stats_of(p, L.lvl_in) : nullptr;
+    a.x16 = (train && xp_of(p, L.lvl_in)) ? xp_of(p, L.lvl_in) + (size_t)(L.cin / 16) * lin.px * 16 : nullptr;
+    if (use_tma) {
+      if ((rc = launch_dense_fwd_tma(a, p->tmap_act[L.lvl_in], nruns * a.nstrips, st))) return rc;
+    } else if ((rc = launch_dense_fwd(a, nruns * a.nstrips, st))) {
+      return rc;
+    }
+  } else if (L.type == L_TD) {
+    GemmPxArgs a;
+    memset(&a, 0, sizeof(a));
+    a.A = act_of(p, L.lvl_in);
+    a.lda = lin.Ct;
+    a.a_off = 0;
+    a.K = L.cin;
+    a.mode = GEMM_POOL;
+    a.H = lin.H;
+    a.W = lin.W;
+    a.Hp = lo.H;
+    a.Wp = lo.W;
+    a.wblocks = (lo.W + 31) / 32;
+    a.ntiles = (long)p->B * lo.H * a.wblocks;
+    a.transform = 1;
+    a.bn = make_bn(p, L, params, bnbuf, train);
+    a.wpk = wsb(p) + L.wpk_fwd;
+    a.N = L.cout;
+    int nparts = td_parts(L.cout, a.part_n0, a.part_np);
+    a.bias = params + L.p_b;
+    a.mask = train ? (const float*)(wsb(p) + L.mask_off) : nullptr;
+    a.out = act_of(p, L.lvl_out);
+    a.ldo = lo.Ct;
+    a.o_off = 0;
+    a.amax = (train && p->training) ? wsb(p) + L.amax_off : nullptr;
+    a.out_xp = train ? xp_of(p, L.lvl_out) : nullptr;
+    a.out_xp_npx = lo.px;
+    int npmax = 0;
+    for (int q = 0; q < nparts; ++q) npmax = std::max(npmax, a.part_np[q]);
+    int gx = (int)std::max(1L, std::min(a.ntiles, (long)((npmax <= 128 ? 3 : 2) * sm) / nparts));
+    if ((rc = launch_gemm_px(a, gx, nparts, st))) return rc;
+    if (train && (rc = launch_channel_stats(act_of(p, L.lvl_out), lo.px, lo.Ct, 0, L.cout, stats_of(p, L.lvl_out), sm, st)))
+      return rc;
+  } else {  // L_TU
+    GemmPxArgs a;
+    memset(&a, 0, sizeof(a));
+    a.A = act_of(p, L.lvl_in);
+    a.lda = lin.Ct;
+    a.a_off = L.in_off;
+    a.K = kUpCh;
+    a.M = lin.px;
+    a.ntiles = (lin.px + 127) / 128;
+    a.mode = GEMM_LINEAR;
+    a.transform = 0;
+    a.wpk = wsb(p) + L.wpk_fwd;
+    a.N = 720;
+    for (int q = 0; q < 3; ++q) {
+      a.part_n0[q] = q * 240;
+      a.part_np[q] = 240;
+    }
+    a.out = (__nv_bfloat16*)(wsb(p) + p->tmp_off);
+    a.ldo = 720;
+    a.o_off = 0;
+    int gx = (int)std::max(1L, std::min(a.ntiles, (long)(2 * sm) / 3));
+    if ((rc = launch_gemm_px(a, gx, 3, st))) return rc;
+    if ((rc = launch_tu_col2im((const __nv_bfloat16*)(wsb(p) + p->tmp_off), act_of(p, L.lvl_out),
+                               train ? xp_of(p, L.lvl_out) : nullptr, params + L.p_b, p->B, lin.H, lin.W, lo.H, lo.W, lo.Ct,
+                               L.out_off, st)))
+      return rc;
+    if (train && (rc = launch_channel_stats(act_of(p, L.lvl_out), lo.px, lo.Ct, L.out_off, kUpCh, stats_of(p, L.lvl_out), sm, st)))
+      return rc;
   }
   return RL_OK;
 }
 
-int rl_head(rl_plan* h, const float* params, const void* y, int y_is_i64, int weighted, float* probs, uint8_t* mask,
-            int backward, const float* dprobs, float grad_scale, const float* grad_scale_dev, float feat_grad_sign,
-            float* grads, void* stream) {
+extern "C" int rl_forward_range(rl_plan* h, const float* params, const float* bnbuf, const float* x, int train, int layer_lo,
+                                int layer_hi, void* stream) {
+  if (!h || !h->p.ws) return rl_fail(RL_ERR_STATE, "rl_forward: plan not bound");
+  if (!params || (!train && !bnbuf)) return rl_fail(RL_ERR_ARG, "rl_forward: null argument");
+  Plan* p = &h->p;
+  const int n = (int)p->layers.size();
+  if (layer_lo < 0 || layer_hi >= n || layer_lo > layer_hi) return rl_fail(RL_ERR_ARG, "rl_forward_range: bad layer range");
+  if (layer_lo == 0 && !x) return rl_fail(RL_ERR_ARG, "rl_forward: null input");
+  cudaStream_t st = (cudaStream_t)stream;
+  for (int li = layer_lo; li <= layer_hi; ++li) {
+    int rc = forward_layer(p, li, params, bnbuf, x, train, st);
+    if (rc) return rc;
+  }
+  return RL_OK;
+}
+
+extern "C" int rl_forward(rl_plan* h, const float* params, const float* bnbuf, const float* x, int train, void* stream) {
+  if (!h || !h->p.ws) return rl_fail(RL_ERR_STATE, "rl_forward: plan not bound");
+  Plan* p = &h->p;
+  if (train) RL_CUDA(cudaMemsetAsync(wsb(p) + p->stats_off_all, 0, p->stats_bytes, (cudaStream_t)stream));
+  return rl_forward_range(h, params, bnbuf, x, train, 0, (int)p->layers.size() - 1, stream);
+}
+
+extern "C" int rl_head(rl_plan* h, const float* params, const void* y, int y_is_i64, int weighted, float* probs, uint8_t* mask,
+                       int backward, const float* dprobs, float feat_grad_sign, void* stream) {
   if (!h || !h->p.ws) return rl_fail(RL_ERR_STATE, "rl_head: plan not bound");
   Plan* p = &h->p;
   cudaStream_t st = (cudaStream_t)stream;
-  if (backward && (!p->training || !grads)) return rl_fail(RL_ERR_STATE, "rl_head: backward needs a training plan and grads");
+  if (!params) return rl_fail(RL_ERR_ARG, "rl_head: null parameters");
+  if (backward && !p->training) return rl_fail(RL_ERR_STATE, "rl_head: backward needs a training plan");
   if (backward == 2 && !dprobs) return rl_fail(RL_ERR_ARG, "rl_head: backward=2 needs dprobs");
   if (backward == 1 && !y) return rl_fail(RL_ERR_ARG, "rl_head: fused CE backward needs labels");
   RL_CUDA(cudaMemsetAsync(scal_of(p), 0, sizeof(Scalars), st));
+  // a backward pass starts here: its raw gradients are staged and scaled into the caller's arena by rl_backward
+  if (backward) RL_CUDA(cudaMemsetAsync(gstage_of(p), 0, (size_t)p->n_params * sizeof(float), st));
   int rc;
   if (y && (rc = launch_label_hist(y, y_is_i64, p->lv[0].px, p->num_cls, scal_of(p), st))) return rc;
   HeadArgs a;
@@ -343,14 +398,16 @@ int rl_head(rl_plan* h, const float* params, const void* y, int y_is_i64, int we
   a.sc = scal_of(p);
   a.weighted = weighted;
   a.dprobs = backward == 2 ? dprobs : nullptr;
-  a.grad_scale = grad_scale;
-  a.grad_scale_dev = grad_scale_dev;
+  a.grad_scale = 1.f;
+  a.grad_scale_dev = nullptr;
   a.feat_grad_sign = feat_grad_sign;
   a.dact = backward ? dact_of(p, 0) : nullptr;
   a.dl = backward ? (__nv_bfloat16*)(wsb(p) + p->dl_off) : nullptr;
-  a.g_b = backward ? grads + p->p_cls_b : nullptr;
+  a.g_b = backward ? gstage_of(p) + p->p_cls_b : nullptr;
   return launch_head(a, p->sm_count, st);
 }
+
+extern "C" {
 
 int rl_bn_running_update(rl_plan* h, float* bnbuf, float momentum, void* stream) {
   if (!h || !h->p.ws || !bnbuf) return rl_fail(RL_ERR_STATE, "rl_bn_running_update: plan not bound / null buffers");
@@ -373,340 +430,519 @@ int rl_sgd_nesterov_step(float* params, const float* grads, float* buf, long n, 
 }  // extern "C"
 
 // ------------------------------------------------------------------------------------------------
-// backward schedule: reverse of the forward layer list
+// backward schedule: reverse of the forward layer list.  Every gradient of one pass goes to the plan's staging arena;
+// rl_backward scales it into the caller's arena at the end (grads += scale * stage).
 // ------------------------------------------------------------------------------------------------
-static int g_overlap = -1;  // DenseLayer weight gradients on the plan's side stream (RL_OVERLAP env / rl_set_option)
+namespace {
 
-static int wgrad_runs(const Plan* p, long npx, int nmb, int nparts, long* px_per_cta, int ctas_per_sm = 2) {
-  long want = std::max(1L, (long)(ctas_per_sm * p->sm_count) / std::max(1, nmb * nparts));
-  long chunks = (npx + 63) / 64;
-  long runs = std::min(want, chunks);
-  long cpr = (chunks + runs - 1) / runs;
-  *px_per_cta = cpr * 64;
-  return (int)((npx + *px_per_cta - 1) / *px_per_cta);
+struct BwdCtx {
+  Plan* p;
+  const float* params;
+  float* gs;  // staging arena
+  cudaStream_t st, st2;
+  int overlap;
+  int dense_count, other_count;
+  size_t tmp_stride;
+};
+
+long wgrad_px_per_cta(long npx, long want_runs, int* nruns) {
+  const long chunks = (npx + 63) / 64;
+  const long runs = std::max(1L, std::min(want_runs, chunks));
+  const long cpr = (chunks + runs - 1) / runs;
+  *nruns = (int)((chunks + cpr - 1) / cpr);
+  return cpr * 64;
 }
 
-extern "C" int rl_backward(rl_plan* h, const float* params, const float* x, float* grads, void* stream) {
+int wgrad_runs(const Plan* p, long npx, int nmb, int nparts, long* px_per_cta, int ctas_per_sm = 2) {
+  int nruns;
+  *px_per_cta = wgrad_px_per_cta(npx, std::max(1L, (long)(ctas_per_sm * p->sm_count) / std::max(1, nmb * nparts)), &nruns);
+  return nruns;
+}
+
+// fork / join helpers for a weight gradient that reads scratch buffer q on the side stream
+int before_dz(BwdCtx& c, int q) {
+  if (c.overlap && c.p->ev_wg_used[q]) RL_CUDA(cudaStreamWaitEvent(c.st, (cudaEvent_t)c.p->ev_wg[q], 0));  // buffer q free again
+  return RL_OK;
+}
+int after_dz(BwdCtx& c, int q) {
+  if (c.overlap) {
+    RL_CUDA(cudaEventRecord((cudaEvent_t)c.p->ev_dz[q], c.st));
+    RL_CUDA(cudaStreamWaitEvent(c.st2, (cudaEvent_t)c.p->ev_dz[q], 0));
+  }
+  return RL_OK;
+}
+int after_wg(BwdCtx& c, int q) {
+  if (c.overlap) {
+    RL_CUDA(cudaEventRecord((cudaEvent_t)c.p->ev_wg[q], c.st2));
+    c.p->ev_wg_used[q] = true;
+  }
+  return RL_OK;
+}
+// the padded dz16 planes of a level are about to be rewritten: every side-stream reader of them must be done
+int before_level_planes(BwdCtx& c, int lvl) {
+  if (!c.overlap) return RL_OK;
+  if (c.p->ev_blk_used[lvl]) RL_CUDA(cudaStreamWaitEvent(c.st, (cudaEvent_t)c.p->ev_blk[lvl], 0));
+  for (int q = 0; q < 2; ++q)
+    if (c.p->ev_wg_used[q]) RL_CUDA(cudaStreamWaitEvent(c.st, (cudaEvent_t)c.p->ev_wg[q], 0));
+  return RL_OK;
+}
+
+void fill_dz_common(const BwdCtx& c, const Layer& L, DzArgs& z) {
+  const Plan* p = c.p;
+  const Level& lout = p->lv[L.lvl_out];
+  memset(&z, 0, sizeof(z));
+  z.act = act_of(p, L.lvl_out);
+  z.dact = dact_of(p, L.lvl_out);
+  z.stats = stats_of(p, L.lvl_out);
+  z.acc = acc_of(p, L.lvl_out);
+  z.Ct = lout.Ct;
+  z.c_off = L.out_off;
+  z.nch = L.cout;
+  z.npx_out = lout.px;
+  z.inv_n_out = 1.0 / (double)lout.px;
+  z.HW_out = lout.H * lout.W;
+  z.g_bias = c.gs + L.p_b;
+  z.B = p->B;
+}
+
+// dz of a DenseLayer into plane buffer q of its level
+int dense_dz(BwdCtx& c, const Layer& L, int q, DzArgs& z) {
+  const Plan* p = c.p;
+  const Level& lin = p->lv[L.lvl_in];
+  fill_dz_common(c, L, z);
+  z.xp = xp_of(p, L.lvl_out);
+  z.kind = 0;
+  z.mask = (const float*)(wsb(p) + L.mask_off);
+  z.planes = 1;
+  z.dz = (__nv_bfloat16*)(wsb(p) + lin.dzp_off + (size_t)q * lin.dzp_npos * 32);
+  z.dz_npos = lin.dzp_npos;
+  z.dz_guard = lin.dzp_guard;
+  z.H = lin.H;
+  z.W = lin.W;
+  return launch_dz_prepare(z, p->sm_count, c.st);
+}
+
+// input gradient of a DenseLayer for arena channels [c_lo, c_lo + nch) (per-layer kernel)
+int dense_dgrad(BwdCtx& c, const Layer& L, const __nv_bfloat16* dz, const uint8_t* wpk, int c_lo, int nch, int rmw_from,
+                bool param_grads) {
+  const Plan* p = c.p;
+  const Level& lin = p->lv[L.lvl_in];
+  const int sm = p->sm_count;
+  DgradArgs d;
+  memset(&d, 0, sizeof(d));
+  d.dense = 1;
+  d.dz = dz;
+  d.dz_npos = lin.dzp_npos;
+  d.dz_guard = lin.dzp_guard;
+  d.Kdz = 16;
+  d.npx = lin.px;
+  d.xp = xp_of(p, L.lvl_in);
+  d.wpk = wpk;
+  d.act = act_of(p, L.lvl_in);
+  d.dact = dact_of(p, L.lvl_in);
+  d.Ct = lin.Ct;
+  d.Cin = nch;
+  d.c_lo = c_lo;
+  d.H = lin.H;
+  d.W = lin.W;
+  d.B = p->B;
+  d.rmw_from = rmw_from;
+  d.bn = make_bn(p, L, c.params, nullptr, 1);
+  d.g_gamma = param_grads ? c.gs + L.p_gamma : nullptr;
+  d.g_beta = param_grads ? c.gs + L.p_beta : nullptr;
+  d.acc = acc_of(p, L.lvl_in);
+  d.strip_w = 160;
+  d.nstrips = (lin.W + d.strip_w - 1) / d.strip_w;
+  const int vrows = p->B * (lin.H + 1);
+  // small levels run their channel blocks in parallel CTAs (launch_dgrad splits over grid.y): keep one wave in total
+  const int nmb_d = (nch + 127) / 128;
+  const bool split = nmb_d > 1 && (long)vrows * (lin.W + 2) <= 40000;
+  int nruns = std::max(1, std::min(vrows, (3 * sm) / (d.nstrips * (split ? nmb_d : 1))));
+  d.vrows_per_cta = (vrows + nruns - 1) / nruns;
+  nruns = (vrows + d.vrows_per_cta - 1) / d.vrows_per_cta;
+  return launch_dgrad(d, nruns * d.nstrips, c.st);
+}
+
+int head_wgrad(BwdCtx& c) {  // classifier weight gradient: dW[k, c] = sum_p dl[p, k] * f[p, c]
+  Plan* p = c.p;
+  WgradArgs w;
+  memset(&w, 0, sizeof(w));
+  w.kind = WG_HEAD;
+  w.A = act_of(p, 0);
+  w.Axp = xp_of(p, 0);
+  w.lda = p->lv[0].Ct;
+  w.a_off = 0;
+  w.Ca = 288;
+  w.transform = 0;
+  w.Bm = (const __nv_bfloat16*)(wsb(p) + p->dl_off);
+  w.ldb = 16;
+  w.N = 16;
+  w.part_n0[0] = 0;
+  w.part_np[0] = 16;
+  w.npx = p->lv[0].px;
+  w.H = p->H;
+  w.W = p->W;
+  w.gw = c.gs + p->p_cls_w;
+  w.Cin_w = 288;
+  w.num_cls = p->num_cls;
+  int nruns = wgrad_runs(p, w.npx, 3, 1, &w.px_per_cta);
+  return launch_wgrad(w, nruns, 3, 1, c.st);
+}
+
+// one layer through the per-layer kernels (TransitionDown / TransitionUp / first conv always; DenseLayers when the
+// block-fused path is off or not applicable)
+int backward_layer(BwdCtx& c, int li) {
+  Plan* p = c.p;
+  const Layer& L = p->layers[li];
+  const Level& lin = p->lv[L.lvl_in];
+  const Level& lout = p->lv[L.lvl_out];
+  const int sm = p->sm_count;
+  int rc;
+  if (L.type == L_DENSE) {
+    const int q = c.dense_count++ & 1;  // dz plane buffer of this layer
+    if (c.overlap && p->ev_blk_used[L.lvl_in]) {
+      RL_CUDA(cudaStreamWaitEvent(c.st, (cudaEvent_t)p->ev_blk[L.lvl_in], 0));
+      p->ev_blk_used[L.lvl_in] = false;
+    }
+    if ((rc = before_dz(c, q))) return rc;
+    DzArgs z;
+    if ((rc = dense_dz(c, L, q, z))) return rc;
+    if ((rc = after_dz(c, q))) return rc;
+    if ((rc = dense_dgrad(c, L, z.dz, wsb(p) + L.wpk_bwd, 0, L.cin, L.rmw_from, true))) return rc;
+    WgradArgs w;
+    memset(&w, 0, sizeof(w));
+    w.kind = WG_DENSE;
+    w.A = act_of(p, L.lvl_in);
+    w.Axp = xp_of(p, L.lvl_in);
+    w.lda = lin.Ct;
+    w.Ca = L.cin;
+    w.transform = 1;
+    w.bn = make_bn(p, L, c.params, nullptr, 1);
+    w.Bm = z.dz;
+    w.dz_npos = lin.dzp_npos;
+    w.dz_guard = lin.dzp_guard;
+    w.ldb = 16;
+    w.N = 144;
+    w.part_n0[0] = 0;
+    w.part_np[0] = 144;
+    w.npx = lin.px;
+    w.H = lin.H;
+    w.W = lin.W;
+    w.gw = c.gs + L.p_w;
+    w.Cin_w = L.cin;
+    w.cs_perm = L.cs_perm;
+    const int nmb = (L.cin + 127) / 128;
+    int wr = wgrad_runs(p, w.npx, nmb, 1, &w.px_per_cta, 2);
+    if ((rc = launch_wgrad(w, wr, nmb, 1, c.st2))) return rc;
+    return after_wg(c, q);
+  }
+  const int tq = 2 + (c.other_count++ & 1);
+  __nv_bfloat16* tmp = (__nv_bfloat16*)(wsb(p) + p->tmp_off + (size_t)(tq - 2) * c.tmp_stride);
+  DzArgs z;
+  fill_dz_common(c, L, z);
+  z.dz = tmp;
+  if (L.type == L_TD) {
+    z.kind = 1;
+    z.mask = (const float*)(wsb(p) + L.mask_off);
+    z.amax = wsb(p) + L.amax_off;
+    z.H = lin.H;
+    z.W = lin.W;
+    z.Hp = lout.H;
+    z.Wp = lout.W;
+    if ((rc = before_dz(c, tq))) return rc;
+    if ((rc = launch_dz_prepare(z, sm, c.st))) return rc;
+    if ((rc = after_dz(c, tq))) return rc;
+    DgradArgs d;
+    memset(&d, 0, sizeof(d));
+    d.dense = 0;
+    d.npx = lin.px;
+    d.xp = xp_of(p, L.lvl_in);
+    d.dz = tmp;
+    d.Kdz = L.cout;
+    d.wpk = wsb(p) + L.wpk_bwd;
+    d.act = act_of(p, L.lvl_in);
+    d.dact = dact_of(p, L.lvl_in);
+    d.Ct = lin.Ct;
+    d.Cin = L.cin;
+    d.H = lin.H;
+    d.W = lin.W;
+    d.B = p->B;
+    d.rmw_from = L.rmw_from;
+    d.bn = make_bn(p, L, c.params, nullptr, 1);
+    d.g_gamma = c.gs + L.p_gamma;
+    d.g_beta = c.gs + L.p_beta;
+    d.acc = acc_of(p, L.lvl_in);
+    d.ntiles = (lin.px + 127) / 128;
+    int grid = (int)std::max(1L, std::min(d.ntiles, (long)3 * sm));
+    if ((rc = launch_dgrad(d, grid, c.st))) return rc;
+    WgradArgs w;
+    memset(&w, 0, sizeof(w));
+    w.kind = WG_TD;
+    w.A = act_of(p, L.lvl_in);
+    w.Axp = xp_of(p, L.lvl_in);
+    w.lda = lin.Ct;
+    w.Ca = L.cin;
+    w.transform = 1;
+    w.bn = d.bn;
+    w.Bm = tmp;
+    w.ldb = L.cout;
+    w.N = L.cout;
+    int nparts = td_parts(L.cout, w.part_n0, w.part_np);
+    w.npx = lin.px;
+    w.H = lin.H;
+    w.W = lin.W;
+    w.gw = c.gs + L.p_w;
+    w.Cin_w = L.cin;
+    const int nmb = (L.cin + 127) / 128;
+    int wr = wgrad_runs(p, w.npx, nmb, nparts, &w.px_per_cta);
+    if ((rc = launch_wgrad(w, wr, nmb, nparts, c.st2))) return rc;
+    return after_wg(c, tq);
+  }
+  if (L.type == L_TU) {
+    z.kind = 2;
+    z.H = lout.H;
+    z.W = lout.W;
+    z.Hp = lin.H;
+    z.Wp = lin.W;
+    if ((rc = before_dz(c, tq))) return rc;
+    if ((rc = launch_dz_prepare(z, sm, c.st))) return rc;
+    if ((rc = after_dz(c, tq))) return rc;
+    GemmPxArgs a;
+    memset(&a, 0, sizeof(a));
+    a.A = tmp;
+    a.lda = 720;
+    a.a_off = 0;
+    a.K = 720;
+    a.M = lin.px;
+    a.ntiles = (lin.px + 127) / 128;
+    a.mode = GEMM_LINEAR;
+    a.transform = 0;
+    a.wpk = wsb(p) + L.wpk_bwd;
+    a.N = kUpCh;
+    a.part_n0[0] = 0;
+    a.part_np[0] = kUpCh;
+    a.out = dact_of(p, L.lvl_in);
+    a.ldo = lin.Ct;
+    a.o_off = L.in_off;
+    a.out_planar_npx = lin.px;
+    int gx = (int)std::max(1L, std::min(a.ntiles, (long)3 * sm));  // N = 80: three CTAs per SM
+    if ((rc = launch_gemm_px(a, gx, 1, c.st))) return rc;
+    WgradArgs w;
+    memset(&w, 0, sizeof(w));
+    w.kind = WG_TU;
+    w.A = act_of(p, L.lvl_in);
+    w.Axp = xp_of(p, L.lvl_in);
+    w.lda = lin.Ct;
+    w.a_off = L.in_off;
+    w.Ca = kUpCh;
+    w.transform = 0;
+    w.Bm = tmp;
+    w.ldb = 720;
+    w.N = 720;
+    for (int q = 0; q < 3; ++q) {
+      w.part_n0[q] = q * 240;
+      w.part_np[q] = 240;
+    }
+    w.npx = lin.px;
+    w.H = lin.H;
+    w.W = lin.W;
+    w.gw = c.gs + L.p_w;
+    int wr = wgrad_runs(p, w.npx, 1, 3, &w.px_per_cta);
+    if ((rc = launch_wgrad(w, wr, 1, 3, c.st2))) return rc;
+    return after_wg(c, tq);
+  }
+  // L_FIRST: weight gradient only (the image needs no gradient)
+  z.kind = 0;
+  if ((rc = before_dz(c, tq))) return rc;
+  if ((rc = launch_dz_prepare(z, sm, c.st))) return rc;
+  WgradArgs w;
+  memset(&w, 0, sizeof(w));
+  w.kind = 4;  // WG_FIRST
+  w.A = (const __nv_bfloat16*)(wsb(p) + p->xcol_off);
+  w.lda = 32;
+  w.Ca = 27;
+  w.transform = 0;
+  w.Bm = tmp;
+  w.ldb = kFirst;
+  w.N = kFirst;
+  w.part_n0[0] = 0;
+  w.part_np[0] = kFirst;
+  w.npx = lout.px;
+  w.H = lout.H;
+  w.W = lout.W;
+  w.gw = c.gs + L.p_w;
+  int wr = wgrad_runs(p, w.npx, 1, 1, &w.px_per_cta);
+  return launch_wgrad(w, wr, 1, 1, c.st);
+}
+
+bool block_fusable(const Plan* p, const Block& b) {
+  return p->opt_bwd_fused && p->opt_xp && p->lv[b.lvl].W + 2 <= 165;
+}
+
+// a whole DenseBlock: chain over the block's own new channels, one fused kernel for the block input, one batched
+// weight-gradient launch (side stream)
+int backward_block(BwdCtx& c, int bi) {
+  Plan* p = c.p;
+  const Block& b = p->blocks[bi];
+  const Level& lv = p->lv[b.lvl];
+  const int sm = p->sm_count;
+  int rc;
+  if ((rc = before_level_planes(c, b.lvl))) return rc;
+  const __nv_bfloat16* dzbuf[kBlockLayers];
+  for (int j = kBlockLayers - 1; j >= 0; --j) {
+    const Layer& L = p->layers[b.first + j];
+    DzArgs z;
+    if ((rc = dense_dz(c, L, j, z))) return rc;
+    dzbuf[j] = z.dz;
+    if (j > 0 && (rc = dense_dgrad(c, L, z.dz, wsb(p) + L.wpk_chain, b.C0, kGrowth * j, 0, false))) return rc;
+  }
+  // ---- weight gradients + BatchNorm parameter gradients of the five layers (side stream; off the critical path)
+  if (c.overlap) {
+    RL_CUDA(cudaEventRecord((cudaEvent_t)p->ev_dz[0], c.st));
+    RL_CUDA(cudaStreamWaitEvent(c.st2, (cudaEvent_t)p->ev_dz[0], 0));
+  }
+  {
+    WgDenseArgs w;
+    memset(&w, 0, sizeof(w));
+    w.nl = kBlockLayers;
+    int groups_total = 0, groups_max = 0;
+    for (int j = 0; j < kBlockLayers; ++j) {
+      const Layer& L = p->layers[b.first + j];
+      WgDenseLayer& wl = w.L[j];
+      wl.wpk_bwd = wsb(p) + L.wpk_bwd;
+      wl.gamma = c.params + L.p_gamma;
+      wl.beta = c.params + L.p_beta;
+      wl.g_gamma = c.gs + L.p_gamma;
+      wl.g_beta = c.gs + L.p_beta;
+      wl.gw = c.gs + L.p_w;
+      wl.dz = dzbuf[j];
+      wl.Cin = L.cin;
+      wl.cs_perm = L.cs_perm;
+      const int g = ((L.cin + 63) / 64 + 2) / 3;
+      groups_total += g;
+      groups_max = std::max(groups_max, g);
+    }
+    w.xp = xp_of(p, b.lvl);
+    w.npx = lv.px;
+    w.H = lv.H;
+    w.W = lv.W;
+    w.dz_npos = lv.dzp_npos;
+    w.dz_guard = lv.dzp_guard;
+    w.stats = stats_of(p, b.lvl);
+    w.Ct = lv.Ct;
+    w.inv_n = 1.0 / (double)lv.px;
+    int nruns;
+    w.px_per_cta = wgrad_px_per_cta(lv.px, std::max(1, sm / std::max(1, groups_total)), &nruns);
+    if ((rc = launch_wgrad_dense2(w, nruns, groups_max, c.st2))) return rc;
+  }
+  if (c.overlap) {
+    RL_CUDA(cudaEventRecord((cudaEvent_t)p->ev_blk[b.lvl], c.st2));
+    p->ev_blk_used[b.lvl] = true;
+  }
+  // ---- block-input gradient of all five layers
+  DgradBulkArgs g;
+  memset(&g, 0, sizeof(g));
+  g.nl = kBlockLayers;
+  for (int j = 0; j < kBlockLayers; ++j) {
+    const Layer& L = p->layers[b.first + j];
+    g.dz[j] = dzbuf[j];
+    g.wpk[j] = wsb(p) + L.wpk_bulk;
+    g.gamma[j] = c.params + L.p_gamma;
+    g.beta[j] = c.params + L.p_beta;
+  }
+  g.stats = stats_of(p, b.lvl);
+  g.inv_n = 1.0 / (double)lv.px;
+  g.Ct = lv.Ct;
+  g.cs_perm = p->layers[b.first].cs_perm;
+  g.dz_npos = lv.dzp_npos;
+  g.dz_guard = lv.dzp_guard;
+  g.xp = xp_of(p, b.lvl);
+  g.dact = dact_of(p, b.lvl);
+  g.npx = lv.px;
+  g.C0 = b.C0;
+  g.cbs = b.cbs;
+  g.H = lv.H;
+  g.W = lv.W;
+  g.B = p->B;
+  g.rmw = b.rmw;
+  g.acc = acc_of(p, b.lvl);
+  const int vrows = p->B * (lv.H + 1);
+  int nruns = std::max(1, std::min(vrows, (2 * sm) / b.ncb));
+  g.vrows_per_cta = (vrows + nruns - 1) / nruns;
+  nruns = (vrows + g.vrows_per_cta - 1) / g.vrows_per_cta;
+  return launch_dgrad_bulk(g, nruns, b.ncb, c.st);
+}
+
+int backward_range(Plan* p, const float* params, int layer_hi, int layer_lo, cudaStream_t st) {
+  const int n = (int)p->layers.size();
+  BwdCtx c;
+  c.p = p;
+  c.params = params;
+  c.gs = gstage_of(p);
+  c.st = st;
+  c.overlap = p->opt_overlap;
+  c.st2 = c.overlap ? (cudaStream_t)p->side_stream : st;
+  c.dense_count = c.other_count = 0;
+  c.tmp_stride = (p->tmp_bytes + 1023) / 1024 * 1024;
+  for (int i = 0; i < 4; ++i) p->ev_wg_used[i] = false;
+  for (int i = 0; i < kLevels; ++i) p->ev_blk_used[i] = false;
+  int rc;
+  int li = layer_hi;
+  if (li == n) {
+    if ((rc = head_wgrad(c))) return rc;
+    --li;
+  }
+  while (li >= layer_lo) {
+    const Layer& L = p->layers[li];
+    if (L.type == L_DENSE && L.jblk == kBlockLayers - 1 && li - (kBlockLayers - 1) >= layer_lo && block_fusable(p, p->blocks[L.blk])) {
+      if ((rc = backward_block(c, L.blk))) return rc;
+      li -= kBlockLayers;
+    } else {
+      if ((rc = backward_layer(c, li))) return rc;
+      --li;
+    }
+  }
+  if (c.overlap) {  // join: every weight gradient is complete before the caller's stream continues
+    for (int q = 0; q < 4; ++q)
+      if (p->ev_wg_used[q]) RL_CUDA(cudaStreamWaitEvent(st, (cudaEvent_t)p->ev_wg[q], 0));
+    for (int l = 0; l < kLevels; ++l)
+      if (p->ev_blk_used[l]) RL_CUDA(cudaStreamWaitEvent(st, (cudaEvent_t)p->ev_blk[l], 0));
+  }
+  return RL_OK;
+}
+
+}  // namespace
+
+extern "C" int rl_backward_range(rl_plan* h, const float* params, int layer_hi, int layer_lo, void* stream) {
+  if (!h || !h->p.ws) return rl_fail(RL_ERR_STATE, "rl_backward: plan not bound");
+  Plan* p = &h->p;
+  if (!p->training) return rl_fail(RL_ERR_STATE, "rl_backward: plan was created without training arenas");
+  if (!params) return rl_fail(RL_ERR_ARG, "rl_backward: null argument");
+  const int n = (int)p->layers.size();
+  if (layer_lo < 0 || layer_hi > n || layer_lo > layer_hi) return rl_fail(RL_ERR_ARG, "rl_backward_range: bad layer range");
+  return backward_range(p, params, layer_hi, layer_lo, (cudaStream_t)stream);
+}
+
+extern "C" int rl_backward(rl_plan* h, const float* params, float* grads, float grad_scale, const float* grad_scale_dev,
+                           void* stream) {
   if (!h || !h->p.ws) return rl_fail(RL_ERR_STATE, "rl_backward: plan not bound");
   Plan* p = &h->p;
   if (!p->training) return rl_fail(RL_ERR_STATE, "rl_backward: plan was created without training arenas");
   if (!params || !grads) return rl_fail(RL_ERR_ARG, "rl_backward: null argument");
-  (void)x;
   cudaStream_t st = (cudaStream_t)stream;
-  const int sm = p->sm_count;
-  int rc;
   RL_CUDA(cudaMemsetAsync(wsb(p) + p->acc_off_all, 0, p->acc_bytes, st));
-  __nv_bfloat16* tmp = (__nv_bfloat16*)(wsb(p) + p->tmp_off);
-  // DenseLayer weight gradients run on a side stream, concurrently with the dz_prepare -> dgrad chain of the following
-  // layers (they only share read-only inputs); RL_OVERLAP=0 keeps everything on the caller's stream.
-  if (g_overlap < 0) {
-    const char* e = getenv("RL_OVERLAP");
-    g_overlap = (e && e[0] == '0') ? 0 : 1;
-  }
-  const int overlap = g_overlap;
-  cudaStream_t st2 = overlap ? (cudaStream_t)p->side_stream : st;
-  // CTAs per SM the two concurrent kernels are sized for (tuning knobs; co-residency: 2 x 56 KB + 1 x 105 KB of smem)
-  static int dg_ctas = -1, wg_ctas = -1;
-  if (dg_ctas < 0) {
-    const char* e = getenv("RL_DG_CTAS");
-    dg_ctas = e ? atoi(e) : 3;
-    e = getenv("RL_WG_CTAS");
-    wg_ctas = e ? atoi(e) : 2;
-  }
-  int dense_count = 0, other_count = 0;
-  for (int i = 0; i < 4; ++i) p->ev_wg_used[i] = false;
-  const size_t tmp_stride = (p->tmp_bytes + 1023) / 1024 * 1024;
-  // fork / join helpers for a weight gradient that reads dz buffer q on the side stream
-  auto before_dz = [&](int q) -> int {
-    if (overlap && p->ev_wg_used[q]) RL_CUDA(cudaStreamWaitEvent(st, (cudaEvent_t)p->ev_wg[q], 0));  // buffer q free again
-    return RL_OK;
-  };
-  auto after_dz = [&](int q) -> int {
-    if (overlap) {
-      RL_CUDA(cudaEventRecord((cudaEvent_t)p->ev_dz[q], st));
-      RL_CUDA(cudaStreamWaitEvent(st2, (cudaEvent_t)p->ev_dz[q], 0));
-    }
-    return RL_OK;
-  };
-  auto after_wg = [&](int q) -> int {
-    if (overlap) {
-      RL_CUDA(cudaEventRecord((cudaEvent_t)p->ev_wg[q], st2));
-      p->ev_wg_used[q] = true;
-    }
-    return RL_OK;
-  };
-  {  // classifier weight gradient: dW[k, c] = sum_p dl[p, k] * f[p, c]
-    WgradArgs w;
-    memset(&w, 0, sizeof(w));
-    w.kind = WG_HEAD;
-    w.A = act_of(p, 0);
-    w.Axp = xp_of(p, 0);
-    w.lda = p->lv[0].Ct;
-    w.a_off = 0;
-    w.Ca = 288;
-    w.transform = 0;
-    w.Bm = (const __nv_bfloat16*)(wsb(p) + p->dl_off);
-    w.ldb = 16;
-    w.N = 16;
-    w.part_n0[0] = 0;
-    w.part_np[0] = 16;
-    w.npx = p->lv[0].px;
-    w.H = p->H;
-    w.W = p->W;
-    w.gw = grads + p->p_cls_w;
-    w.Cin_w = 288;
-    w.num_cls = p->num_cls;
-    int nruns = wgrad_runs(p, w.npx, 3, 1, &w.px_per_cta);
-    if ((rc = launch_wgrad(w, nruns, 3, 1, st))) return rc;
-  }
-  for (int li = (int)p->layers.size() - 1; li >= 0; --li) {
-    const Layer& L = p->layers[li];
-    const Level& lin = p->lv[L.lvl_in];
-    const Level& lout = p->lv[L.lvl_out];
-    DzArgs z;
-    memset(&z, 0, sizeof(z));
-    z.act = act_of(p, L.lvl_out);
-    z.dact = dact_of(p, L.lvl_out);
-    z.stats = stats_of(p, L.lvl_out);
-    z.acc = acc_of(p, L.lvl_out);
-    z.Ct = lout.Ct;
-    z.c_off = L.out_off;
-    z.nch = L.cout;
-    z.npx_out = lout.px;
-    z.inv_n_out = 1.0 / (double)lout.px;
-    z.HW_out = lout.H * lout.W;
-    int tq = 2;
-    if (L.type != L_DENSE) {
-      tq = 2 + (other_count++ & 1);
-      tmp = (__nv_bfloat16*)(wsb(p) + p->tmp_off + (size_t)(tq - 2) * tmp_stride);
-    }
-    z.dz = tmp;
-    z.g_bias = grads + L.p_b;
-    z.B = p->B;
-    // only the one-thread-per-pixel DenseLayer kernel reads x from the planar mirror; the chunk-per-thread TD / TU / first
-    // conv kernels are coalesced on the NHWC arena
-    z.xp = L.type == L_DENSE ? xp_of(p, L.lvl_out) : nullptr;
-    if (L.type == L_DENSE) {
-      z.kind = 0;
-      z.mask = (const float*)(wsb(p) + L.mask_off);
-      const int q = dense_count++ & 1;  // dz buffer of this layer
-      z.planes = 1;
-      z.dz = (__nv_bfloat16*)(wsb(p) + lin.dzp_off + (size_t)q * lin.dzp_npos * 32);
-      z.dz_npos = lin.dzp_npos;
-      z.dz_guard = lin.dzp_guard;
-      z.H = lin.H;
-      z.W = lin.W;
-      if ((rc = before_dz(q))) return rc;
-      if ((rc = launch_dz_prepare(z, sm, st))) return rc;
-      if ((rc = after_dz(q))) return rc;
-      DgradArgs d;
-      memset(&d, 0, sizeof(d));
-      d.dense = 1;
-      d.dz = z.dz;
-      d.dz_npos = lin.dzp_npos;
-      d.dz_guard = lin.dzp_guard;
-      d.Kdz = 16;
-      d.npx = lin.px;
-      d.xp = xp_of(p, L.lvl_in);
-      d.wpk = wsb(p) + L.wpk_bwd;
-      d.act = act_of(p, L.lvl_in);
-      d.dact = dact_of(p, L.lvl_in);
-      d.Ct = lin.Ct;
-      d.Cin = L.cin;
-      d.H = lin.H;
-      d.W = lin.W;
-      d.B = p->B;
-      d.rmw_from = L.rmw_from;
-      d.bn = make_bn(p, L, params, nullptr, 1);
-      d.g_gamma = grads + L.p_gamma;
-      d.g_beta = grads + L.p_beta;
-      d.acc = acc_of(p, L.lvl_in);
-      d.strip_w = 160;
-      d.nstrips = (lin.W + d.strip_w - 1) / d.strip_w;
-      const int vrows = p->B * (lin.H + 1);
-      // small levels run their channel blocks in parallel CTAs (launch_dgrad splits over grid.y): keep one wave in total
-      const int nmb_d = (L.cin + 127) / 128;
-      const bool split = nmb_d > 1 && (long)vrows * (lin.W + 2) <= 40000;
-      int nruns = std::max(1, std::min(vrows, (dg_ctas * sm) / (d.nstrips * (split ? nmb_d : 1))));
-      d.vrows_per_cta = (vrows + nruns - 1) / nruns;
-      nruns = (vrows + d.vrows_per_cta - 1) / d.vrows_per_cta;
-      if ((rc = launch_dgrad(d, nruns * d.nstrips, st))) return rc;
-      WgradArgs w;
-      memset(&w, 0, sizeof(w));
-      w.kind = WG_DENSE;
-      w.A = act_of(p, L.lvl_in);
-      w.Axp = xp_of(p, L.lvl_in);
-      w.lda = lin.Ct;
-      w.Ca = L.cin;
-      w.transform = 1;
-      w.bn = d.bn;
-      w.Bm = z.dz;
-      w.dz_npos = lin.dzp_npos;
-      w.dz_guard = lin.dzp_guard;
-      w.ldb = 16;
-      w.N = 144;
-      w.part_n0[0] = 0;
-      w.part_np[0] = 144;
-      w.npx = lin.px;
-      w.H = lin.H;
-      w.W = lin.W;
-      w.gw = grads + L.p_w;
-      w.Cin_w = L.cin;
-      w.cs_perm = L.cs_perm;
-      const int nmb = (L.cin + 127) / 128;
-      int wr = wgrad_runs(p, w.npx, nmb, 1, &w.px_per_cta, wg_ctas);
-      if ((rc = launch_wgrad(w, wr, nmb, 1, st2))) return rc;
-      if ((rc = after_wg(q))) return rc;
-    } else if (L.type == L_TD) {
-      z.kind = 1;
-      z.mask = (const float*)(wsb(p) + L.mask_off);
-      z.amax = wsb(p) + L.amax_off;
-      z.H = lin.H;
-      z.W = lin.W;
-      z.Hp = lout.H;
-      z.Wp = lout.W;
-      if ((rc = before_dz(tq))) return rc;
-      if ((rc = launch_dz_prepare(z, sm, st))) return rc;
-      if ((rc = after_dz(tq))) return rc;
-      DgradArgs d;
-      memset(&d, 0, sizeof(d));
-      d.dense = 0;
-      d.npx = lin.px;
-      d.xp = xp_of(p, L.lvl_in);
-      d.dz = tmp;
-      d.Kdz = L.cout;
-      d.wpk = wsb(p) + L.wpk_bwd;
-      d.act = act_of(p, L.lvl_in);
-      d.dact = dact_of(p, L.lvl_in);
-      d.Ct = lin.Ct;
-      d.Cin = L.cin;
-      d.H = lin.H;
-      d.W = lin.W;
-      d.B = p->B;
-      d.rmw_from = L.rmw_from;
-      d.bn = make_bn(p, L, params, nullptr, 1);
-      d.g_gamma = grads + L.p_gamma;
-      d.g_beta = grads + L.p_beta;
-      d.acc = acc_of(p, L.lvl_in);
-      d.ntiles = (lin.px + 127) / 128;
-      int grid = (int)std::max(1L, std::min(d.ntiles, (long)3 * sm));
-      if ((rc = launch_dgrad(d, grid, st))) return rc;
-      WgradArgs w;
-      memset(&w, 0, sizeof(w));
-      w.kind = WG_TD;
-      w.A = act_of(p, L.lvl_in);
-      w.Axp = xp_of(p, L.lvl_in);
-      w.lda = lin.Ct;
-      w.Ca = L.cin;
-      w.transform = 1;
-      w.bn = d.bn;
-      w.Bm = tmp;
-      w.ldb = L.cout;
-      w.N = L.cout;
-      int nparts = td_parts(L.cout, w.part_n0, w.part_np);
-      w.npx = lin.px;
-      w.H = lin.H;
-      w.W = lin.W;
-      w.gw = grads + L.p_w;
-      w.Cin_w = L.cin;
-      const int nmb = (L.cin + 127) / 128;
-      int wr = wgrad_runs(p, w.npx, nmb, nparts, &w.px_per_cta);
-      if ((rc = launch_wgrad(w, wr, nmb, nparts, st2))) return rc;
-      if ((rc = after_wg(tq))) return rc;
-    } else if (L.type == L_TU) {
-      z.kind = 2;
-      z.H = lout.H;
-      z.W = lout.W;
-      z.Hp = lin.H;
-      z.Wp = lin.W;
-      if ((rc = before_dz(tq))) return rc;
-      if ((rc = launch_dz_prepare(z, sm, st))) return rc;
-      if ((rc = after_dz(tq))) return rc;
-      GemmPxArgs a;
-      memset(&a, 0, sizeof(a));
-      a.A = tmp;
-      a.lda = 720;
-      a.a_off = 0;
-      a.K = 720;
-      a.M = lin.px;
-      a.ntiles = (lin.px + 127) / 128;
-      a.mode = GEMM_LINEAR;
-      a.transform = 0;
-      a.wpk = wsb(p) + L.wpk_bwd;
-      a.N = kUpCh;
-      a.part_n0[0] = 0;
-      a.part_np[0] = kUpCh;
-      a.out = dact_of(p, L.lvl_in);
-      a.ldo = lin.Ct;
-      a.o_off = L.in_off;
-      a.out_planar_npx = lin.px;
-      int gx = (int)std::max(1L, std::min(a.ntiles, (long)3 * sm));  // N = 80: three CTAs per SM
-      if ((rc = launch_gemm_px(a, gx, 1, st))) return rc;
-      WgradArgs w;
-      memset(&w, 0, sizeof(w));
-      w.kind = WG_TU;
-      w.A = act_of(p, L.lvl_in);
-      w.Axp = xp_of(p, L.lvl_in);
-      w.lda = lin.Ct;
-      w.a_off = L.in_off;
-      w.Ca = kUpCh;
-      w.transform = 0;
-      w.Bm = tmp;
-      w.ldb = 720;
-      w.N = 720;
-      for (int q = 0; q < 3; ++q) {
-        w.part_n0[q] = q * 240;
-        w.part_np[q] = 240;
-      }
-      w.npx = lin.px;
-      w.H = lin.H;
-      w.W = lin.W;
-      w.gw = grads + L.p_w;
-      int wr = wgrad_runs(p, w.npx, 1, 3, &w.px_per_cta);
-      if ((rc = launch_wgrad(w, wr, 1, 3, st2))) return rc;
-      if ((rc = after_wg(tq))) return rc;
-    } else {  // L_FIRST: weight gradient only (the image needs no gradient)
-      z.kind = 0;
-      if ((rc = before_dz(tq))) return rc;
-      if ((rc = launch_dz_prepare(z, sm, st))) return rc;
-      WgradArgs w;
-      memset(&w, 0, sizeof(w));
-      w.kind = 4;  // WG_FIRST
-      w.A = (const __nv_bfloat16*)(wsb(p) + p->xcol_off);
-      w.lda = 32;
-      w.Ca = 27;
-      w.transform = 0;
-      w.Bm = tmp;
-      w.ldb = kFirst;
-      w.N = kFirst;
-      w.part_n0[0] = 0;
-      w.part_np[0] = kFirst;
-      w.npx = lout.px;
-      w.H = lout.H;
-      w.W = lout.W;
-      w.gw = grads + L.p_w;
-      int wr = wgrad_runs(p, w.npx, 1, 1, &w.px_per_cta);
-      if ((rc = launch_wgrad(w, wr, 1, 1, st))) return rc;
-    }
-  }
-  if (overlap)  // join: every weight gradient is complete before the caller's stream continues (optimizer, all-reduce)
-    for (int q = 0; q < 4; ++q)
-      if (p->ev_wg_used[q]) RL_CUDA(cudaStreamWaitEvent(st, (cudaEvent_t)p->ev_wg[q], 0));
-  return RL_OK;
+  int rc = backward_range(p, params, (int)p->layers.size(), 0, st);
+  if (rc) return rc;
+  return launch_grad_accum(grads, gstage_of(p), p->n_params, grad_scale, grad_scale_dev, st);
 }
 
-extern "C" int rl_set_option(const char* name, int value) {
-  if (name && strcmp(name, "overlap") == 0) {
-    g_overlap = value ? 1 : 0;
-    return RL_OK;
-  }
-  if (name && strcmp(name, "xp") == 0) {  // takes effect with the next rl_forward (the mirror is written by the forward pass)
-    g_xp = value != 0;
-    return RL_OK;
-  }
-  if (name && strcmp(name, "fwd_tma") == 0) {
-    g_fwd_tma = value != 0;
-    return RL_OK;
-  }
-  return rl_fail(RL_ERR_ARG, "rl_set_option: unknown option");
+extern "C" int rl_plan_set_option(rl_plan* h, const char* name, int value) {
+  if (!h || !name) return rl_fail(RL_ERR_ARG, "rl_plan_set_option: null argument");
+  Plan& p = h->p;
+  if (strcmp(name, "overlap") == 0) p.opt_overlap = value ? 1 : 0;
+  else if (strcmp(name, "xp") == 0) p.opt_xp = value ? 1 : 0;  // takes effect with the next rl_forward (the mirror is written by the forward pass)
+  else if (strcmp(name, "fwd_tma") == 0) p.opt_fwd_tma = value ? 1 : 0;
+  else if (strcmp(name, "bwd_fused") == 0) p.opt_bwd_fused = value ? 1 : 0;
+  else return rl_fail(RL_ERR_ARG, "rl_plan_set_option: unknown option '%s'", name);
+  return RL_OK;
 }

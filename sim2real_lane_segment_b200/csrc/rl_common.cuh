@@ -15,7 +15,7 @@ int rl_fail(int code, const char* fmt, ...);
 namespace rl {
 // kernel classes for launch counting and the optional per-class CUDA-event timing used by bench.py's roofline
 enum KernelClass { KC_DENSE_FWD = 0, KC_GEMM_PX, KC_DGRAD_DENSE, KC_DGRAD_TD, KC_WGRAD, KC_HEAD, KC_DZ_PREPARE,
-                   KC_STATS, KC_FIRST_FWD, KC_TU_COL2IM, KC_PACK, KC_OPT, KC_MISC, KC_COUNT };
+                   KC_STATS, KC_FIRST_FWD, KC_TU_COL2IM, KC_PACK, KC_OPT, KC_MISC, KC_DGRAD_BULK, KC_WGRAD_DENSE, KC_COUNT };
 struct ProfScope {
   int cls;
   cudaStream_t st;
@@ -23,26 +23,6 @@ struct ProfScope {
   ProfScope(int cls, cudaStream_t st);
   ~ProfScope();
 };
-}  // namespace rl
-
-namespace rl {
-// Programmatic dependent launch: the kernel may start while its stream predecessor is still draining; it must execute
-// pdl_wait() (griddepcontrol.wait) before touching global memory.  Opt-in with RL_PDL=1 (slower on B200 in round 1).
-bool pdl_enabled();
-template <typename... KArgs, typename... Args>
-inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = grid;
-  cfg.blockDim = block;
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = pdl_enabled() ? 1 : 0;
-  return cudaLaunchKernelEx(&cfg, kernel, args...);
-}
 }  // namespace rl
 
 #define RL_CUDA(expr)                                                                                   \

@@ -7,70 +7,22 @@
 // (TMEM lane = thread) is a *channel*: the per-channel BatchNorm-backward sums Σg and Σg·x̂ are then plain
 // per-thread accumulations, and every thread streams one channel column of the NHWC arenas.
 // The 3x3 taps are 9 row-shifted views of one 16-channel halo tile in shared memory (start-address offsets).
-#include <stdlib.h>
-
 #include "rl_common.cuh"
 #include "rl_dev.cuh"
 #include "rl_kernels.h"
 
 namespace rl {
 
-constexpr int kDzRows = 464;
-
-__device__ __forceinline__ void unpack8(uint4 v, float* f) {
-  float2 a = unpack_bf16x2(v.x), b = unpack_bf16x2(v.y), c = unpack_bf16x2(v.z), d = unpack_bf16x2(v.w);
-  f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
-}
-__device__ __forceinline__ uint4 pack8(const float* v) {
-  return make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
-}
-  // halo tile rows: 128 + 2*(strip+2) + 2 <= 464 for strips up to 165 columns
-
 // ------------------------------------------------------------------------------------------------
 // epilogue shared by both dgrad kernels.  Accumulator: rows (TMEM lanes = threads) are PIXELS, columns are the
 // (up to 128) input channels of the current channel block, so every thread streams 32-byte channel groups of its
-// own pixel from the NHWC arenas (x, dX) with 16-byte accesses.  The per-channel BatchNorm-backward sums
+// own pixel from the planar arenas (x mirror, dX).  The per-channel BatchNorm-backward sums
 //   S1_c = Σ_p g[p,c]      S2_c = Σ_p g[p,c]·(x[p,c] - mean_c)          (g = relu-masked input gradient)
-// are reduced across the 32 pixels of a warp with a transposing butterfly (16 shuffles per quantity per 16 channels)
-// and kept in registers across tiles.
+// are reduced across the 32 pixels of a warp with transposing butterflies and kept in registers across tiles.
 // ------------------------------------------------------------------------------------------------
 struct DgradConsts {  // per channel of the current block, in shared memory: {s, t, gamma*rstd, mean}
   float4 k[128];
 };
-
-// Σ over the 32 lanes of v[k] for k = 0..15; lane l ends up holding the total of k = (l >> 1) & 15
-__device__ __forceinline__ float warp_reduce16(float* v, int lane) {
-  {
-    const bool hi = lane & 16;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const float send = hi ? v[i] : v[i + 8], keep = hi ? v[i + 8] : v[i];
-      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
-    }
-  }
-  {
-    const bool hi = lane & 8;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const float send = hi ? v[i] : v[i + 4], keep = hi ? v[i + 4] : v[i];
-      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
-    }
-  }
-  {
-    const bool hi = lane & 4;
-#pragma unroll
-    for (int i = 0; i < 2; ++i) {
-      const float send = hi ? v[i] : v[i + 2], keep = hi ? v[i + 2] : v[i];
-      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
-    }
-  }
-  {
-    const bool hi = lane & 2;
-    const float send = hi ? v[0] : v[1], keep = hi ? v[1] : v[0];
-    v[0] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
-  }
-  return v[0] + __shfl_xor_sync(0xffffffffu, v[0], 1);
-}
 
 // Σ over the 32 lanes of v[k], k = 0..7; every lane ends up with the total of k = (lane >> 2) & 7
 __device__ __forceinline__ float warp_reduce8(float* v, int lane) {
@@ -103,72 +55,32 @@ __device__ __forceinline__ float warp_reduce8(float* v, int lane) {
 struct DgradPre {
   uint4 x0, x1, d0, d1;
 };
-// drow: this pixel's slot in the first 16-channel group plane of the channel block; dgs: elements between group planes
+// xrow / drow_: this pixel's slot in the first 16-channel group plane of the channel block (planar layouts: dgs elements
+// between group planes) or, for xrow with xgs == 0, its NHWC row
 __device__ __forceinline__ void dgrad_prefetch(DgradPre& p, const __nv_bfloat16* xrow, const __nv_bfloat16* drow_, int c0,
-                                               int nvalid, bool rmw, int variant, long dgs, long xgs = 0) {
+                                               int nvalid, bool rmw, long dgs, long xgs) {
   const __nv_bfloat16* drow = drow_ + (long)(c0 >> 4) * dgs - c0;  // so that drow + c0 addresses group c0/16
   if (xgs != 0 && xrow != nullptr) xrow += (long)(c0 >> 4) * xgs - c0;  // planar activation mirror: same addressing
   if (xrow != nullptr && c0 < nvalid) {
-    if (variant & 32) {
-      p.x0 = p.x1 = make_uint4(0x3f803f80u, 0x3f803f80u, 0x3f803f80u, 0x3f803f80u);
-    } else if (variant & 2) {
-      const u32x8 xv = (variant & 1) ? ldg256_nc(xrow + c0) : ldg256_nc_nohint(xrow + c0);
-      p.x0 = xv.lo;
-      p.x1 = xv.hi;
-    } else {
-      p.x0 = ldg128(xrow + c0);
-      p.x1 = ldg128(xrow + c0 + 8);
-    }
-    if (rmw && !(variant & 16)) {
-      if (variant & 2) {
-        const u32x8 dv = (variant & 1) ? ld256(drow + c0) : ld256_nohint(drow + c0);
-        p.d0 = dv.lo;
-        p.d1 = dv.hi;
-      } else {
-        p.d0 = *reinterpret_cast<const uint4*>(drow + c0);
-        p.d1 = *reinterpret_cast<const uint4*>(drow + c0 + 8);
-      }
+    const u32x8 xv = ldg256_nc(xrow + c0);
+    p.x0 = xv.lo;
+    p.x1 = xv.hi;
+    if (rmw) {
+      const u32x8 dv = ld256(drow + c0);
+      p.d0 = dv.lo;
+      p.d1 = dv.hi;
     } else {
       p.d0 = p.d1 = make_uint4(0, 0, 0, 0);
     }
   }
 }
 
-// one 128-pixel tile x one channel block; P = this thread's pixel (or -1); S1/S2: per-thread running totals, index =
-// channel group (16 channels), the lane's channel inside the group is (lane >> 1) & 15.  pre[0..1] hold groups 0 and 1.
-// Cross-pixel sums of a warp (32 pixels) for 8 channels x 2 quantities through a private shared-memory scratch:
-// every lane writes its 8+8 values as a row (stride 12 floats: conflict-free 16-byte stores), then lane
-// (up, q, col) = (lane>>4, (lane>>3)&1, lane&7) adds 16 rows of column col of quantity q and the two row halves are
-// combined with one shuffle.  Returns Σ_pixels quantity q of channel col in every lane.
-constexpr int kScrPerWarp = 800;  // floats: gs matrix [32][12] at 0, gx matrix at 400 (16 banks apart)
-__device__ __forceinline__ float warp_colsum8(float* sc, const float* gs, const float* gx, int lane) {
-  float4* w0 = reinterpret_cast<float4*>(sc + lane * 12);
-  float4* w1 = reinterpret_cast<float4*>(sc + 400 + lane * 12);
-  w0[0] = make_float4(gs[0], gs[1], gs[2], gs[3]);
-  w0[1] = make_float4(gs[4], gs[5], gs[6], gs[7]);
-  w1[0] = make_float4(gx[0], gx[1], gx[2], gx[3]);
-  w1[1] = make_float4(gx[4], gx[5], gx[6], gx[7]);
-  __syncwarp();
-  const int col = lane & 7, q = (lane >> 3) & 1, up = lane >> 4;
-  const float* src = sc + q * 400 + col;
-  float acc = 0.f;
-#pragma unroll
-  for (int r = 0; r < 16; ++r) {
-    const int row = up ? 16 + ((r + 6) & 15) : r;  // rotation keeps the four 8-lane groups on disjoint banks
-    acc += src[row * 12];
-  }
-  acc += __shfl_xor_sync(0xffffffffu, acc, 16);
-  __syncwarp();
-  return acc;
-}
-
-// kSmemSums: cross-pixel sums through a shared-memory scratch or (false, what both kernels use) by shuffle butterflies:
-// the scratch variant's column reads were the hottest lines of the 1x1 kernel and its 12.8 KB cost a resident CTA.
-template <bool kSmemSums>
+// one 128-pixel tile x one channel block; P = this thread's pixel (or -1); S1: per-thread running totals, index =
+// channel group (16 channels): lane (up, q, col) = (lane>>4, (lane>>3)&1, lane&7) keeps quantity q (0: Σg, 1: Σg(x-mean))
+// of channel 8*up + col of the group.  pre[0..1] hold groups 0 and 1.  cbase: arena channel of the block's column 0.
 __device__ __forceinline__ void dgrad_epilogue(uint32_t tmem_acc, int warp, int lane, const __nv_bfloat16* xrow,
                                                __nv_bfloat16* drow, int cbase, int nvalid, const DgradConsts* k,
-                                               const DgradArgs& a, float* S1, float* S2, DgradPre* pre, float* s_scr) {
-  float* sc = kSmemSums ? s_scr + warp * kScrPerWarp : nullptr;
+                                               const DgradArgs& a, float* S1, DgradPre* pre) {
 #pragma unroll
   for (int gi = 0; gi < 8; ++gi) {
     const int c0 = gi * 16;
@@ -176,8 +88,8 @@ __device__ __forceinline__ void dgrad_epilogue(uint32_t tmem_acc, int warp, int 
       float g[16];
       tmem_ld16(tmem_acc + ((uint32_t)(warp * 32) << 16) + c0, g);
       const DgradPre cur = pre[gi & 1];
-      if (gi + 2 < 8) dgrad_prefetch(pre[gi & 1], xrow, drow, c0 + 32, nvalid, (cbase + c0 + 32) >= a.rmw_from, a.variant, 16 * a.npx, a.xp ? 16 * a.npx : 0);
-      // two halves of 8 channels keep the fp32 temporaries small (register budget: 4 CTAs per SM)
+      if (gi + 2 < 8) dgrad_prefetch(pre[gi & 1], xrow, drow, c0 + 32, nvalid, (cbase + c0 + 32) >= a.rmw_from, 16 * a.npx, a.xp ? 16 * a.npx : 0);
+      // two halves of 8 channels keep the fp32 temporaries small (register budget: 3 CTAs per SM)
       uint4 dpk[2];
       float rs[2];
 #pragma unroll
@@ -201,40 +113,23 @@ __device__ __forceinline__ void dgrad_epilogue(uint32_t tmem_acc, int warp, int 
           for (int i = 0; i < 8; ++i) gs[i] = gx[i] = 0.f;
           dpk[h] = make_uint4(0, 0, 0, 0);
         }
-        if (a.variant & 4) {  // triage switch: skip the cross-pixel sums
-          rs[h] = gs[0] + gx[0];
-        } else if (kSmemSums) {
-          rs[h] = warp_colsum8(sc, gs, gx, lane);
-        } else {
-          // butterflies: lane ends with the total of column (lane >> 2) & 7; lanes with bit 3 of... keep both quantities
-          const float r1 = warp_reduce8(gs, lane), r2 = warp_reduce8(gx, lane);
-          // re-distribute to the (up, q, col) convention of the scratch variant: col = lane & 7, q = (lane >> 3) & 1
-          const int src = (lane & 7) << 2;  // a lane that holds column (lane & 7)
-          const float a1 = __shfl_sync(0xffffffffu, r1, src), a2 = __shfl_sync(0xffffffffu, r2, src);
-          rs[h] = ((lane >> 3) & 1) ? a2 : a1;
-        }
+        // butterflies: every lane ends with the total of column (lane >> 2) & 7; re-distribute to the (up, q, col)
+        // convention: col = lane & 7, q = (lane >> 3) & 1
+        const float r1 = warp_reduce8(gs, lane), r2 = warp_reduce8(gx, lane);
+        const int src = (lane & 7) << 2;  // a lane that holds column (lane & 7)
+        const float a1 = __shfl_sync(0xffffffffu, r1, src), a2 = __shfl_sync(0xffffffffu, r2, src);
+        rs[h] = ((lane >> 3) & 1) ? a2 : a1;
       }
-      if (xrow != nullptr && !(a.variant & 8)) {
-        __nv_bfloat16* dg = drow + (long)(c0 >> 4) * 16 * a.npx;
-        if (a.variant & 2) {
-          st256(dg, dpk[0], dpk[1]);
-        } else {
-          *reinterpret_cast<uint4*>(dg) = dpk[0];
-          *reinterpret_cast<uint4*>(dg + 8) = dpk[1];
-        }
-      }
-      // lane (up, q, col) keeps quantity q (0: Σg, 1: Σg(x-mean)) of channel 8*up + col of this group
+      if (xrow != nullptr) st256(drow + (long)(c0 >> 4) * 16 * a.npx, dpk[0], dpk[1]);
       S1[gi] += (lane & 16) ? rs[1] : rs[0];
     }
   }
-  (void)S2;
 }
 
 __device__ __forceinline__ void dgrad_consts_init(DgradConsts* k, float* s_rstd, const DgradArgs& a, int mb) {
-  const int c = mb * 128 + threadIdx.x;
   float s = 0.f, t = 0.f, gr = 0.f, mean = 0.f, rstd = 0.f;
-  if (c < a.Cin) {
-    BnCoef b = bn_coef(a.bn, c);
+  if (mb * 128 + (int)threadIdx.x < a.Cin) {
+    BnCoef b = bn_coef(a.bn, a.c_lo + mb * 128 + threadIdx.x);
     s = b.s;
     t = b.t;
     gr = b.gamma * b.rstd;
@@ -246,9 +141,8 @@ __device__ __forceinline__ void dgrad_consts_init(DgradConsts* k, float* s_rstd,
 }
 
 // block totals -> gradient slots: dβ = S1, dγ = rstd·S2, and the deferred mean terms A += γ·rstd·S1, B += γ·rstd·(rstd·S2)
-__device__ __forceinline__ void dgrad_flush(float* s_sum /*[2][128]*/, const float* S1, const float* S2, int warp, int lane,
-                                            const DgradConsts* k, const float* s_rstd, const DgradArgs& a, int mb,
-                                            int nvalid) {
+__device__ __forceinline__ void dgrad_flush(float* s_sum /*[2][128]*/, const float* S1, int lane, const DgradConsts* k,
+                                            const float* s_rstd, const DgradArgs& a, int mb, int nvalid) {
   for (int i = threadIdx.x; i < 256; i += 128) s_sum[i] = 0.f;
   __syncthreads();
   {
@@ -259,16 +153,17 @@ __device__ __forceinline__ void dgrad_flush(float* s_sum /*[2][128]*/, const flo
   }
   __syncthreads();
   const int cl = threadIdx.x;
-  if (cl < nvalid && !(a.variant & 64)) {  // (bit 6: triage switch, skip the global accumulation)
-    const int c = mb * 128 + cl;
+  if (cl < nvalid) {
+    const int c = a.c_lo + mb * 128 + cl;
     const float s1 = s_sum[cl], s2 = s_rstd[cl] * s_sum[128 + cl];
-    const int rc = ref_channel(c, a.bn.cs_perm);
-    atomicAdd(a.g_beta + rc, s1);
-    atomicAdd(a.g_gamma + rc, s2);
+    if (a.g_beta != nullptr) {
+      const int rc = ref_channel(c, a.bn.cs_perm);
+      atomicAdd(a.g_beta + rc, s1);
+      atomicAdd(a.g_gamma + rc, s2);
+    }
     atomicAdd(a.acc + c, (double)(k->k[cl].z * s1));
     atomicAdd(a.acc + a.Ct + c, (double)(k->k[cl].z * s2));
   }
-  (void)warp;
 }
 
 // ================================================================================================
@@ -305,8 +200,6 @@ __global__ void __launch_bounds__(128, 3) dgrad_dense_kernel(DgradArgs a) {
     fence_mbar_init();
   }
   if (warp == 0) tmem_alloc(&tmem_base_s, 128);
-  pdl_trigger();
-  pdl_wait();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -348,9 +241,10 @@ __global__ void __launch_bounds__(128, 3) dgrad_dense_kernel(DgradArgs a) {
   for (int mb = mb_lo; mb < mb_hi; ++mb) {
     const int nvalid = min(128, a.Cin - mb * 128);
     const uint32_t idesc = umma_idesc_bf16((uint32_t)nvalid, 0, 0);
-    float S1[8], S2[8];
+    float S1[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) S1[i] = S2[i] = 0.f;
+    for (int i = 0; i < 8; ++i) S1[i] = 0.f;
+    const int cb0 = a.c_lo + mb * 128;  // arena channel of accumulator column 0
     __syncthreads();  // every MMA of the previous block has been waited for: sW / constants / dz buffers may be overwritten
     dgrad_consts_init(kc, s_rstd, a, mb);
     if (tid == 0) {
@@ -369,11 +263,11 @@ __global__ void __launch_bounds__(128, 3) dgrad_dense_kernel(DgradArgs a) {
           if (ri < a.H && xc >= x0 && xc < x1) P = (img * a.H + ri) * a.W + xc;
         }
       }
-      const __nv_bfloat16* xrow = P < 0 ? nullptr : (a.xp ? a.xp + dact_index(a.npx, P, mb * 128) : a.act + (size_t)P * a.Ct + mb * 128);
-      __nv_bfloat16* drow = P >= 0 ? a.dact + dact_index(a.npx, P, mb * 128) : nullptr;
+      const __nv_bfloat16* xrow = P < 0 ? nullptr : (a.xp ? a.xp + dact_index(a.npx, P, cb0) : a.act + (size_t)P * a.Ct + cb0);
+      __nv_bfloat16* drow = P >= 0 ? a.dact + dact_index(a.npx, P, cb0) : nullptr;
       DgradPre pre[2];
-      dgrad_prefetch(pre[0], xrow, drow, 0, nvalid, (mb * 128) >= a.rmw_from, a.variant, 16 * a.npx, a.xp ? 16 * a.npx : 0);
-      dgrad_prefetch(pre[1], xrow, drow, 16, nvalid, (mb * 128 + 16) >= a.rmw_from, a.variant, 16 * a.npx, a.xp ? 16 * a.npx : 0);
+      dgrad_prefetch(pre[0], xrow, drow, 0, nvalid, cb0 >= a.rmw_from, 16 * a.npx, a.xp ? 16 * a.npx : 0);
+      dgrad_prefetch(pre[1], xrow, drow, 16, nvalid, (cb0 + 16) >= a.rmw_from, 16 * a.npx, a.xp ? 16 * a.npx : 0);
       load_dz(tile);           // previous tile's MMAs were waited for before its epilogue: the buffer is free
       fence_proxy_async();
       __syncthreads();         // also: every thread is past the epilogue of tile-1 -> TMEM reusable
@@ -399,12 +293,12 @@ __global__ void __launch_bounds__(128, 3) dgrad_dense_kernel(DgradArgs a) {
       mbar_wait(&bar_mma, n_mma & 1);
       ++n_mma;
       tc_fence_after();
-      dgrad_epilogue<false>(tmem, warp, lane, xrow, drow, mb * 128, nvalid, kc, a, S1, S2, pre, nullptr);
+      dgrad_epilogue(tmem, warp, lane, xrow, drow, cb0, nvalid, kc, a, S1, pre);
       tc_fence_before();
     }
     if (ntiles == 0 && tid == 0) mbar_wait(&bar_w, n_w & 1);
     ++n_w;
-    dgrad_flush(s_sum, S1, S2, warp, lane, kc, s_rstd, a, mb, nvalid);
+    dgrad_flush(s_sum, S1, lane, kc, s_rstd, a, mb, nvalid);
   }
   tc_fence_before();
   __syncthreads();
@@ -420,7 +314,6 @@ __global__ void __launch_bounds__(128, 3) dgrad_td_kernel(DgradArgs a) {
   DgradConsts* kcs = reinterpret_cast<DgradConsts*>(smem + 2 * 32768);
   float* s_rstd = reinterpret_cast<float*>(kcs + 1);
   float* s_sum = s_rstd + 128;
-  float* s_scr = s_sum + 256;
   __shared__ uint64_t bar_full[2], bar_done[2];
   __shared__ uint32_t tmem_base_s;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -436,8 +329,6 @@ __global__ void __launch_bounds__(128, 3) dgrad_td_kernel(DgradArgs a) {
     fence_mbar_init();
   }
   if (warp == 0) tmem_alloc(&tmem_base_s, 128);
-  pdl_trigger();
-  pdl_wait();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -449,9 +340,9 @@ __global__ void __launch_bounds__(128, 3) dgrad_td_kernel(DgradArgs a) {
   for (int mb = 0; mb < nmb; ++mb) {
     const int nvalid = min(128, a.Cin - mb * 128);
     const uint32_t idesc = umma_idesc_bf16((uint32_t)nvalid, 0, 0);
-    float S1[8], S2[8];
+    float S1[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) S1[i] = S2[i] = 0.f;
+    for (int i = 0; i < 8; ++i) S1[i] = 0.f;
     __syncthreads();
     dgrad_consts_init(kcs, s_rstd, a, mb);
     __syncthreads();
@@ -466,8 +357,8 @@ __global__ void __launch_bounds__(128, 3) dgrad_td_kernel(DgradArgs a) {
       const __nv_bfloat16* xrow = P < 0 ? nullptr : (a.xp ? a.xp + dact_index(a.npx, P, mb * 128) : a.act + (size_t)P * a.Ct + mb * 128);
       __nv_bfloat16* drow = P >= 0 ? a.dact + dact_index(a.npx, P, mb * 128) : nullptr;
       DgradPre pre[2];
-      dgrad_prefetch(pre[0], xrow, drow, 0, nvalid, (mb * 128) >= a.rmw_from, a.variant, 16 * a.npx, a.xp ? 16 * a.npx : 0);
-      dgrad_prefetch(pre[1], xrow, drow, 16, nvalid, (mb * 128 + 16) >= a.rmw_from, a.variant, 16 * a.npx, a.xp ? 16 * a.npx : 0);
+      dgrad_prefetch(pre[0], xrow, drow, 0, nvalid, (mb * 128) >= a.rmw_from, 16 * a.npx, a.xp ? 16 * a.npx : 0);
+      dgrad_prefetch(pre[1], xrow, drow, 16, nvalid, (mb * 128 + 16) >= a.rmw_from, 16 * a.npx, a.xp ? 16 * a.npx : 0);
       ld.load(rowptr, min(8, a.Kdz / 8));
       for (int kc = 0; kc < nkc; ++kc) {
         const int ck = min(64, a.Kdz - kc * 64);
@@ -505,44 +396,33 @@ __global__ void __launch_bounds__(128, 3) dgrad_td_kernel(DgradArgs a) {
         mbar_wait(&bar_done[s], u & 1);
         tc_fence_after();
       }
-      dgrad_epilogue<false>(tmem, warp, lane, xrow, drow, mb * 128, nvalid, kcs, a, S1, S2, pre, nullptr);
+      dgrad_epilogue(tmem, warp, lane, xrow, drow, mb * 128, nvalid, kcs, a, S1, pre);
       tc_fence_before();
       __syncthreads();
     }
-    dgrad_flush(s_sum, S1, S2, warp, lane, kcs, s_rstd, a, mb, nvalid);
+    dgrad_flush(s_sum, S1, lane, kcs, s_rstd, a, mb, nvalid);
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem, 128);
 }
 
-int launch_dgrad(const DgradArgs& a_in, int grid, cudaStream_t st) {
-  static int variant = -1;
-  if (variant < 0) {
-    const char* e = getenv("RL_VARIANT");
-    variant = e ? atoi(e) : 3;
-  }
-  DgradArgs a = a_in;
-  a.variant = variant;
-  static bool configured = false;
-  if (!configured) {
-    RL_CUDA(cudaFuncSetAttribute(dgrad_dense_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 84 * 1024));
-    RL_CUDA(cudaFuncSetAttribute(dgrad_td_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 84 * 1024));
-    configured = true;
-  }
+constexpr size_t kDgradDenseSmem = 36864 + 2 * kDzRows * 16 + sizeof(DgradConsts) + 384 * sizeof(float);
+constexpr size_t kDgradTdSmem = 2 * 32768 + sizeof(DgradConsts) + 384 * sizeof(float);
+
+int launch_dgrad(const DgradArgs& a, int grid, cudaStream_t st) {
   if (a.dense) {
     if (a.strip_w + 2 > 165) return rl_fail(RL_ERR_SHAPE, "dgrad: strip too wide");
-    size_t smem = 36864 + 2 * kDzRows * 16 + sizeof(DgradConsts) + 384 * sizeof(float);
     const int nmb = (a.Cin + 127) / 128;
     const long vrows = (long)a.B * (a.H + 1);
     const bool split = nmb > 1 && vrows * (a.W + 2) <= 40000;  // small level: channel blocks in parallel CTAs (rl_api.cu sizes grid.x accordingly)
-    { ProfScope _ps(KC_DGRAD_DENSE, st);
-    RL_CUDA(launch_pdl(dgrad_dense_kernel, dim3(grid, split ? nmb : 1), dim3(128), smem, st, a)); }
+    ProfScope _ps(KC_DGRAD_DENSE, st);
+    dgrad_dense_kernel<<<dim3(grid, split ? nmb : 1), 128, kDgradDenseSmem, st>>>(a);
   } else {
-    size_t smem = 2 * 32768 + sizeof(DgradConsts) + 384 * sizeof(float);
-    { ProfScope _ps(KC_DGRAD_TD, st);
-    RL_CUDA(launch_pdl(dgrad_td_kernel, dim3(grid), dim3(128), smem, st, a)); }
+    ProfScope _ps(KC_DGRAD_TD, st);
+    dgrad_td_kernel<<<grid, 128, kDgradTdSmem, st>>>(a);
   }
+  RL_CUDA(cudaGetLastError());
   return RL_OK;
 }
 
@@ -582,8 +462,6 @@ __global__ void __launch_bounds__(kWgThreads, 2) wgrad_kernel(WgradArgs a) {
     fence_mbar_init();
   }
   if (warp == 0) tmem_alloc(&tmem_base_s, 256);
-  pdl_trigger();
-  pdl_wait();
   if (tid < 128) {
     float s = 0.f, t = 0.f;
     if (a.transform && tid < ca) {
@@ -747,18 +625,22 @@ __global__ void __launch_bounds__(kWgThreads, 2) wgrad_kernel(WgradArgs a) {
 }
 
 int launch_wgrad(const WgradArgs& a, int nruns, int nmb, int nparts, cudaStream_t st) {
-  static bool configured = false;
-  if (!configured) {
-    RL_CUDA(cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-    configured = true;
-  }
   int npmax = 0;
   for (int i = 0; i < nparts; ++i) npmax = a.part_np[i] > npmax ? a.part_np[i] : npmax;
   size_t smem = 1024 + 3 * (16384 + (size_t)npmax * 128);
   if (smem > 160 * 1024) return rl_fail(RL_ERR_SHAPE, "wgrad: smem %zu too large", smem);
-  { ProfScope _ps(KC_WGRAD, st);
-  RL_CUDA(launch_pdl(wgrad_kernel, dim3(nruns, nmb, nparts), dim3(kWgThreads), smem, st, a)); }
+  {
+    ProfScope _ps(KC_WGRAD, st);
+    wgrad_kernel<<<dim3(nruns, nmb, nparts), kWgThreads, smem, st>>>(a);
+  }
   RL_CUDA(cudaGetLastError());
+  return RL_OK;
+}
+
+int configure_bwd_kernels() {
+  RL_CUDA(cudaFuncSetAttribute(dgrad_dense_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 84 * 1024));
+  RL_CUDA(cudaFuncSetAttribute(dgrad_td_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 84 * 1024));
+  RL_CUDA(cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
   return RL_OK;
 }
 

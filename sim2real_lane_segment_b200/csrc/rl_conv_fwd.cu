@@ -69,8 +69,6 @@ __global__ void __launch_bounds__(kFwdThreads, 2) dense_fwd_kernel(DenseFwdArgs 
   }
   if (warp == 0) tmem_alloc(&tmem_base_s, 256);
   for (int i = tid; i < 4 * kRing * 4; i += kFwdThreads) zs[i] = 0.f;
-  pdl_trigger();
-  pdl_wait();  // ---- everything above is CTA-local; global memory only from here on
   if (tid < 16) s_bias16[tid] = a.bias[tid];
   for (int c = tid; c < a.Cin; c += kFwdThreads) {
     BnCoef k = bn_coef(a.bn, c);
@@ -300,6 +298,7 @@ __global__ void __launch_bounds__(kFwdThreads, 2) dense_fwd_kernel(DenseFwdArgs 
 constexpr int kF2Threads = 320;
 constexpr int kF2A = 6, kF2W = 3;  // maximum activation ring depth; weight ring depth in streaming mode
 constexpr int kF2ABytes = 16384, kF2WBytes = 18432;
+constexpr size_t kF2Cap = 224 * 1024;
 
 struct alignas(64) DenseFwdTmaArgs {
   CUtensorMap tmap;
@@ -382,13 +381,9 @@ __global__ void __launch_bounds__(kF2Threads, 1) dense_fwd_tma_kernel(const __gr
       for (int tile = 0; tile < ntiles; ++tile)
         for (int kc = 0; kc < nkc; ++kc) {
           mbar_wait(&a_empty[s], ph);
-          if (a.dbg & 8) {
-            mbar_arrive(&a_full[s]);
-          } else {
-            mbar_arrive_expect_tx(&a_full[s], kF2ABytes);
-            if (strips) tma_load_3d(sA + s * kF2ABytes, &P.tmap, kc * 64, xs, rin0 + tile, &a_full[s]);
-            else tma_load_2d(sA + s * kF2ABytes, &P.tmap, kc * 64, P0 + tile * 128, &a_full[s]);
-          }
+          mbar_arrive_expect_tx(&a_full[s], kF2ABytes);
+          if (strips) tma_load_3d(sA + s * kF2ABytes, &P.tmap, kc * 64, xs, rin0 + tile, &a_full[s]);
+          else tma_load_2d(sA + s * kF2ABytes, &P.tmap, kc * 64, P0 + tile * 128, &a_full[s]);
           if (++s == NA) {
             s = 0;
             ph ^= 1;
@@ -437,7 +432,7 @@ __global__ void __launch_bounds__(kF2Threads, 1) dense_fwd_tma_kernel(const __gr
         }
         for (int kc = 0; kc < nkc; ++kc, ++g) {
           if (!wres && g + 2 < total) issue_w(g + 2);
-          const int n16 = (a.dbg & 2) ? 0 : (kc == nkc - 1 ? last_n16 : 4);
+          const int n16 = kc == nkc - 1 ? last_n16 : 4;
           mbar_wait(&a_ready[sa], pa);
           if (!wres) mbar_wait(&w_full[sw], pw);
           tc_fence_after();
@@ -447,14 +442,9 @@ __global__ void __launch_bounds__(kF2Threads, 1) dense_fwd_tma_kernel(const __gr
           if (n16 > 1) umma_ss(dacc, ad + 2, wd + 288, idesc, 1);
           if (n16 > 2) umma_ss(dacc, ad + 4, wd + 576, idesc, 1);
           if (n16 > 3) umma_ss(dacc, ad + 6, wd + 864, idesc, 1);
-          if (a.dbg & 64) {
-            mbar_arrive(&a_empty[sa]);
-            if (kc == nkc - 1) mbar_arrive(&acc_full[buf]);
-          } else {
-            umma_commit(&a_empty[sa]);
-            if (!wres) umma_commit(&w_empty[sw]);
-            if (kc == nkc - 1) umma_commit(&acc_full[buf]);
-          }
+          umma_commit(&a_empty[sa]);
+          if (!wres) umma_commit(&w_empty[sw]);
+          if (kc == nkc - 1) umma_commit(&acc_full[buf]);
           if (++sa == NA) {
             sa = 0;
             pa ^= 1;
@@ -476,7 +466,7 @@ __global__ void __launch_bounds__(kF2Threads, 1) dense_fwd_tma_kernel(const __gr
       for (int kc = 0; kc < nkc; ++kc) {
         const int ck = min(64, a.Cin - kc * 64);
         mbar_wait(&a_full[s], ph);
-        if (8 * j < ck && !(a.dbg & 1)) {
+        if (8 * j < ck) {
           const float* sp = s_s + kc * 64 + 8 * j;
           const float* tp = s_t + kc * 64 + 8 * j;
           const float4 s0 = *reinterpret_cast<const float4*>(sp), s1 = *reinterpret_cast<const float4*>(sp + 4);
@@ -494,7 +484,7 @@ __global__ void __launch_bounds__(kF2Threads, 1) dense_fwd_tma_kernel(const __gr
             base[i * 128] = o;
           }
         }
-        if (!(a.dbg & 32)) fence_proxy_async();
+        fence_proxy_async();
         __syncwarp();
         if (lane == 0) mbar_arrive(&a_ready[s]);
         if (++s == NA) {
@@ -548,7 +538,7 @@ __global__ void __launch_bounds__(kF2Threads, 1) dense_fwd_tma_kernel(const __gr
           tmem_ld16_nowait(tacc + (dxi + 1) * 48 + 32, vn + 32);
         }
         const int qx = xx - dx;
-        const bool okx = in_valid && qx >= x0 && qx < x1 && !(a.dbg & 4);
+        const bool okx = in_valid && qx >= x0 && qx < x1;
 #pragma unroll
         for (int dyi = 0; dyi < 3; ++dyi) {
           const int dy = dyi - 1;
@@ -584,7 +574,7 @@ __global__ void __launch_bounds__(kF2Threads, 1) dense_fwd_tma_kernel(const __gr
         if (wide) epilogue_sync();
       }
       const int lim = (tile == ntiles - 1) ? n_in : max(0, min(t0 + 128 - SW - 1, n_in));
-      for (int e0 = emit_pos; e0 < ((a.dbg & 16) ? 0 : lim); e0 += 128) {
+      for (int e0 = emit_pos; e0 < lim; e0 += 128) {
         const int e = e0 + et;
         if (e < lim) {
           const int er = e / SW, ec = e - er * SW;
@@ -663,12 +653,7 @@ __global__ void __launch_bounds__(kF2Threads, 1) dense_fwd_tma_kernel(const __gr
 }
 
 int launch_dense_fwd_tma(const DenseFwdArgs& a, const void* tmap, int grid, cudaStream_t st) {
-  constexpr size_t kCap = 224 * 1024;  // dynamic shared memory of the one resident CTA
-  static bool configured = false;
-  if (!configured) {
-    RL_CUDA(cudaFuncSetAttribute(dense_fwd_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCap));
-    configured = true;
-  }
+  constexpr size_t kCap = kF2Cap;  // dynamic shared memory of the one resident CTA
   const int strip_mode = a.W > 160;
   if (!strip_mode && a.nstrips != 1) return rl_fail(RL_ERR_SHAPE, "dense_fwd_tma: a level up to 160 wide is one strip");
   if (strip_mode && (a.strip_w < 1 || a.strip_w > 126)) return rl_fail(RL_ERR_SHAPE, "dense_fwd_tma: strips are at most 126 wide");
@@ -688,8 +673,11 @@ int launch_dense_fwd_tma(const DenseFwdArgs& a, const void* tmap, int grid, cuda
   }
   const size_t smem = fixed + (P.w_resident ? wall : (size_t)kF2W * kF2WBytes) + (size_t)P.na * kF2ABytes;
   if (smem > kCap) return rl_fail(RL_ERR_SHAPE, "dense_fwd_tma: smem %zu too large", smem);
-  { ProfScope _ps(KC_DENSE_FWD, st);
-  RL_CUDA(launch_pdl(dense_fwd_tma_kernel, dim3(grid), dim3(kF2Threads), smem, st, P)); }
+  {
+    ProfScope _ps(KC_DENSE_FWD, st);
+    dense_fwd_tma_kernel<<<grid, kF2Threads, smem, st>>>(P);
+  }
+  RL_CUDA(cudaGetLastError());
   return RL_OK;
 }
 
@@ -752,8 +740,6 @@ __global__ void __launch_bounds__(128, 2) gemm_px_kernel(GemmPxArgs a) {
   }
   const uint32_t tmem_cols = np <= 128 ? 128u : 256u;  // accumulator columns of this part: 3 CTAs per SM fit when <= 128
   if (warp == 0) tmem_alloc(&tmem_base_s, tmem_cols);
-  pdl_trigger();
-  pdl_wait();
   if (a.transform)
     for (int c = tid; c < a.K; c += 128) {
       BnCoef k = bn_coef(a.bn, c);
@@ -944,14 +930,12 @@ size_t gemm_px_smem(int K, int np_max) { return (((size_t)K * 8 + 127) & ~(size_
 // ------------------------------------------------------------------------------------------------ launchers
 int launch_dense_fwd(const DenseFwdArgs& a, int grid, cudaStream_t st) {
   size_t smem = dense_fwd_smem(a.Cin);
-  static size_t configured = 0;
-  if (smem > configured) {
-    RL_CUDA(cudaFuncSetAttribute(dense_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
-    configured = 110 * 1024;
-  }
   if (smem > 110 * 1024) return rl_fail(RL_ERR_SHAPE, "dense_fwd: smem %zu too large", smem);
-  { ProfScope _ps(KC_DENSE_FWD, st);
-  RL_CUDA(launch_pdl(dense_fwd_kernel, dim3(grid), dim3(kFwdThreads), smem, st, a)); }
+  {
+    ProfScope _ps(KC_DENSE_FWD, st);
+    dense_fwd_kernel<<<grid, kFwdThreads, smem, st>>>(a);
+  }
+  RL_CUDA(cudaGetLastError());
   return RL_OK;
 }
 
@@ -959,14 +943,19 @@ int launch_gemm_px(const GemmPxArgs& a, int grid_x, int nparts, cudaStream_t st)
   int npmax = 0;
   for (int i = 0; i < nparts; ++i) npmax = a.part_np[i] > npmax ? a.part_np[i] : npmax;
   size_t smem = gemm_px_smem(a.K, npmax);
-  static bool configured = false;
-  if (!configured) {
-    RL_CUDA(cudaFuncSetAttribute(gemm_px_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
-    configured = true;
-  }
   if (smem > 110 * 1024) return rl_fail(RL_ERR_SHAPE, "gemm_px: smem %zu too large (K=%d np=%d)", smem, a.K, npmax);
-  { ProfScope _ps(KC_GEMM_PX, st);
-  RL_CUDA(launch_pdl(gemm_px_kernel, dim3(grid_x, nparts), dim3(128), smem, st, a)); }
+  {
+    ProfScope _ps(KC_GEMM_PX, st);
+    gemm_px_kernel<<<dim3(grid_x, nparts), 128, smem, st>>>(a);
+  }
+  RL_CUDA(cudaGetLastError());
+  return RL_OK;
+}
+
+int configure_fwd_kernels() {
+  RL_CUDA(cudaFuncSetAttribute(dense_fwd_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kF2Cap));
+  RL_CUDA(cudaFuncSetAttribute(dense_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
+  RL_CUDA(cudaFuncSetAttribute(gemm_px_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
   return RL_OK;
 }
 

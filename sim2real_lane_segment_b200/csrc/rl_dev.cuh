@@ -114,6 +114,51 @@ struct TileLoader {
   }
 };
 
+__device__ __forceinline__ void unpack8(uint4 v, float* f) {
+  float2 a = unpack_bf16x2(v.x), b = unpack_bf16x2(v.y), c = unpack_bf16x2(v.z), d = unpack_bf16x2(v.w);
+  f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
+}
+__device__ __forceinline__ uint4 pack8(const float* v) {
+  return make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+}
+
+// halo tile of the zero-padded dz16 planes: 128 + 2*(strip+2) + 2 <= 464 rows for strips up to 165 columns
+constexpr int kDzRows = 464;
+
+// Σ over the 32 lanes of v[k] for k = 0..15 (v is clobbered); lane l ends up holding the total of k = (l >> 1) & 15
+__device__ __forceinline__ float warp_reduce16(float* v, int lane) {
+  {
+    const bool hi = lane & 16;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float send = hi ? v[i] : v[i + 8], keep = hi ? v[i + 8] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    }
+  }
+  {
+    const bool hi = lane & 8;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float send = hi ? v[i] : v[i + 4], keep = hi ? v[i + 4] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+    }
+  }
+  {
+    const bool hi = lane & 4;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const float send = hi ? v[i] : v[i + 2], keep = hi ? v[i + 2] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+    }
+  }
+  {
+    const bool hi = lane & 2;
+    const float send = hi ? v[0] : v[1], keep = hi ? v[1] : v[0];
+    v[0] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+  }
+  return v[0] + __shfl_xor_sync(0xffffffffu, v[0], 1);
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -1,6 +1,5 @@
 // rl_error.cu — thread-local last-error string behind rl_last_error().
 #include <stdarg.h>
-#include <stdlib.h>
 #include <string.h>
 
 #include "rl_common.cuh"
@@ -13,19 +12,6 @@ int rl_fail(int code, const char* fmt, ...) {
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
   return code;
-}
-}  // namespace rl
-
-namespace rl {
-bool pdl_enabled() {
-  static int v = -1;
-  if (v < 0) {
-    // measured on B200 (round 1): 29.7 ms/step with programmatic dependent launch vs 25.5 ms without -- the early
-    // dependents take SM slots from the draining kernel -- so it is opt-in (RL_PDL=1)
-    const char* e = getenv("RL_PDL");
-    v = (e && e[0] == '1') ? 1 : 0;
-  }
-  return v != 0;
 }
 }  // namespace rl
 

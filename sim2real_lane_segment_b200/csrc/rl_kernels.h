@@ -19,7 +19,6 @@ struct DenseFwdArgs {
   const float* mask;         // [B][16] dropout scale or null
   BnSrc bn;
   double* stats_out;         // level stats base (Σx at [c], Σx² at [Ct+c]) or null
-  int dbg;                   // triage switches (RL_FWD_DBG), 0 in production
   __nv_bfloat16* x16;        // training: the output's 16-channel group plane [px][16] of the planar mirror (or null)
 };
 int launch_dense_fwd(const DenseFwdArgs& a, int grid, cudaStream_t st);
@@ -62,15 +61,15 @@ struct DgradArgs {
   const uint8_t* wpk;        // dense: per M-block [18][128][8]; td: per M-block, per K chunk [8][128][8]
   const __nv_bfloat16* act;  // level arena
   __nv_bfloat16* dact;       // gradient arena, planar by 16-channel group (rl_dev.cuh: dact_index)
-  int Ct, Cin, H, W, B;
+  int Ct, Cin, H, W, B;      // Cin: number of channels this launch covers, starting at arena channel c_lo
+  int c_lo;                  // first arena channel (0 for a whole layer; C0 of the block for the chain launches)
   int rmw_from;
   BnSrc bn;
-  float* g_gamma;            // reference-ordered gradient slots
+  float* g_gamma;            // reference-ordered gradient slots; null: this launch leaves dgamma / dbeta to wgrad_dense2
   float* g_beta;
   double* acc;               // level accumulators: A at [c], B at [Ct+c]
   int vrows_per_cta, nstrips, strip_w;  // dense work decomposition (virtual rows: H+1 per image)
   long ntiles;                           // td: 128-pixel tiles
-  int variant;                           // tuning switches (env RL_VARIANT): bit0 L2::128B hint, bit1 256-bit accesses
   long npx;                              // pixels of the level (group stride of the planar gradient arena = 16 * npx)
   const __nv_bfloat16* xp;               // planar mirror of the activation arena (same layout as dact) or null
 };
@@ -99,6 +98,60 @@ struct WgradArgs {
   int num_cls;
 };
 int launch_wgrad(const WgradArgs& a, int nruns, int nmb, int nparts, cudaStream_t st);
+
+// ---------------------------------------------------------------- backward of a whole DenseBlock (rl_bwd_fused.cu)
+// Input gradient of all five DenseLayers of a block with respect to the block's INPUT channels [0, C0):
+//   dX[p, c] (+)= Σ_j γ_j r_c · relu'_j(p, c) · (dz_j ⊛ W_j)[p, c]
+// one pass over x and dX instead of five; the BatchNorm-backward mean terms of these channels (A_c, B_c) are the
+// pixel sums of the total it adds.  dγ_j / dβ_j come from wgrad_dense2_kernel.
+struct DgradBulkArgs {
+  int nl;                        // layers fused (kBlockLayers)
+  const __nv_bfloat16* dz[5];    // zero-padded dz16 planes of layer j
+  const uint8_t* wpk[5];         // [ncb][18][96][8] packed weights of layer j for the block-input channels
+  const float* gamma[5];         // reference-ordered BatchNorm weights of layer j
+  const float* beta[5];
+  const double* stats;           // level stats (Σx, Σx²)
+  double inv_n;
+  int Ct, cs_perm;
+  long dz_npos, dz_guard;
+  const __nv_bfloat16* xp;       // planar activation mirror
+  __nv_bfloat16* dact;           // planar gradient arena
+  long npx;
+  int C0, cbs;                   // block-input channels, channel-block size
+  int H, W, B, vrows_per_cta;
+  int rmw;
+  double* acc;                   // level accumulators A at [c], B at [Ct + c]
+};
+int launch_dgrad_bulk(const DgradBulkArgs& a, int nruns, int ncb, cudaStream_t st);
+
+// Weight gradients of the (up to five) DenseLayers of a block in one launch (grid.z = layer), plus dγ / dβ of their
+// BatchNorms.  For 64 channels at a time two operands are built from x: m·x̂ and m (m = relu mask), so with
+// D2 = (m·x̂)ᵀ·im2col(dz), D1 = mᵀ·im2col(dz):  dW = γ·D2 + β·D1,  dγ = Σ_n W·D2,  dβ = Σ_n W·D1.
+struct WgDenseLayer {
+  const uint8_t* wpk_bwd;        // [mb][18][128][8] packed weights (contracted with D1 / D2 for dβ / dγ)
+  const float* gamma;            // reference-ordered
+  const float* beta;
+  float* g_gamma;
+  float* g_beta;
+  float* gw;
+  const __nv_bfloat16* dz;       // zero-padded dz16 planes
+  int Cin, cs_perm;
+};
+struct WgDenseArgs {
+  WgDenseLayer L[5];
+  int nl;
+  const __nv_bfloat16* xp;       // planar activation mirror
+  long npx;
+  int H, W;
+  long dz_npos, dz_guard;
+  const double* stats;
+  int Ct;
+  double inv_n;
+  long px_per_cta;
+};
+int launch_wgrad_dense2(const WgDenseArgs& a, int nruns, int ngroups, cudaStream_t st);
+// once per device / plan bind: opt the kernels into their dynamic shared-memory sizes
+int configure_kernels();
 
 // ---------------------------------------------------------------- CUDA-core kernels (rl_misc.cu)
 int launch_pack_weights(const Plan* p, const float* params, cudaStream_t st);
@@ -170,5 +223,7 @@ int launch_adamw(float* p, const float* g, float* m, float* v, long n, float lr,
 int launch_sgd_nesterov(float* p, const float* g, float* buf, long n, float lr, float momentum, float wd, int first,
                         float grad_scale, cudaStream_t st);
 int launch_fill_masks(float* masks, long n, float p_drop, unsigned long long seed, unsigned long long step, cudaStream_t st);
+// grads[i] += scale * (*scale_dev) * stage[i]   (end of a backward pass; scale_dev may be null)
+int launch_grad_accum(float* grads, const float* stage, long n, float scale, const float* scale_dev, cudaStream_t st);
 
 }  // namespace rl

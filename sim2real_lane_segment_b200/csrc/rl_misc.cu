@@ -13,10 +13,6 @@ static inline int cdiv(long a, long b) { return (int)((a + b - 1) / b); }
 // ================================================================================================
 // weight packing (fp32 reference layouts -> bf16 chunk-layout operands), one table-driven launch
 // ================================================================================================
-__device__ __forceinline__ uint4 pack8(const float* v) {
-  return make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
-}
-
 __global__ void pack_weights_kernel(const PackEntry* tab, const float* __restrict__ params, uint8_t* ws) {
   const PackEntry e = tab[blockIdx.y];
   const float* w = params + e.p_w;
@@ -82,6 +78,20 @@ __global__ void pack_weights_kernel(const PackEntry* tab, const float* __restric
           int n = nb + k;
           if (n < 720) v[k] = w[((long)ci * 80 + n % 80) * 9 + n / 80];
         }
+        break;
+      }
+      case 6: {  // dense bwd, chain launch: [j=tap*2+half][cl][8 co], arena channel c_lo + cl (rows >= nch stay zero)
+        int j = (int)(i / 128), cl = (int)(i % 128);
+        int tap = j >> 1, half = j & 1, c = e.c_lo + cl;
+        if (cl < e.nch)
+          for (int k = 0; k < 8; ++k) v[k] = w[((long)(half * 8 + k) * C + ref_channel(c, e.cs_perm)) * 9 + tap];
+        break;
+      }
+      case 7: {  // dense bwd, block-input kernel: [cb][j=tap*2+half][cl][8 co], channel cb*cbs + cl < C0 (c_lo = C0, nch = cbs)
+        int cb = (int)(i / (18 * kBulkCb)), rem = (int)(i % (18 * kBulkCb)), j = rem / kBulkCb, cl = rem % kBulkCb;
+        int tap = j >> 1, half = j & 1, c = cb * e.nch + cl;
+        if (cl < e.nch && c < e.c_lo)
+          for (int k = 0; k < 8; ++k) v[k] = w[((long)(half * 8 + k) * C + ref_channel(c, e.cs_perm)) * 9 + tap];
         break;
       }
     }
@@ -166,8 +176,6 @@ int launch_first_fwd(const Plan* p, const float* x, const float* params, int tra
 __global__ void __launch_bounds__(256) channel_stats_kernel(const __nv_bfloat16* __restrict__ arena, long npx, int Ct,
                                                             int c_off, int nch, double* stats) {
   extern __shared__ float sred[];  // [blockDim][16]
-  pdl_trigger();
-  pdl_wait();
   const int nchunk = nch / 8;
   const int ppb = blockDim.x / nchunk;  // pixel lanes per block
   const int j = threadIdx.x % nchunk, pl = threadIdx.x / nchunk;
@@ -206,7 +214,8 @@ int launch_channel_stats(const __nv_bfloat16* arena, long npx, int Ct, int c_off
   int nchunk = nch / 8, ppb = 256 / nchunk;
   int grid = (int)std::min<long>((npx + ppb - 1) / ppb, (long)sm * 4);
   { ProfScope _ps(KC_STATS, st);
-  RL_CUDA(launch_pdl(channel_stats_kernel, dim3(grid), dim3(256), 256 * 16 * sizeof(float), st, arena, npx, Ct, c_off, nch, stats)); }
+  channel_stats_kernel<<<grid, 256, 256 * 16 * sizeof(float), st>>>(arena, npx, Ct, c_off, nch, stats); }
+  RL_CUDA(cudaGetLastError());
   return RL_OK;
 }
 
@@ -217,8 +226,6 @@ int launch_channel_stats(const __nv_bfloat16* arena, long npx, int Ct, int c_off
 __global__ void __launch_bounds__(256) tu_col2im_kernel(const __nv_bfloat16* __restrict__ ycol, __nv_bfloat16* out,
                                                         __nv_bfloat16* out_xp, const float* __restrict__ bias, int B, int h, int w, int H, int W,
                                                         int Ct, int o_off) {
-  pdl_trigger();
-  pdl_wait();
   const long total = (long)B * H * W * 10;
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
     const int i32 = (int)i, P32 = i32 / 10, j = i32 - P32 * 10;   // < 2^31 work items: 32-bit index arithmetic
@@ -256,7 +263,8 @@ int launch_tu_col2im(const __nv_bfloat16* ycol, __nv_bfloat16* out, __nv_bfloat1
   long total = (long)B * H * W * 10;
   int grid = (int)std::min<long>((total + 255) / 256, 148L * 16);
   { ProfScope _ps(KC_TU_COL2IM, st);
-  RL_CUDA(launch_pdl(tu_col2im_kernel, dim3(grid), dim3(256), 0, st, ycol, out, out_xp, bias, B, h, w, H, W, Ct, o_off)); }
+  tu_col2im_kernel<<<grid, 256, 0, st>>>(ycol, out, out_xp, bias, B, h, w, H, W, Ct, o_off); }
+  RL_CUDA(cudaGetLastError());
   return RL_OK;
 }
 
@@ -517,11 +525,6 @@ int launch_head(const HeadArgs& a, int sm, cudaStream_t st) {
 // output-gradient preparation:   dz = dropout_scale * (dX - A_c - xhat * B_c)
 // (A_c, B_c): BatchNorm-backward mean terms summed over all consumer layers of channel c.
 // ================================================================================================
-__device__ __forceinline__ void unpack8(uint4 v, float* f) {
-  float2 a = unpack_bf16x2(v.x), b = unpack_bf16x2(v.y), c = unpack_bf16x2(v.z), d = unpack_bf16x2(v.w);
-  f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
-}
-
 __global__ void __launch_bounds__(256) dz_prepare_kernel(DzArgs a) {
   extern __shared__ float sm[];  // reduction scratch [256][8]
   float* s_red = sm;
@@ -676,8 +679,6 @@ __device__ __forceinline__ DzConst dz_const(const DzArgs& a, int c) {
 __global__ void __launch_bounds__(256) dz_dense16_kernel(DzArgs a) {
   __shared__ float s_red[8][16];
   __shared__ float2 s_k[16];  // dz = mask * (dX - A' - x * B'),  B' = rstd * B,  A' = A - mean * B'
-  pdl_trigger();
-  pdl_wait();
   if (threadIdx.x < 16) {
     const DzConst k = dz_const(a, threadIdx.x);
     const float b2 = k.rstd * k.B;
@@ -740,8 +741,6 @@ __global__ void __launch_bounds__(256) dz_dense16_kernel(DzArgs a) {
 // TransitionDown output: one thread per (pooled pixel, 8-channel chunk) scatters to the 4 pixels of its 2x2 window
 __global__ void __launch_bounds__(256) dz_td_kernel(DzArgs a) {
   extern __shared__ float sm[];
-  pdl_trigger();
-  pdl_wait();
   const int nchunk = a.nch / 8, ppb = blockDim.x / nchunk;
   const int j = threadIdx.x % nchunk, pl = threadIdx.x / nchunk;
   DzConst* s_k = reinterpret_cast<DzConst*>(sm + 256 * 8);  // [nch]
@@ -826,8 +825,6 @@ __global__ void __launch_bounds__(256) dz_td_kernel(DzArgs a) {
 // image are zero-filled by the threads of the last input row / column.
 __global__ void __launch_bounds__(250) dz_tu_kernel(DzArgs a) {
   extern __shared__ float sm[];
-  pdl_trigger();
-  pdl_wait();
   const int j = threadIdx.x % 10, pl = threadIdx.x / 10;   // 10 chunks of 8 channels, 25 pixel lanes
   const int h = a.Hp, w = a.Wp;
   DzConst* s_k = reinterpret_cast<DzConst*>(sm + 250 * 8);  // [80]
@@ -892,7 +889,8 @@ int launch_dz_prepare(const DzArgs& a, int sm, cudaStream_t st) {
   if (a.kind == 0 && a.planes && a.nch == 16) {
     int grid = (int)std::min<long>((a.npx_out + 255) / 256, (long)sm * 8);
     { ProfScope _ps(KC_DZ_PREPARE, st);
-    RL_CUDA(launch_pdl(dz_dense16_kernel, dim3(grid), dim3(256), 0, st, a)); }
+    dz_dense16_kernel<<<grid, 256, 0, st>>>(a); }
+  RL_CUDA(cudaGetLastError());
     return RL_OK;
   }
   if (a.kind == 1) {
@@ -900,14 +898,16 @@ int launch_dz_prepare(const DzArgs& a, int sm, cudaStream_t st) {
     long npool = (long)a.B * a.Hp * a.Wp;
     int grid = (int)std::max<long>(1, std::min<long>((npool + ppb - 1) / ppb, (long)sm * 8));
     { ProfScope _ps(KC_DZ_PREPARE, st);
-    RL_CUDA(launch_pdl(dz_td_kernel, dim3(grid), dim3(256), 256 * 8 * sizeof(float) + a.nch * sizeof(DzConst), st, a)); }
+    dz_td_kernel<<<grid, 256, 256 * 8 * sizeof(float) + a.nch * sizeof(DzConst), st>>>(a); }
+  RL_CUDA(cudaGetLastError());
     return RL_OK;
   }
   if (a.kind == 2 && a.nch == 80) {
     long nout = (long)a.B * a.H * a.W;
     int grid = (int)std::max<long>(1, std::min<long>((nout + 24) / 25, (long)sm * 8));
     { ProfScope _ps(KC_DZ_PREPARE, st);
-    RL_CUDA(launch_pdl(dz_tu_kernel, dim3(grid), dim3(250), 250 * 8 * sizeof(float) + 80 * sizeof(DzConst), st, a)); }
+    dz_tu_kernel<<<grid, 250, 250 * 8 * sizeof(float) + 80 * sizeof(DzConst), st>>>(a); }
+  RL_CUDA(cudaGetLastError());
     return RL_OK;
   }
   size_t smem = (size_t)(256 * 8) * sizeof(float);
@@ -991,6 +991,21 @@ int launch_sgd_nesterov(float* p, const float* g, float* buf, long n, float lr, 
   int grid = (int)std::min<long>((n + 255) / 256, 148L * 8);
   { ProfScope _ps(KC_OPT, st);
   sgd_nesterov_kernel<<<grid, 256, 0, st>>>(p, g, buf, n, lr, momentum, wd, first, grad_scale); }
+  RL_CUDA(cudaGetLastError());
+  return RL_OK;
+}
+
+// grads += scale * stage: end of a backward pass (the raw gradients of one pass are staged so that the loss's grad_output,
+// a device scalar, can be applied without the head kernel having to wait for it)
+__global__ void __launch_bounds__(256) grad_accum_kernel(float* __restrict__ g, const float* __restrict__ stage, long n, float scale,
+                                                         const float* __restrict__ scale_dev) {
+  const float sc = scale * (scale_dev ? __ldg(scale_dev) : 1.f);
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) g[i] = fmaf(sc, stage[i], g[i]);
+}
+int launch_grad_accum(float* grads, const float* stage, long n, float scale, const float* scale_dev, cudaStream_t st) {
+  int grid = (int)std::min<long>((n + 255) / 256, 148L * 8);
+  { ProfScope _ps(KC_OPT, st);
+  grad_accum_kernel<<<grid, 256, 0, st>>>(grads, stage, n, scale, scale_dev); }
   RL_CUDA(cudaGetLastError());
   return RL_OK;
 }

@@ -35,6 +35,11 @@ int build_plan(Plan* p, int B, int H, int W, int num_cls, int training) {
     p->ev_dz[i] = p->ev_wg[i] = nullptr;
     p->ev_wg_used[i] = false;
   }
+  for (int i = 0; i < kLevels; ++i) {
+    p->ev_blk[i] = nullptr;
+    p->ev_blk_used[i] = false;
+  }
+  p->opt_overlap = p->opt_xp = p->opt_fwd_tma = p->opt_bwd_fused = 1;
   p->err[0] = 0;
   // B*H*W*16 < 2^31: the elementwise kernels index pixels (and pixel x chunk work items) with 32-bit arithmetic
   if (B < 1 || H < 32 || W < 32 || num_cls < 2 || num_cls > 4 || (long)B * H * W >= (1L << 27)) {
@@ -71,6 +76,7 @@ int build_plan(Plan* p, int B, int H, int W, int num_cls, int training) {
     L.b_rm = L.b_rv = -1;
     L.bn_index = -1;
     L.rmw_from = 0;
+    L.blk = L.jblk = -1;
     p->layers.push_back(L);
     return (int)p->layers.size() - 1;
   };
@@ -95,6 +101,23 @@ int build_plan(Plan* p, int B, int H, int W, int num_cls, int training) {
       id_up[i][j] = mk(L_DENSE, l, l, cin, kGrowth, 0, cin, cskip[l]);
       if (j == kBlockLayers - 1 && l != 0) p->layers.back().rmw_from = cskip[l] + kUpCh;
     }
+  }
+  // ---- DenseBlocks (consecutive runs of five dense layers on one level)
+  p->blocks.clear();
+  for (int i = 0; i + kBlockLayers <= (int)p->layers.size(); ++i) {
+    if (p->layers[i].type != L_DENSE || p->layers[i].blk >= 0) continue;
+    Block b;
+    b.first = i;
+    b.lvl = p->layers[i].lvl_in;
+    b.C0 = p->layers[i].cin;
+    b.rmw = p->layers[i + kBlockLayers - 1].rmw_from == 0 ? 1 : 0;
+    b.ncb = (b.C0 + kBulkCb - 1) / kBulkCb;
+    b.cbs = (((b.C0 + b.ncb - 1) / b.ncb) + 15) / 16 * 16;
+    for (int j = 0; j < kBlockLayers; ++j) {
+      p->layers[i + j].blk = (int)p->blocks.size();
+      p->layers[i + j].jblk = j;
+    }
+    p->blocks.push_back(b);
   }
   // ---- parameter offsets in the reference's registration order (tiramisu.py:33-87, TrainingBase.py:32-33)
   long off = 0, boff = 0;
@@ -146,7 +169,7 @@ int build_plan(Plan* p, int B, int H, int W, int num_cls, int training) {
   };
   p->scal_off = carve(1024);
   p->bntab_off = carve(64 * 64);
-  p->packtab_off = carve(160 * sizeof(PackEntry));
+  p->packtab_off = carve(256 * sizeof(PackEntry));
   // packed weights
   p->wpk_off = ws;
   for (Layer& L : p->layers) {
@@ -154,6 +177,8 @@ int build_plan(Plan* p, int B, int H, int W, int num_cls, int training) {
       int nkc = (L.cin + 63) / 64, nmb = (L.cin + 127) / 128;
       L.wpk_fwd = carve((size_t)nkc * 18432);
       L.wpk_bwd = carve((size_t)nmb * 36864);
+      L.wpk_chain = training ? carve(36864) : 0;
+      L.wpk_bulk = training ? carve((size_t)p->blocks[L.blk].ncb * 18 * kBulkCb * 16) : 0;
     } else if (L.type == L_TD) {
       int nkc = (L.cin + 63) / 64, nmb = (L.cin + 127) / 128;
       L.wpk_fwd = carve((size_t)nkc * 8 * L.cin * 16);  // all parts: sum(np) = C rows per chunk-slot
@@ -198,7 +223,7 @@ int build_plan(Plan* p, int B, int H, int W, int num_cls, int training) {
     Level& L = p->lv[l];
     L.dzp_guard = L.W + 3;
     L.dzp_npos = L.dzp_guard + (long)B * (L.H + 1) * (L.W + 2) + 128 + 2 * (L.W + 2) + 8;
-    L.dzp_off = training ? carve((size_t)L.dzp_npos * 32 * 2) : 0;
+    L.dzp_off = training ? carve((size_t)L.dzp_npos * 32 * kDzBufs) : 0;
   }
   p->dzp_bytes = ws - p->dzp_off_all;
   // Planar mirror of the activation arenas (training): [Ct/16][px][16] like the gradient arenas.  Every producer writes
@@ -208,6 +233,7 @@ int build_plan(Plan* p, int B, int H, int W, int num_cls, int training) {
   for (int l = 0; l < kLevels; ++l) p->lv[l].xp_off = training ? carve((size_t)p->lv[l].px * p->lv[l].Ct * 2) : 0;
   p->dl_bytes = training ? (size_t)p->lv[0].px * 16 * 2 : 0;
   p->dl_off = carve(p->dl_bytes);
+  p->gstage_off = training ? carve((size_t)p->n_params * sizeof(float)) : 0;
   p->ws_bytes = ws;
   return 0;
 }

@@ -30,6 +30,9 @@ constexpr int kBlockLayers = 5;
 constexpr int kLevels = 6;  // 5 resolution levels + bottleneck
 constexpr int kUpCh = 80;   // growth * layers carried upward by every TransitionUp
 constexpr int kTaps = 9;
+constexpr int kDzBufs = 5;      // padded dz16 plane pairs per level: one per DenseLayer of a block
+constexpr int kBulkCb = 96;     // channel block of the fused block input-gradient kernel (two halves of <= 48)
+constexpr int kBulkHalf = 48;
 
 struct Level {
   int H, W, Ct;
@@ -40,8 +43,8 @@ struct Level {
   long px;                       // B*H*W
   // zero-padded planes of the 16-channel output gradient of a DenseLayer (training):
   // two planes [npos][8] bf16; position(b,y,x) = guard + (b*(H+1)+y)*(W+2) + x+1; pads are never written
-  size_t dzp_off;                // two buffers of 2 planes each (alternate DenseLayers of the level use alternate buffers,
-  long dzp_npos, dzp_guard;      // so a layer's weight gradient can still read its dz while the next layer's is written)
+  size_t dzp_off;                // kDzBufs buffers of 2 planes each: DenseLayer j of a block uses buffer j, so the block's
+  long dzp_npos, dzp_guard;      // fused input-gradient kernel and its weight gradients can read all five after the chain
 };
 
 struct Layer {
@@ -53,15 +56,29 @@ struct Layer {
   long p_gamma, p_beta, p_w, p_b;  // float offsets into the parameter / gradient arenas (-1: absent)
   long b_rm, b_rv;                 // float offsets into the BN-buffer arena
   size_t wpk_fwd, wpk_bwd;         // byte offsets into workspace (packed bf16 weights)
+  size_t wpk_chain, wpk_bulk;      // dense layers: [18][128][8] rows = the block's earlier new channels; [ncb][18][96][8] block inputs
+  int blk, jblk;                   // dense layers: index into Plan::blocks and position 0..4 inside the block (else -1)
   size_t mask_off;                 // byte offset into workspace: float[B][cout] dropout scale (0 or 1/(1-p))
   size_t amax_off;                 // TD only: byte offset of uint8 argmax [pooled px][C]
   int rmw_from;                    // backward: input-gradient channels below this are overwritten, not accumulated
   int bn_index;                    // 0..59 or -1
 };
 
+// A DenseBlock (reference layers.py:18-40): five growth-16 layers on one level.  Channels [0, C0) are the block's
+// input, [C0, C0 + 80) the layers' outputs.  Backward runs the five layers as a chain over the new channels only and
+// then ONE kernel adds the input gradient of all five layers to the block input (dgrad_bulk_kernel).
+struct Block {
+  int first;     // index of layer 0 of the block in Plan::layers
+  int lvl;
+  int C0;
+  int rmw;       // 1: the block-input gradient accumulates into earlier contributions, 0: it is the first writer
+  int ncb, cbs;  // channel blocks of the fused kernel: ncb blocks of cbs channels (the last one may be shorter)
+};
+
 struct PackEntry {
-  int kind;      // 0 dense fwd, 1 dense bwd, 2 TD fwd, 3 TD bwd, 4 TU fwd, 5 TU bwd
+  int kind;      // 0 dense fwd, 1 dense bwd, 2 TD fwd, 3 TD bwd, 4 TU fwd, 5 TU bwd, 6 dense chain bwd, 7 dense bulk bwd
   int cin, cs_perm, np0;
+  int c_lo, nch;  // kind 6: channel range [c_lo, c_lo + nch); kind 7: c_lo = C0, nch = cbs
   long dst_off;  // bytes into workspace
   long n16;      // number of 16-byte chunks to produce
   long p_w;      // float offset of the weight tensor in the parameter arena
@@ -72,6 +89,7 @@ struct Plan {
   int sm_count;
   Level lv[kLevels];
   std::vector<Layer> layers;
+  std::vector<Block> blocks;
   long n_params;      // floats in the parameter arena (3 461 220 for 4 classes)
   long n_bnbuf;       // floats in the BN-buffer arena
   long p_cls_w, p_cls_b;
@@ -91,10 +109,16 @@ struct Plan {
   void* ws;                           // bound workspace (device)
   alignas(64) unsigned char tmap_act[6][128];  // CUtensorMap per level arena: [pixels][Ct] bf16, box 128 px x 64 ch, 128-byte swizzle
   bool tmap_ok;
-  void* side_stream;                  // cudaStream_t: DenseLayer weight gradients run here, concurrently with the dgrad chain
-  void* ev_dz[4];                     // cudaEvent_t: dz buffer q written (main stream); 0,1: DenseLayer planes, 2,3: scratch
+  size_t gstage_off;                  // training: fp32 [n_params] raw gradients of one backward pass (scaled into `grads` at its end)
+  void* side_stream;                  // cudaStream_t: weight gradients run here, concurrently with the input-gradient chain
+  void* ev_dz[4];                     // cudaEvent_t: dz buffer q written (main stream); 0,1: per-layer path, 2,3: scratch
   void* ev_wg[4];                     // cudaEvent_t: weight gradient that read buffer q finished (side stream)
   bool ev_wg_used[4];
+  void* ev_blk[kLevels];              // cudaEvent_t: the batched weight gradients of the last DenseBlock of a level finished
+  bool ev_blk_used[kLevels];
+  // per-plan switches (rl_plan_set_option): side-stream overlap, planar activation mirror, tensor-map forward,
+  // block-fused backward
+  int opt_overlap, opt_xp, opt_fwd_tma, opt_bwd_fused;
   bool training;                      // arenas for gradients present
   char err[256];
 };

@@ -14,7 +14,9 @@ from . import _lib
 _SIGS_DONE = False
 
 Q_NUM_LAYERS, Q_ACT_OFF, Q_DACT_OFF, Q_CT, Q_H, Q_W, Q_CSKIP, Q_SCAL_OFF, Q_LAYER_TYPE, Q_LAYER_MASK_OFF, \
-    Q_LAYER_COUT, Q_LAYER_PARAM_W, Q_STATS_OFF = range(13)
+    Q_LAYER_COUT, Q_LAYER_PARAM_W, Q_STATS_OFF, Q_GSTAGE_OFF, Q_XP_OFF, Q_ACC_OFF, Q_LAYER_LEVEL_IN, Q_LAYER_LEVEL_OUT, \
+    Q_LAYER_CIN, Q_LAYER_IN_OFF, Q_LAYER_OUT_OFF, Q_LAYER_CS_PERM, Q_LAYER_AMAX_OFF, Q_LAYER_RMW_FROM, \
+    Q_LAYER_PARAM_GAMMA, Q_LAYER_PARAM_B, Q_LAYER_BN_RM, Q_DL_OFF = range(28)
 
 
 def _sigs(L):
@@ -32,9 +34,12 @@ def _sigs(L):
     L.rl_pack_weights.argtypes = [c_void_p, c_void_p, c_void_p]
     L.rl_set_dropout.argtypes = [c_void_p, c_float, c_ulonglong, c_ulonglong, c_void_p]
     L.rl_forward.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p]
+    L.rl_forward_range.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]
     L.rl_head.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_float,
-                          c_void_p, c_float, c_void_p, c_void_p]
-    L.rl_backward.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
+                          c_void_p]
+    L.rl_backward.argtypes = [c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_void_p]
+    L.rl_backward_range.argtypes = [c_void_p, c_void_p, c_int, c_int, c_void_p]
+    L.rl_plan_set_option.argtypes = [c_void_p, ctypes.c_char_p, c_int]
     L.rl_bn_running_update.argtypes = [c_void_p, c_void_p, c_float, c_void_p]
     L.rl_adamw_step.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_long, c_float, c_float, c_float, c_float,
                                 c_float, c_long, c_float, c_void_p]
@@ -64,7 +69,6 @@ class Engine:
         self.n_bnbuf = self.L.rl_plan_num_bn_buffers(h)
         self.ws_bytes = self.L.rl_plan_workspace_bytes(h)
         self.ws = None
-        self.dropout_step = 0
 
     # ------------------------------------------------------------------ plumbing
     def bind(self):
@@ -108,6 +112,35 @@ class Engine:
         off, Ct = self.query(Q_STATS_OFF, level), self.query(Q_CT, level)
         return self._ws_view[off:off + 16 * Ct].view(torch.float64).view(2, Ct)
 
+    def level_acc(self, level):
+        """BatchNorm-backward mean terms of a level: float64 [2, Ct] = (Σ A-terms, Σ B-terms), before the division by N"""
+        off, Ct = self.query(Q_ACC_OFF, level), self.query(Q_CT, level)
+        return self._ws_view[off:off + 16 * Ct].view(torch.float64).view(2, Ct)
+
+    def level_planar(self, level, which):
+        """raw planar view [Ct/16, B, H, W, 16] bf16 of a level's gradient arena ('dact') or activation mirror ('xp')"""
+        off = self.query(Q_DACT_OFF if which == "dact" else Q_XP_OFF, level)
+        Ct, H, W = self.query(Q_CT, level), self.query(Q_H, level), self.query(Q_W, level)
+        n = self.B * H * W * Ct
+        return self._ws_view[off:off + 2 * n].view(torch.bfloat16).view(Ct // 16, self.B, H, W, 16)
+
+    def set_level(self, level, nhwc, which="act"):
+        """write a [B, H, W, Ct] tensor into a level's activation arena (and its planar mirror) or gradient arena"""
+        t = nhwc.to(torch.bfloat16)
+        if which == "act":
+            self.level_view(level).copy_(t)
+            which = "xp"
+        Ct = t.shape[-1]
+        self.level_planar(level, which).copy_(t.view(self.B, t.shape[1], t.shape[2], Ct // 16, 16).permute(3, 0, 1, 2, 4))
+
+    def gstage(self):
+        """float32 [num_params]: raw gradients of the current backward pass (before rl_backward's final scaling)"""
+        off = self.query(Q_GSTAGE_OFF)
+        return self._ws_view[off:off + 4 * self.n_params].view(torch.float32)
+
+    def set_option(self, name, value):
+        _lib.check(self.L.rl_plan_set_option(self.h, name.encode(), int(value)))
+
     def scalars(self):
         """device views: hist int32[8], cm int32[64], (loss_num, loss_den) float64[2], bad_label int32[1]"""
         off = self.query(Q_SCAL_OFF)
@@ -124,31 +157,36 @@ class Engine:
         _need_cuda(params)
         _lib.check(self.L.rl_pack_weights(self.h, _lib.ptr(params), _lib.cur_stream()))
 
-    def set_dropout(self, p_drop, seed=0, step=None):
-        if step is None:
-            step = self.dropout_step
-            self.dropout_step += 1
-        _lib.check(self.L.rl_set_dropout(self.h, float(p_drop), seed, step, _lib.cur_stream()))
+    def set_dropout(self, p_drop, seed=0, step=0):
+        _lib.check(self.L.rl_set_dropout(self.h, float(p_drop), seed & 0xFFFFFFFFFFFFFFFF, step, _lib.cur_stream()))
 
     def forward(self, params, bnbuf, x, train):
         _need_cuda(params, bnbuf, x)
         assert x.dtype == torch.float32 and x.is_contiguous() and tuple(x.shape) == (self.B, 3, self.H, self.W)
         _lib.check(self.L.rl_forward(self.h, _lib.ptr(params), _lib.ptr(bnbuf), _lib.ptr(x), int(train), _lib.cur_stream()))
 
-    def head(self, params, y=None, weighted=False, probs=None, mask=None, backward=0, dprobs=None, grad_scale=1.0,
-             feat_grad_sign=1.0, grads=None, grad_scale_dev=None):
-        _need_cuda(params, y, probs, mask, dprobs, grads, grad_scale_dev)
+    def forward_range(self, params, bnbuf, x, train, lo, hi):
+        _need_cuda(params, bnbuf, x)
+        _lib.check(self.L.rl_forward_range(self.h, _lib.ptr(params), _lib.ptr(bnbuf), _lib.ptr(x), int(train), lo, hi,
+                                           _lib.cur_stream()))
+
+    def head(self, params, y=None, weighted=False, probs=None, mask=None, backward=0, dprobs=None, feat_grad_sign=1.0):
+        _need_cuda(params, y, probs, mask, dprobs)
         y64 = 0
         if y is not None:
             assert y.is_contiguous() and y.dtype in (torch.uint8, torch.int64)
             y64 = int(y.dtype == torch.int64)
         _lib.check(self.L.rl_head(self.h, _lib.ptr(params), _lib.ptr(y), y64, int(weighted), _lib.ptr(probs), _lib.ptr(mask),
-                                  int(backward), _lib.ptr(dprobs), float(grad_scale), _lib.ptr(grad_scale_dev),
-                                  float(feat_grad_sign), _lib.ptr(grads), _lib.cur_stream()))
+                                  int(backward), _lib.ptr(dprobs), float(feat_grad_sign), _lib.cur_stream()))
 
-    def backward(self, params, x, grads):
-        _need_cuda(params, x, grads)
-        _lib.check(self.L.rl_backward(self.h, _lib.ptr(params), _lib.ptr(x), _lib.ptr(grads), _lib.cur_stream()))
+    def backward(self, params, grads, grad_scale=1.0, grad_scale_dev=None):
+        _need_cuda(params, grads, grad_scale_dev)
+        _lib.check(self.L.rl_backward(self.h, _lib.ptr(params), _lib.ptr(grads), float(grad_scale), _lib.ptr(grad_scale_dev),
+                                      _lib.cur_stream()))
+
+    def backward_range(self, params, hi, lo):
+        _need_cuda(params)
+        _lib.check(self.L.rl_backward_range(self.h, _lib.ptr(params), hi, lo, _lib.cur_stream()))
 
     def bn_running_update(self, bnbuf, momentum=0.1):
         _need_cuda(bnbuf)

@@ -37,20 +37,47 @@ def _group_range(rt, group):
 
 
 class _FlatOptimizer(torch.optim.Optimizer):
+    """State lives in flat arenas parallel to the parameter arena; ``self.state[p]`` holds per-parameter VIEWS of them (and
+    a ``step`` tensor) under torch's own key names, so ``state_dict()`` / ``load_state_dict()`` round-trip through
+    Lightning checkpoints and are interchangeable with the stock torch optimizer of the same kind."""
+    STATE_KEYS = ()
+
     def __init__(self, params, defaults):
         super().__init__(params, defaults)
         self.rt = _runtime_of([p for g in self.param_groups for p in g["params"]])
         self._ranges = None
+        self._arena = None
+        self._flat = {}
         self._steps = 0
         self.grad_scale = 1.0   # multiplies the gradients inside the kernel (1/world_size after a summed all-reduce)
+
+    def _all_params(self):
+        return [p for g in self.param_groups for p in g["params"]]
+
+    def _publish_state(self):
+        """(re)create the per-parameter views of the flat state arenas in self.state"""
+        base = self.rt.params.data_ptr()
+        for p in self._all_params():
+            off = (p.data_ptr() - base) // 4
+            st = self.state[p]
+            st["step"] = torch.tensor(float(self._steps))
+            for k in self.STATE_KEYS:
+                st[k] = self._flat[k][off:off + p.numel()].view(p.shape)
 
     def _ensure(self):
         self.rt.flatten()
         self.rt.reattach_grads()
         if self._ranges is None or self._arena is not self.rt.params:
+            old = self._flat if self._arena is not None else {}
             self._arena = self.rt.params
             self._ranges = [_group_range(self.rt, g) for g in self.param_groups]
-            self._alloc_state()
+            self._flat = {}
+            for k in self.STATE_KEYS:
+                t = torch.zeros_like(self.rt.params)
+                if k in old and old[k].numel() == t.numel():   # the arena moved (.to(), .cuda()): the state moves with it
+                    t.copy_(old[k])
+                self._flat[k] = t
+            self._publish_state()
 
     def zero_grad(self, set_to_none=True):
         # gradients live in the flat arena and the kernels accumulate into it: one memset, views stay attached
@@ -58,14 +85,43 @@ class _FlatOptimizer(torch.optim.Optimizer):
         self.rt.reattach_grads()
         self.rt.grads.zero_()
 
+    def _after_step(self):
+        for p in self._all_params():
+            self.state[p]["step"] = torch.tensor(float(self._steps))
+        self.rt.mark_weights_changed()
+
+    def load_state_dict(self, state_dict):
+        super().load_state_dict(state_dict)          # fills self.state[p] with loaded copies (torch's own machinery)
+        loaded = {p: dict(self.state[p]) for p in self._all_params() if p in self.state}
+        self._ranges = None
+        self._arena = None
+        self._ensure()                               # fresh flat arenas + views
+        base = self.rt.params.data_ptr()
+        steps = 0
+        for p, st in loaded.items():
+            off = (p.data_ptr() - base) // 4
+            for k in self.STATE_KEYS:
+                if k in st and st[k] is not None:
+                    self._flat[k][off:off + p.numel()].copy_(st[k].reshape(-1).to(self._flat[k].device, torch.float32))
+            if "step" in st:
+                steps = max(steps, int(float(st["step"])))
+        self._steps = steps
+        self._publish_state()
+
 
 class FusedAdamW(_FlatOptimizer):
+    STATE_KEYS = ("exp_avg", "exp_avg_sq")
+
     def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2):
         super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
 
-    def _alloc_state(self):
-        self.exp_avg = torch.zeros_like(self.rt.params)
-        self.exp_avg_sq = torch.zeros_like(self.rt.params)
+    @property
+    def exp_avg(self):
+        return self._flat["exp_avg"]
+
+    @property
+    def exp_avg_sq(self):
+        return self._flat["exp_avg_sq"]
 
     @torch.no_grad()
     def step(self, closure=None):
@@ -75,18 +131,21 @@ class FusedAdamW(_FlatOptimizer):
         for g, (lo, hi) in zip(self.param_groups, self._ranges):
             engine.adamw_step(self.rt.params[lo:hi], self.rt.grads[lo:hi], self.exp_avg[lo:hi], self.exp_avg_sq[lo:hi],
                               g["lr"], g["betas"][0], g["betas"][1], g["eps"], g["weight_decay"], self._steps, self.grad_scale)
-        self.rt.mark_weights_changed()
+        self._after_step()
         return loss
 
 
 class FusedSGD(_FlatOptimizer):
+    STATE_KEYS = ("momentum_buffer",)
+
     def __init__(self, params, lr=1e-3, momentum=0.9, weight_decay=0.0, nesterov=True):
         if not nesterov or momentum <= 0:
             raise NotImplementedError("FusedSGD implements the reference's configuration: momentum with nesterov=True")
         super().__init__(params, dict(lr=lr, momentum=momentum, weight_decay=weight_decay, nesterov=True))
 
-    def _alloc_state(self):
-        self.momentum_buf = torch.zeros_like(self.rt.params)
+    @property
+    def momentum_buf(self):
+        return self._flat["momentum_buffer"]
 
     @torch.no_grad()
     def step(self, closure=None):
@@ -97,5 +156,5 @@ class FusedSGD(_FlatOptimizer):
         for g, (lo, hi) in zip(self.param_groups, self._ranges):
             engine.sgd_nesterov_step(self.rt.params[lo:hi], self.rt.grads[lo:hi], self.momentum_buf[lo:hi], g["lr"],
                                      g["momentum"], g["weight_decay"], first, self.grad_scale)
-        self.rt.mark_weights_changed()
+        self._after_step()
         return loss

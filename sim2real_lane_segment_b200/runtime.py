@@ -8,9 +8,11 @@
   under autograd, registers one node whose backward runs head-backward + the whole network backward;
 * ``Runtime.fused_loss`` is the SimpleTrainModule.training_step fast path (class-weighted CE computed on device).
 """
+import collections
 import weakref
 
 import torch
+import torch.distributed as dist
 
 from . import _lib, spec
 from .engine import Engine
@@ -45,11 +47,13 @@ class Runtime:
         self.classifier_ref = None
         self.num_cls = 4
         self.params = self.grads = self.bnbuf = None
-        self.engines = {}
+        self.engines = collections.OrderedDict()   # LRU: train / val / tail-batch shapes of a fit loop stay alive
+        self.max_engines = 4
         self.generation = 0
         self.weights_version = 0           # bumped whenever parameter values may have changed
         self.dropout_p = DROP_P
-        self.dropout_seed = 0x5EED
+        self.dropout_seed = None           # None: derived from torch.initial_seed() and the distributed rank at first use
+        self.dropout_step = 0              # one monotonically increasing counter for all plans of this network
         self._anchor = None
         self._counts = []
 
@@ -145,20 +149,33 @@ class Runtime:
         self.weights_version += 1
 
     # ------------------------------------------------------------------ engines
-    def engine_for(self, x, need_grad):
+    def engine_for(self, x, need_grad, train=False):
         B, _, H, W = x.shape
+        if x.device != self.params.device:
+            raise _lib.RightLaneError(f"input on {x.device} but the network lives on {self.params.device}")
         key = (B, H, W, self.num_cls, bool(need_grad), x.device.index)
         eng = self.engines.get(key)
         if eng is None:
-            if len(self.engines) >= 3:   # a plan owns its activation arenas: keep only a few shapes alive
-                self.engines.pop(next(iter(self.engines))).close()
+            while len(self.engines) >= self.max_engines:   # a plan owns its activation arenas: evict the least recently used
+                self.engines.popitem(last=False)[1].close()
             eng = Engine(B, H, W, self.num_cls, training=need_grad, device=x.device).bind()
             eng._packed_version = -1
             self.engines[key] = eng
-        if eng._packed_version != self.weights_version:
+        else:
+            self.engines.move_to_end(key)
+        # Training-mode forwards always repack the bf16 tensor-core operands from the fp32 arena (one 18 us launch), so
+        # ANY in-place parameter update (stock torch optimizers, nn.init, EMA swaps) is picked up; eval-mode forwards
+        # repack when a tracked change happened (fused optimizers, load_state_dict, mark_weights_changed()).
+        if train or eng._packed_version != self.weights_version:
             eng.pack_weights(self.params)
             eng._packed_version = self.weights_version
         return eng
+
+    def _dropout_seed(self):
+        if self.dropout_seed is None:
+            rank = dist.get_rank() if dist.is_available() and dist.is_initialized() else 0
+            self.dropout_seed = (torch.initial_seed() * 0x9E3779B97F4A7C15 + rank * 0xD1B54A32D192ED03 + 0x5EED) & (2 ** 64 - 1)
+        return self.dropout_seed
 
     def _check_generation(self, tok):
         if tok.generation != self.generation:
@@ -171,9 +188,14 @@ class Runtime:
         x = x.contiguous().float()
         train = ex.training
         need_grad = train and torch.is_grad_enabled()
-        eng = self.engine_for(x, need_grad)
+        with torch.cuda.device(x.device):
+            return self._run_extractor(x, train, need_grad)
+
+    def _run_extractor(self, x, train, need_grad):
+        eng = self.engine_for(x, need_grad, train)
         if train:
-            eng.set_dropout(self.dropout_p, self.dropout_seed)
+            eng.set_dropout(self.dropout_p, self._dropout_seed(), self.dropout_step)
+            self.dropout_step += 1
         eng.forward(self.params, self.bnbuf, x, train)
         if train:
             eng.bn_running_update(self.bnbuf, 0.1)
@@ -182,28 +204,37 @@ class Runtime:
         self.generation += 1
         return FeatureToken(self, eng, x, train, self.generation)
 
-    def run_head(self, tok, y=None, weighted=False, want_probs=True, want_mask=False):
+    def run_head(self, tok, y=None, weighted=False, want_probs=True, want_mask=False, backward=0):
+        """fused head; backward=1 (training plans): the same launch also writes d(loss)/d(features) for grad_output 1"""
         self._check_generation(tok)
         eng, x = tok.engine, tok.x
         B, _, H, W = x.shape
         probs = torch.empty(B, self.num_cls, H, W, device=x.device, dtype=torch.float32) if want_probs else None
         mask = torch.empty(B, H, W, device=x.device, dtype=torch.uint8) if want_mask else None
-        eng.head(self.params, y=y, weighted=weighted, probs=probs, mask=mask)
+        with torch.cuda.device(x.device):
+            eng.head(self.params, y=y, weighted=weighted, probs=probs, mask=mask, backward=backward, feat_grad_sign=tok.sign)
         return probs, mask
 
-    def run_backward(self, tok, y=None, weighted=True, dprobs=None, grad_scale=1.0, grad_scale_dev=None):
+    def run_backward(self, tok, y=None, weighted=True, dprobs=None, grad_scale=1.0, grad_scale_dev=None, head_done=False):
         self._check_generation(tok)
         if not tok.engine.training:
             raise _lib.RightLaneError("backward requested for a forward pass that ran without gradient arenas")
         self.reattach_grads()
         eng = tok.engine
-        if dprobs is not None:
-            eng.head(self.params, y=y, weighted=weighted, backward=2, dprobs=dprobs.contiguous().float(),
-                     feat_grad_sign=tok.sign, grads=self.grads)
-        else:
-            eng.head(self.params, y=y, weighted=weighted, backward=1, grad_scale=grad_scale, feat_grad_sign=tok.sign,
-                     grads=self.grads, grad_scale_dev=grad_scale_dev)
-        eng.backward(self.params, tok.x, self.grads)
+        with torch.cuda.device(tok.x.device):
+            if dprobs is not None:
+                eng.head(self.params, y=y, weighted=weighted, backward=2, dprobs=dprobs.contiguous().float(),
+                         feat_grad_sign=tok.sign)
+            elif not head_done:
+                eng.head(self.params, y=y, weighted=weighted, backward=1, feat_grad_sign=tok.sign)
+            eng.backward(self.params, self.grads, grad_scale, grad_scale_dev)
+
+    def check_labels(self, eng):
+        """labels outside [0, num_cls) are excluded from loss, gradient and metrics by the kernels; the reference's
+        cross_entropy raises on them.  Reads the plan's counter (a host sync: call it at epoch ends, not per step)."""
+        bad = int(eng.scalars()[3].item())
+        if bad:
+            raise _lib.RightLaneError(f"{bad} label values outside [0, {self.num_cls}) in the last batch")
 
     def metrics_from_scalars(self, eng):
         """(loss, confusion matrix int64 [C,C]) as device tensors from the plan's scalar block — no host sync"""
@@ -229,21 +260,23 @@ class _ProbsFn(torch.autograd.Function):
 
 
 class _FusedLossFn(torch.autograd.Function):
-    """SimpleTrainModule.training_step (reference SimpleTrain.py:11-25): class-weighted CE on the probabilities."""
+    """SimpleTrainModule.training_step (reference SimpleTrain.py:11-25): class-weighted CE on the probabilities.
+    On a training plan the head runs ONCE: the forward launch already writes d(loss)/d(features) for grad_output 1, and
+    backward() scales the staged gradients by the real grad_output (a device scalar: no host synchronisation)."""
 
     @staticmethod
     def forward(ctx, anchor, tok, y, weighted):
         ctx.tok, ctx.y, ctx.weighted = tok, y, weighted
         rt = tok.rt
-        rt.run_head(tok, y=y, weighted=weighted, want_probs=False)
+        ctx.head_done = bool(tok.engine.training and tok.train)
+        rt.run_head(tok, y=y, weighted=weighted, want_probs=False, backward=1 if ctx.head_done else 0)
         loss, cm = rt.metrics_from_scalars(tok.engine)
         ctx.mark_non_differentiable(cm)
         return loss.clone(), cm.clone()
 
     @staticmethod
     def backward(ctx, dloss, _dcm):
-        # grad_output of the loss (1 unless the caller scales the loss) is read by the head kernel from device
-        # memory, so no host synchronisation happens between forward and backward
         gs = dloss.detach().reshape(1).float().contiguous()
-        ctx.tok.rt.run_backward(ctx.tok, y=ctx.y, weighted=ctx.weighted, grad_scale=1.0, grad_scale_dev=gs)
+        ctx.tok.rt.run_backward(ctx.tok, y=ctx.y, weighted=ctx.weighted, grad_scale=1.0, grad_scale_dev=gs,
+                                head_done=ctx.head_done)
         return None, None, None, None

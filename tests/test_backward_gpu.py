@@ -29,11 +29,13 @@ NEAR_LOSS = ["classifier.finalConv.weight", "classifier.finalConv.bias",
              "featureExtractor.denseBlocksUp.4.layers.4.conv.weight"]
 
 
-def _run_cuda(fx, masks):
+def _run_cuda(fx, masks, options=None):
     B, H, W, C = fx["B"], fx["H"], fx["W"], fx["num_cls"]
     sd = net.init_state_dict(num_cls=C, seed=fx["seed"])
     params, bn = flatten_state_dict(sd, C, "cuda")
     eng = Engine(B, H, W, C, training=True).bind()
+    for k, v in (options or {}).items():
+        eng.set_option(k, v)
     eng.pack_weights(params)
     if masks is not None:
         install_drop_masks(eng, masks)
@@ -41,8 +43,8 @@ def _run_cuda(fx, masks):
     y = fx["y"].cuda()
     grads = torch.zeros_like(params)
     eng.forward(params, bn, x, train=True)
-    eng.head(params, y=y, weighted=True, backward=1, grad_scale=1.0, grads=grads)
-    eng.backward(params, x, grads)
+    eng.head(params, y=y, weighted=True, backward=1)
+    eng.backward(params, grads)
     torch.cuda.synchronize()
     hist, cm, loss, bad = eng.scalars()
     return sd, eng, unflatten_params(grads.cpu(), C), float(loss[0] / loss[1])
@@ -108,27 +110,35 @@ def test_whole_gradient_vs_fp32_oracle_and_autocast_envelope(with_drop):
     assert worst[0][0] < 0.15, worst[:5]
 
 
+def _spread(fx, opt_a, opt_b):
+    """whole-gradient distance between two configurations, next to the run-to-run spread of the second one"""
+    out = [_run_cuda(fx, None, o) for o in (opt_a, opt_b, opt_b)]
+    assert abs(out[0][3] - out[1][3]) < 1e-6
+    cat = lambda d: torch.cat([d[k].reshape(-1) for k in out[0][2]])
+    a, b, b2 = cat(out[0][2]), cat(out[1][2]), cat(out[2][2])
+    return rel_err(a, b), rel_err(b2, b)
+
+
 @pytest.mark.gpu
 def test_planar_activation_mirror_gives_the_same_gradients():
-    """the input-gradient kernels read x either from the NHWC arenas or from the planar mirror the forward pass writes
-    beside them (rl_set_option("xp")): same values, so the gradients agree up to the order of the fp32 atomics"""
-    from sim2real_lane_segment_b200 import _lib
-    L = _lib.lib()
+    """the per-layer input-gradient kernels read x either from the NHWC arenas or from the planar mirror the forward pass
+    writes beside them (plan option "xp"): same values, so the gradients agree up to the order of the fp32 atomics"""
     B, H, W, C = 4, 64, 96, 4
     x, y = steps.synthetic_batch(B, H, W, C, seed=9)
     fx = {"B": B, "H": H, "W": W, "num_cls": C, "seed": 4, "x": x, "y": y.to(torch.uint8)}
-    out = {}
-    try:
-        for run, mode in enumerate((0, 1, 1)):
-            assert L.rl_set_option(b"xp", mode) == 0
-            _, _, g, loss = _run_cuda(fx, None)
-            out[run] = (g, loss)
-    finally:
-        L.rl_set_option(b"xp", 1)
-    # run-to-run spread of two identical runs (bf16 roundings downstream of order-dependent fp32 atomics) sets the scale
-    assert abs(out[0][1] - out[1][1]) < 1e-6
-    cat = lambda d: torch.cat([d[k].reshape(-1) for k in out[0][0]])
-    a, b, b2 = cat(out[0][0]), cat(out[1][0]), cat(out[2][0])
-    d_ab, d_bb = rel_err(a, b), rel_err(b2, b)
+    d_ab, d_bb = _spread(fx, {"xp": 0}, {"xp": 1, "bwd_fused": 0})
     print(f"whole gradient, mirror off vs on: {d_ab:.2e}; on vs on (run-to-run): {d_bb:.2e}")
     assert d_ab <= 3.0 * d_bb + 1e-3
+
+
+@pytest.mark.gpu
+def test_block_fused_backward_matches_the_per_layer_backward():
+    """plan option "bwd_fused": DenseBlocks through dgrad_bulk / wgrad_dense2 vs five per-layer launches.  Same
+    arithmetic up to (i) one bf16 rounding of the block-input gradient per block instead of one per layer and (ii) the
+    m*xhat operand split of the weight gradient, so the two whole gradients differ by bf16-rounding noise only."""
+    B, H, W, C = 4, 64, 96, 4
+    x, y = steps.synthetic_batch(B, H, W, C, seed=9)
+    fx = {"B": B, "H": H, "W": W, "num_cls": C, "seed": 4, "x": x, "y": y.to(torch.uint8)}
+    d_ab, d_bb = _spread(fx, {"bwd_fused": 0}, {"bwd_fused": 1})
+    print(f"whole gradient, per-layer vs block-fused: {d_ab:.2e}; fused vs fused (run-to-run): {d_bb:.2e}")
+    assert d_ab <= 0.06

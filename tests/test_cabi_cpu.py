@@ -115,9 +115,12 @@ def test_argument_errors_of_the_stateless_entry_points(lib):
     lib.rl_overlay.argtypes = [vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp, ctypes.c_int, vp, vp]
     assert lib.rl_overlay(None, 1, 4, 4, 4, 4, None, 0, None, None) == -1
     assert lib.rl_overlay(vp(16), 1, 4, 4, 0, 4, vp(16), 0, vp(16), None) == -2
-    assert lib.rl_set_option(b"no_such_option", 1) == -1
-    assert lib.rl_set_option(b"overlap", 1) == 0 and lib.rl_set_option(b"fwd_tma", 1) == 0
     rc, h = _plan(lib, 1, 64, 64, 4)
+    lib.rl_plan_set_option.argtypes = [vp, ctypes.c_char_p, ctypes.c_int]
+    assert lib.rl_plan_set_option(h, b"no_such_option", 1) == -1
+    assert b"no_such_option" in lib.rl_last_error()
+    for name in (b"overlap", b"fwd_tma", b"xp", b"bwd_fused"):
+        assert lib.rl_plan_set_option(h, name, 1) == 0
     lib.rl_forward.argtypes = [vp, vp, vp, vp, ctypes.c_int, vp]
     assert lib.rl_forward(h, vp(16), vp(16), vp(16), 1, None) != 0                              # plan not bound
     assert b"not bound" in lib.rl_last_error()

@@ -49,8 +49,8 @@ def test_training_step_with_column_strips():
     eng.pack_weights(params)
     grads = torch.zeros_like(params)
     eng.forward(params, bn, x.cuda(), train=True)
-    eng.head(params, y=y.cuda(), weighted=True, backward=1, grads=grads)
-    eng.backward(params, x.cuda(), grads)
+    eng.head(params, y=y.cuda(), weighted=True, backward=1)
+    eng.backward(params, grads)
     torch.cuda.synchronize()
     g = unflatten_params(grads.cpu(), C)
     tr = steps.Trainer({k: v.cuda() for k, v in sd.items()}, num_cls=C)

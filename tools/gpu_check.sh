@@ -1,0 +1,23 @@
+#!/bin/bash
+# One parameterised GPU-box script (replaces the per-experiment scratch scripts of round 1):
+#   tools/gpu_check.sh [tests|ops|bench|launches|all] ...
+# Everything it writes goes to gpurun_out/.
+set -u
+mkdir -p gpurun_out
+for what in "$@"; do
+  case "$what" in
+    ops)      python -m pytest tests/test_ops_gpu.py -x -q -s 2>&1 | tail -150 > gpurun_out/ops.log; tail -40 gpurun_out/ops.log ;;
+    opsall)   python -m pytest tests/test_ops_gpu.py -q 2>&1 | tail -80 > gpurun_out/ops.log; tail -60 gpurun_out/ops.log ;;
+    tests)    python -m pytest tests -m gpu -x -q 2>&1 | tail -60 > gpurun_out/tests.log; tail -30 gpurun_out/tests.log ;;
+    testsall) python -m pytest tests -m gpu -q 2>&1 | tail -120 > gpurun_out/tests.log; tail -60 gpurun_out/tests.log ;;
+    smoke)    python __graft_entry__.py smoke 2>&1 | tail -5 ;;
+    bench)    python bench.py --steps 10 --warmup 3 > gpurun_out/bench.json 2> gpurun_out/bench.err; cat gpurun_out/bench.json; tail -3 gpurun_out/bench.err ;;
+    benchq)   python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench.json 2> gpurun_out/bench.err; cat gpurun_out/bench.json; tail -3 gpurun_out/bench.err ;;
+    perlaunch) python tools/per_launch.py > gpurun_out/per_launch.txt 2>&1; cat gpurun_out/per_launch.txt ;;
+    perlaunch0) BWD_FUSED=0 python tools/per_launch.py > gpurun_out/per_launch_unfused.txt 2>&1; cat gpurun_out/per_launch_unfused.txt ;;
+    launches) python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/plain.log 2>&1 &&
+              ncu --metrics gpu__time_duration.sum --clock-control none -s 1200 -c 400 --csv --log-file gpurun_out/launches.csv \
+                  python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu.log 2>&1; tail -2 gpurun_out/ncu.log ;;
+    *) echo "unknown step $what" ;;
+  esac
+done

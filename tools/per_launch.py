@@ -15,9 +15,13 @@ def step(i):
     opt.zero_grad(); l = m.training_step((x, y), i); l.backward(); opt.step()
 for i in range(3): step(i)
 L = _lib.lib()
-L.rl_set_option(b'overlap', 0)
+for eng in m.runtime().engines.values():
+    eng.set_option("overlap", 0)
+    if os.environ.get("BWD_FUSED") == "0":
+        eng.set_option("bwd_fused", 0)
+step(0)
 L.rl_profile_begin(); step(0)
-msb = (ctypes.c_double * 13)(); lnb = (ctypes.c_long * 13)()
+msb = (ctypes.c_double * bench.NK)(); lnb = (ctypes.c_long * bench.NK)()
 L.rl_profile_end(msb, lnb)
 ms = (ctypes.c_float * 4096)(); cl = (ctypes.c_int * 4096)()
 n = L.rl_profile_launches(ms, cl, 4096)
