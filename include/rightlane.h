@@ -116,9 +116,11 @@ int rl_backward_range(rl_plan* p, const float* params, int layer_hi, int layer_l
 /* running_mean / running_var momentum update of all 60 BatchNorm2d layers from the last training forward */
 int rl_bn_running_update(rl_plan* p, float* bn_buffers, float momentum, void* stream);
 
-/* torch.optim.AdamW step (SimpleTrain.py:28) over a flat arena; step >= 1; grad_scale multiplies g first */
-int rl_adamw_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long n, float lr, float beta1,
-                  float beta2, float eps, float weight_decay, long step, float grad_scale, void* stream);
+/* torch.optim.AdamW step (SimpleTrain.py:28) over a flat arena; step >= 1; grad_scale multiplies g first.  The
+ * hyper-parameters are doubles: 1 - beta, the bias corrections and lr / bias_correction1 are formed in double, as torch
+ * forms them in Python floats, before the fp32 update. */
+int rl_adamw_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long n, double lr, double beta1,
+                  double beta2, double eps, double weight_decay, long step, float grad_scale, void* stream);
 /* torch.optim.SGD(momentum, nesterov=True, weight_decay) step (MMETrainingModule.py:16-19) */
 int rl_sgd_nesterov_step(float* params, const float* grads, float* momentum_buf, long n, float lr, float momentum,
                          float weight_decay, int first_step, float grad_scale, void* stream);

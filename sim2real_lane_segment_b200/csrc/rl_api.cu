@@ -200,6 +200,14 @@ int rl_plan_bind(rl_plan* h, void* workspace, void* stream) {
     int rc = configure_kernels();  // per device: a process may bind plans on several GPUs
     if (rc) return rc;
   }
+  if (p.training)
+    for (int l = 0; l < kLevels; ++l)
+      for (int q = 0; q < kDzBufs; ++q) {
+        const Level& lv = p.lv[l];
+        int rc = encode_dz_tmap(p.tmap_dz[l][q], wsb(&p) + lv.dzp_off + (size_t)q * lv.dzp_npos * 32, lv.dzp_npos, lv.dzp_guard,
+                                lv.W, (long)p.B * (lv.H + 1), bulk_tile_pitch(lv.W));
+        if (rc) return rc;
+      }
   if (p.training && !p.side_stream) {
     cudaStream_t s2;
     RL_CUDA(cudaStreamCreateWithFlags(&s2, cudaStreamNonBlocking));
@@ -414,11 +422,10 @@ int rl_bn_running_update(rl_plan* h, float* bnbuf, float momentum, void* stream)
   return launch_bn_running(&h->p, bnbuf, momentum, (cudaStream_t)stream);
 }
 
-int rl_adamw_step(float* params, const float* grads, float* m, float* v, long n, float lr, float b1, float b2, float eps,
-                  float wd, long step, float grad_scale, void* stream) {
+int rl_adamw_step(float* params, const float* grads, float* m, float* v, long n, double lr, double b1, double b2, double eps,
+                  double wd, long step, float grad_scale, void* stream) {
   if (!params || !grads || !m || !v || n <= 0 || step < 1) return rl_fail(RL_ERR_ARG, "rl_adamw_step: bad argument");
-  const float bc1 = (float)(1.0 - pow((double)b1, (double)step)), bc2 = (float)(1.0 - pow((double)b2, (double)step));
-  return launch_adamw(params, grads, m, v, n, lr, b1, b2, eps, wd, bc1, bc2, grad_scale, (cudaStream_t)stream);
+  return launch_adamw(params, grads, m, v, n, lr, b1, b2, eps, wd, step, grad_scale, (cudaStream_t)stream);
 }
 
 int rl_sgd_nesterov_step(float* params, const float* grads, float* buf, long n, float lr, float momentum, float wd,
@@ -776,7 +783,7 @@ int backward_layer(BwdCtx& c, int li) {
 }
 
 bool block_fusable(const Plan* p, const Block& b) {
-  return p->opt_bwd_fused && p->opt_xp && p->lv[b.lvl].W + 2 <= 165;
+  return p->opt_bwd_fused && p->opt_xp && p->lv[b.lvl].W + 2 <= 165;  // (the chain launches use the un-stripped per-layer kernel)
 }
 
 // a whole DenseBlock: chain over the block's own new channels, one fused kernel for the block input, one batched
@@ -818,7 +825,7 @@ int backward_block(BwdCtx& c, int bi) {
       wl.dz = dzbuf[j];
       wl.Cin = L.cin;
       wl.cs_perm = L.cs_perm;
-      const int g = ((L.cin + 63) / 64 + 2) / 3;
+      const int g = ((L.cin + 63) / 64 + 1) / 2;
       groups_total += g;
       groups_max = std::max(groups_max, g);
     }
@@ -831,8 +838,10 @@ int backward_block(BwdCtx& c, int bi) {
     w.stats = stats_of(p, b.lvl);
     w.Ct = lv.Ct;
     w.inv_n = 1.0 / (double)lv.px;
+    w.acc = acc_of(p, b.lvl);
+    w.C0 = b.C0;
     int nruns;
-    w.px_per_cta = wgrad_px_per_cta(lv.px, std::max(1, sm / std::max(1, groups_total)), &nruns);
+    w.px_per_cta = wgrad_px_per_cta(lv.px, std::max(1, (2 * sm) / std::max(1, groups_total)), &nruns);
     if ((rc = launch_wgrad_dense2(w, nruns, groups_max, c.st2))) return rc;
   }
   if (c.overlap) {
@@ -865,12 +874,19 @@ int backward_block(BwdCtx& c, int bi) {
   g.W = lv.W;
   g.B = p->B;
   g.rmw = b.rmw;
-  g.acc = acc_of(p, b.lvl);
-  const int vrows = p->B * (lv.H + 1);
-  int nruns = std::max(1, std::min(vrows, (2 * sm) / b.ncb));
-  g.vrows_per_cta = (vrows + nruns - 1) / nruns;
-  nruns = (vrows + g.vrows_per_cta - 1) / g.vrows_per_cta;
-  return launch_dgrad_bulk(g, nruns, b.ncb, c.st);
+  g.TP = bulk_tile_pitch(lv.W);
+  const int TR = 128 / g.TP;
+  g.ncolt = (lv.W + g.TP - 3) / (g.TP - 2);
+  g.ntiles = (long)((p->B * (lv.H + 1) + TR - 1) / TR) * g.ncolt;
+  long nruns = std::max(1L, std::min(g.ntiles, (long)(2 * sm) / b.ncb));
+  g.tiles_per_cta = (int)((g.ntiles + nruns - 1) / nruns);
+  nruns = (g.ntiles + g.tiles_per_cta - 1) / g.tiles_per_cta;
+  const void* tmaps[kBlockLayers];
+  for (int j = 0; j < kBlockLayers; ++j) tmaps[j] = p->tmap_dz[b.lvl][j];
+  if ((rc = launch_dgrad_bulk(g, tmaps, (int)nruns, b.ncb, c.st))) return rc;
+  // the block-input channels' mean terms come from the weight-gradient launch: whoever produced those channels runs next
+  if (c.overlap) RL_CUDA(cudaStreamWaitEvent(c.st, (cudaEvent_t)p->ev_blk[b.lvl], 0));
+  return RL_OK;
 }
 
 int backward_range(Plan* p, const float* params, int layer_hi, int layer_lo, cudaStream_t st) {

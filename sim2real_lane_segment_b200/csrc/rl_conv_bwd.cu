@@ -372,13 +372,13 @@ __global__ void __launch_bounds__(128, 3) dgrad_td_kernel(DgradArgs a) {
           bulk_g2s(sW, a.wpk + ((size_t)mb * nkc + kc) * 16384, wbytes, &bar_full[s]);
         }
         ld.store(sB, rowptr, ck / 8, nullptr, nullptr);
+        fence_proxy_async();  // before the next loads are issued (the fence waits for outstanding memory operations)
         if (kc + 1 < nkc) {
           const __nv_bfloat16* rp[4];
 #pragma unroll
           for (int i = 0; i < 4; ++i) rp[i] = rowptr[i] ? rowptr[i] + (kc + 1) * 64 : nullptr;
           ld.load(rp, min(8, (a.Kdz - (kc + 1) * 64) / 8));
         }
-        fence_proxy_async();
         __syncthreads();
         if (tid == 0) {
           mbar_wait(&bar_full[s], u & 1);
@@ -575,12 +575,13 @@ __global__ void __launch_bounds__(kWgThreads, 2) wgrad_kernel(WgradArgs a) {
         *reinterpret_cast<uint4*>(sA + ((size_t)j * 64 + a_row) * 16) = o;
       }
     }
+    // fence BEFORE the next global loads are issued: fence.proxy.async waits for the thread's outstanding memory operations
+    cp_async_wait<1>();  // B(k) has landed (B(k+1) may still be in flight)
+    fence_proxy_async();
     // stage (k+2)%3 == (k-1)%3 is recycled for chunk k+2 once the MMAs of chunk k-1 have retired
     if (k >= 1) mbar_wait(&bar_done[(k - 1) % 3], ((k - 1) / 3) & 1);
     load_a(k + 2, r);
     issue_b(k + 2, stage_base + ((k + 2) % 3) * kStageBytes + 16384);
-    cp_async_wait<2>();  // B(k) has landed (B(k+1), B(k+2) may still be in flight)
-    fence_proxy_async();
     __syncthreads();
     if (tid == 0) {
       tc_fence_after();

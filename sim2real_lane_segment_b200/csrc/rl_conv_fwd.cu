@@ -150,14 +150,14 @@ __global__ void __launch_bounds__(kFwdThreads, 2) dense_fwd_kernel(DenseFwdArgs 
         const uint32_t s = g & 1, u = g >> 1;
         if (u > 0) mbar_wait(&bar_done[s], (u - 1) & 1);
         ld.store(stage_base + s * kStageBytes, rowptr, ck / 8, s_s + kc * 64, s_t + kc * 64);
+        fence_proxy_async();  // before the next loads are issued (the fence waits for outstanding memory operations)
+        mbar_arrive(&bar_ready[s]);
         if (kc + 1 < nkc) {  // prefetch the next chunk while this one is consumed
           const __nv_bfloat16* rp[4];
 #pragma unroll
           for (int i = 0; i < 4; ++i) rp[i] = rowptr[i] ? rowptr[i] + (kc + 1) * 64 : nullptr;
           ld.load(rp, min(8, (a.Cin - (kc + 1) * 64) / 8));
         }
-        fence_proxy_async();
-        mbar_arrive(&bar_ready[s]);
       }
       // first chunk of the next tile streams in behind this tile's epilogue
       if (tile + 1 < ntiles) {
@@ -813,13 +813,13 @@ __global__ void __launch_bounds__(128, 2) gemm_px_kernel(GemmPxArgs a) {
         bulk_g2s(sW, wpart + (size_t)kc * stageB, wbytes, &bar_full[s]);
       }
       ld.store(sA, rowptr, ck / 8, a.transform ? s_s + kc * 64 : nullptr, s_t + kc * 64);
+      fence_proxy_async();  // before the next loads are issued (the fence waits for outstanding memory operations)
       if (kc + 1 < nkc) {
         const __nv_bfloat16* rp[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) rp[i] = rowptr[i] ? rowptr[i] + (kc + 1) * 64 : nullptr;
         ld.load(rp, min(8, (a.K - (kc + 1) * 64) / 8));
       }
-      fence_proxy_async();
       __syncthreads();
       if (tid == 0) {
         mbar_wait(&bar_full[s], u & 1);

@@ -118,11 +118,16 @@ struct DgradBulkArgs {
   __nv_bfloat16* dact;           // planar gradient arena
   long npx;
   int C0, cbs;                   // block-input channels, channel-block size
-  int H, W, B, vrows_per_cta;
+  int H, W, B;
+  int TP, ncolt;                 // tile pitch (8 / 16 / 32: TR = 128 / TP rows x TP - 2 columns per tile), tiles per row of tiles
+  long ntiles;
+  int tiles_per_cta;
   int rmw;
-  double* acc;                   // level accumulators A at [c], B at [Ct + c]
 };
-int launch_dgrad_bulk(const DgradBulkArgs& a, int nruns, int ncb, cudaStream_t st);
+// tmaps[j]: 128-byte CUtensorMap blob of layer j's dz planes (encode_dz_tmap)
+int launch_dgrad_bulk(const DgradBulkArgs& a, const void* const* tmaps, int nruns, int ncb, cudaStream_t st);
+int encode_dz_tmap(void* tmap_out, const void* plane0, long npos, long guard, int W, long nvrows, int TP);
+inline int bulk_tile_pitch(int W) { return W + 2 <= 8 ? 8 : (W + 2 <= 16 ? 16 : 32); }
 
 // Weight gradients of the (up to five) DenseLayers of a block in one launch (grid.z = layer), plus dγ / dβ of their
 // BatchNorms.  For 64 channels at a time two operands are built from x: m·x̂ and m (m = relu mask), so with
@@ -148,6 +153,8 @@ struct WgDenseArgs {
   int Ct;
   double inv_n;
   long px_per_cta;
+  double* acc;                   // level accumulators (A at [c], B at [Ct + c]); channels below C0 receive the layers' mean terms
+  int C0;
 };
 int launch_wgrad_dense2(const WgDenseArgs& a, int nruns, int ngroups, cudaStream_t st);
 // once per device / plan bind: opt the kernels into their dynamic shared-memory sizes
@@ -218,8 +225,8 @@ struct BnTabEntry {
   float inv_n, unbias;  // 1/N, N/(N-1)
 };
 int launch_bn_running(const Plan* p, float* bnbuf, float momentum, cudaStream_t st);
-int launch_adamw(float* p, const float* g, float* m, float* v, long n, float lr, float b1, float b2, float eps, float wd,
-                 float bc1, float bc2, float grad_scale, cudaStream_t st);
+int launch_adamw(float* p, const float* g, float* m, float* v, long n, double lr, double b1, double b2, double eps, double wd,
+                 long step, float grad_scale, cudaStream_t st);
 int launch_sgd_nesterov(float* p, const float* g, float* buf, long n, float lr, float momentum, float wd, int first,
                         float grad_scale, cudaStream_t st);
 int launch_fill_masks(float* masks, long n, float p_drop, unsigned long long seed, unsigned long long step, cudaStream_t st);

@@ -949,15 +949,16 @@ int launch_bn_running(const Plan* p, float* bnbuf, float momentum, cudaStream_t 
 // ================================================================================================
 // optimizers over the flat parameter arena (reference SimpleTrain.py:28 AdamW; MMETrainingModule.py:16-19 SGD)
 // ================================================================================================
+// (1 - beta), the decay factor, the step size and 1/sqrt(bias correction 2) are formed in double on the host, as
+// torch.optim.AdamW forms them in Python floats, and only then rounded to fp32
 __global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
-                                                    float* __restrict__ v, long n, float lr, float b1, float b2, float eps,
-                                                    float wd, float bc1, float bc2, float gs) {
-  const float step_size = lr / bc1, inv_sqrt_bc2 = rsqrtf(bc2);
+                                                    float* __restrict__ v, long n, float decay, float b1, float b2, float eps,
+                                                    float omb1, float omb2, float step_size, float inv_sqrt_bc2, float gs) {
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
     const float gi = g[i] * gs;
-    float pi = p[i] * (1.f - lr * wd);
-    const float mi = b1 * m[i] + (1.f - b1) * gi;
-    const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+    float pi = p[i] * decay;
+    const float mi = fmaf(b1, m[i], omb1 * gi);
+    const float vi = fmaf(b2, v[i], omb2 * gi * gi);
     const float denom = sqrtf(vi) * inv_sqrt_bc2 + eps;
     pi -= step_size * (mi / denom);
     p[i] = pi;
@@ -966,11 +967,13 @@ __global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, const
   }
 }
 
-int launch_adamw(float* p, const float* g, float* m, float* v, long n, float lr, float b1, float b2, float eps, float wd,
-                 float bc1, float bc2, float grad_scale, cudaStream_t st) {
+int launch_adamw(float* p, const float* g, float* m, float* v, long n, double lr, double b1, double b2, double eps, double wd,
+                 long step, float grad_scale, cudaStream_t st) {
   int grid = (int)std::min<long>((n + 255) / 256, 148L * 8);
+  const double bc1 = 1.0 - pow(b1, (double)step), bc2 = 1.0 - pow(b2, (double)step);
   { ProfScope _ps(KC_OPT, st);
-  adamw_kernel<<<grid, 256, 0, st>>>(p, g, m, v, n, lr, b1, b2, eps, wd, bc1, bc2, grad_scale); }
+  adamw_kernel<<<grid, 256, 0, st>>>(p, g, m, v, n, (float)(1.0 - lr * wd), (float)b1, (float)b2, (float)eps, (float)(1.0 - b1),
+                                     (float)(1.0 - b2), (float)(lr / bc1), (float)(1.0 / sqrt(bc2)), grad_scale); }
   RL_CUDA(cudaGetLastError());
   return RL_OK;
 }

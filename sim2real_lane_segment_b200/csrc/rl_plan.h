@@ -108,6 +108,7 @@ struct Plan {
   size_t ws_bytes;
   void* ws;                           // bound workspace (device)
   alignas(64) unsigned char tmap_act[6][128];  // CUtensorMap per level arena: [pixels][Ct] bf16, box 128 px x 64 ch, 128-byte swizzle
+  alignas(64) unsigned char tmap_dz[kLevels][kDzBufs][128];  // CUtensorMap per padded dz16 buffer (dgrad_bulk_kernel halo tiles)
   bool tmap_ok;
   size_t gstage_off;                  // training: fp32 [n_params] raw gradients of one backward pass (scaled into `grads` at its end)
   void* side_stream;                  // cudaStream_t: weight gradients run here, concurrently with the input-gradient chain

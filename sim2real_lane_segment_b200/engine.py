@@ -41,8 +41,8 @@ def _sigs(L):
     L.rl_backward_range.argtypes = [c_void_p, c_void_p, c_int, c_int, c_void_p]
     L.rl_plan_set_option.argtypes = [c_void_p, ctypes.c_char_p, c_int]
     L.rl_bn_running_update.argtypes = [c_void_p, c_void_p, c_float, c_void_p]
-    L.rl_adamw_step.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_long, c_float, c_float, c_float, c_float,
-                                c_float, c_long, c_float, c_void_p]
+    L.rl_adamw_step.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_long, ctypes.c_double, ctypes.c_double,
+                                ctypes.c_double, ctypes.c_double, ctypes.c_double, c_long, c_float, c_void_p]
     L.rl_sgd_nesterov_step.argtypes = [c_void_p, c_void_p, c_void_p, c_long, c_float, c_float, c_float, c_int, c_float,
                                        c_void_p]
     _SIGS_DONE = True

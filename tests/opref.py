@@ -155,8 +155,11 @@ def dense_block_bwd(x, dX, sums, n, acc, layers, C0, rmw_from_last, fused):
         k = (L["gamma"].float() * rstd).double()                                       # γ·rstd
         contrib = g * k
         if fused:
-            a_op = bf16r(torch.where(m, xh32, torch.zeros_like(xh32))).double()         # m·x̂ operand
+            # operand pair of wgrad_dense2: m·(x - c) with c = bf16(mean) (rounded to bf16), and m;  x̂ = r·(x - c) - r·(mean - c)
+            cc = bf16r(mean)
+            d_op = bf16r(x[..., :cin].float() - cc).double()
             m_op = m.double()
+            a_op = m_op * (rstd.double() * d_op - (rstd * (mean - cc)).double())
             dgamma = (G * a_op).sum((0, 1, 2))
             dbeta = (G * m_op).sum((0, 1, 2))
             dw = conv_w_grad(a_op, dz) * L["gamma"].double()[None, :, None, None] + \
@@ -185,9 +188,10 @@ def dense_block_bwd(x, dX, sums, n, acc, layers, C0, rmw_from_last, fused):
             dX[..., :cin] = bf16r((base + contrib).float()).double()
         out["layers"][j] = dict(dgamma=dgamma, dbeta=dbeta, dw=dw, dbias=dbias, dz=dz)
     if fused:
-        xh0 = torch.addcmul(-mean[:C0] * rstd[:C0], x[..., :C0].float(), rstd[:C0]).double()
-        acc[0, :C0] += delta.sum((0, 1, 2))
-        acc[1, :C0] += (delta * xh0).sum((0, 1, 2))
+        for j in range(5):   # Σ_p Δ = Σ_j γ_j r·dβ_j and Σ_p Δ·x̂ = Σ_j γ_j r·dγ_j: added by the weight-gradient kernel
+            kj = (layers[j]["gamma"].float()[:C0] * rstd[:C0]).double()
+            acc[0, :C0] += kj * out["layers"][j]["dbeta"][:C0]
+            acc[1, :C0] += kj * out["layers"][j]["dgamma"][:C0]
         base = dX[..., :C0] if rmw_from_last == 0 else torch.zeros_like(delta)
         dX[..., :C0] = bf16r((base + delta).float()).double()
     out["dX"], out["acc"] = dX, acc

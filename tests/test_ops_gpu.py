@@ -90,6 +90,9 @@ class Net:
 
 def check_bf16(ours, ref64, what, frac_ok=0.999, norm_tol=2e-3):
     u = R.bf16_ulps(ours, ref64)
+    # elements far below the tensor's scale (saturated softmax gradients ~1e-20 ...) are held to an absolute bound instead
+    floor = 1e-6 * float(ref64.abs().max())
+    u = torch.where((ours.double() - ref64.double()).abs() <= floor, torch.zeros_like(u), u)
     within = float((u <= 1.0).double().mean())
     e = R.rel(ours, R.bf16r(ref64.float()))
     print(f"{what}: {100 * within:.4f}% within 1 bf16 spacing, max {float(u.max()):.2f}, norm rel err vs rounded ref {e:.2e}")

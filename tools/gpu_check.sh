@@ -7,7 +7,7 @@ mkdir -p gpurun_out
 for what in "$@"; do
   case "$what" in
     ops)      python -m pytest tests/test_ops_gpu.py -x -q -s 2>&1 | tail -150 > gpurun_out/ops.log; tail -40 gpurun_out/ops.log ;;
-    opsall)   python -m pytest tests/test_ops_gpu.py -q 2>&1 | tail -80 > gpurun_out/ops.log; tail -60 gpurun_out/ops.log ;;
+    opsall)   python -m pytest tests/test_ops_gpu.py -q -rP 2>&1 > gpurun_out/ops.log; grep -E "^(PASSED|FAILED|ERROR)|rel err|within|passed|failed|differ" gpurun_out/ops.log | tail -220 ;;
     tests)    python -m pytest tests -m gpu -x -q 2>&1 | tail -60 > gpurun_out/tests.log; tail -30 gpurun_out/tests.log ;;
     testsall) python -m pytest tests -m gpu -q 2>&1 | tail -120 > gpurun_out/tests.log; tail -60 gpurun_out/tests.log ;;
     smoke)    python __graft_entry__.py smoke 2>&1 | tail -5 ;;
@@ -18,6 +18,10 @@ for what in "$@"; do
     launches) python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/plain.log 2>&1 &&
               ncu --metrics gpu__time_duration.sum --clock-control none -s 1200 -c 400 --csv --log-file gpurun_out/launches.csv \
                   python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu.log 2>&1; tail -2 gpurun_out/ncu.log ;;
+    ncu:*)    k="${what#ncu:}"   # one launch of kernel regex k (first occurrence after 3 warm-up steps) with the full metric set
+              python tools/one_step.py > gpurun_out/plain_one_step.log 2>&1 &&
+              ncu --set full --clock-control none --import-source on -k "regex:$k" -s ${NCU_SKIP:-0} -c 1 -f -o "gpurun_out/prof_$k" \
+                  python tools/one_step.py > "gpurun_out/ncu_$k.log" 2>&1; tail -3 "gpurun_out/ncu_$k.log" ;;
     *) echo "unknown step $what" ;;
   esac
 done
