@@ -80,6 +80,10 @@ int rl_pack_weights(rl_plan* p, const float* params, void* stream);
 /* nn.Dropout2d(0.2) keep-scales (models/FCDenseNet/layers.py:12,51) for all layers: p_drop = 0 writes 1.0 everywhere
  * (eval / parity runs); tests may overwrite the per-layer float[B][cout] blocks (RL_Q_LAYER_MASK_OFF). */
 int rl_set_dropout(rl_plan* p, float p_drop, unsigned long long seed, unsigned long long step, void* stream);
+/* the same with the step counter read from device memory (step + *step_dev): the launch holds no host state that changes
+ * between steps, so it can be part of a captured CUDA graph of the whole training step */
+int rl_set_dropout_dev(rl_plan* p, float p_drop, unsigned long long seed, unsigned long long step, const long long* step_dev,
+                       void* stream);
 
 /* FCDenseNetFeatureExtractor.forward without the final F.normalize (tiramisu.py:89-103): x fp32 [B,3,H,W] ->
  * level-0 arena (288 channels).  train != 0: BatchNorm uses batch statistics (and they are retained for
@@ -108,6 +112,12 @@ int rl_head(rl_plan* p, const float* params, const void* y, int y_is_i64, int we
  * (grad_scale_dev: the loss's grad_output as a device scalar, read without a host sync).
  * Requires rl_forward(train=1) and rl_head(backward != 0) on the same plan. */
 int rl_backward(rl_plan* p, const float* params, float* grads, float grad_scale, const float* grad_scale_dev, void* stream);
+/* The three pieces rl_backward is made of, for callers that interleave the pass with other work (data-parallel training
+ * fires the all-reduce of a parameter range as soon as the layers that own it are done, ddp.py):
+ *   rl_backward_begin: clears the BatchNorm-backward accumulators;  rl_backward_range: see below;
+ *   rl_grad_accum: grads[lo:hi) += grad_scale * (grad_scale_dev ? *grad_scale_dev : 1) * stage[lo:hi)  (float offsets). */
+int rl_backward_begin(rl_plan* p, void* stream);
+int rl_grad_accum(rl_plan* p, float* grads, long lo, long hi, float grad_scale, const float* grad_scale_dev, void* stream);
 /* backward of layers layer_hi..layer_lo only (descending; layer_hi = RL_Q_NUM_LAYERS adds the classifier weight
  * gradient), from whatever the gradient arenas hold, into the gradient stage; no clearing, no final scaling: the
  * per-layer / per-DenseBlock entry point the parity tests use (autograd of layers.py:5-69 one module at a time). */
@@ -121,6 +131,10 @@ int rl_bn_running_update(rl_plan* p, float* bn_buffers, float momentum, void* st
  * forms them in Python floats, before the fp32 update. */
 int rl_adamw_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long n, double lr, double beta1,
                   double beta2, double eps, double weight_decay, long step, float grad_scale, void* stream);
+/* the same update with the hyper-parameters in device memory, hyper_dev = double[6] {lr, beta1, beta2, eps, weight_decay, step}:
+ * graph-capturable (the learning-rate schedule and the step counter change between replays without re-capturing) */
+int rl_adamw_step_dev(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long n, const double* hyper_dev,
+                      float grad_scale, void* stream);
 /* torch.optim.SGD(momentum, nesterov=True, weight_decay) step (MMETrainingModule.py:16-19) */
 int rl_sgd_nesterov_step(float* params, const float* grads, float* momentum_buf, long n, float lr, float momentum,
                          float weight_decay, int first_step, float grad_scale, void* stream);

@@ -236,10 +236,15 @@ int rl_pack_weights(rl_plan* h, const float* params, void* stream) {
 }
 
 int rl_set_dropout(rl_plan* h, float p_drop, unsigned long long seed, unsigned long long step, void* stream) {
+  return rl_set_dropout_dev(h, p_drop, seed, step, nullptr, stream);
+}
+
+int rl_set_dropout_dev(rl_plan* h, float p_drop, unsigned long long seed, unsigned long long step, const long long* step_dev,
+                       void* stream) {
   if (!h || !h->p.ws) return rl_fail(RL_ERR_STATE, "rl_set_dropout: plan not bound");
   if (p_drop < 0.f || p_drop >= 1.f) return rl_fail(RL_ERR_ARG, "rl_set_dropout: p_drop %f out of range", p_drop);
   return launch_fill_masks((float*)(wsb(&h->p) + h->p.mask_off_all), (long)(h->p.mask_bytes / sizeof(float)), p_drop, seed,
-                           step, (cudaStream_t)stream);
+                           step, step_dev, (cudaStream_t)stream);
 }
 
 }  // extern "C"
@@ -426,6 +431,12 @@ int rl_adamw_step(float* params, const float* grads, float* m, float* v, long n,
                   double wd, long step, float grad_scale, void* stream) {
   if (!params || !grads || !m || !v || n <= 0 || step < 1) return rl_fail(RL_ERR_ARG, "rl_adamw_step: bad argument");
   return launch_adamw(params, grads, m, v, n, lr, b1, b2, eps, wd, step, grad_scale, (cudaStream_t)stream);
+}
+
+int rl_adamw_step_dev(float* params, const float* grads, float* m, float* v, long n, const double* hyper_dev, float grad_scale,
+                      void* stream) {
+  if (!params || !grads || !m || !v || !hyper_dev || n <= 0) return rl_fail(RL_ERR_ARG, "rl_adamw_step_dev: bad argument");
+  return launch_adamw_dev(params, grads, m, v, n, hyper_dev, grad_scale, (cudaStream_t)stream);
 }
 
 int rl_sgd_nesterov_step(float* params, const float* grads, float* buf, long n, float lr, float momentum, float wd,
@@ -939,17 +950,30 @@ extern "C" int rl_backward_range(rl_plan* h, const float* params, int layer_hi, 
   return backward_range(p, params, layer_hi, layer_lo, (cudaStream_t)stream);
 }
 
-extern "C" int rl_backward(rl_plan* h, const float* params, float* grads, float grad_scale, const float* grad_scale_dev,
-                           void* stream) {
+extern "C" int rl_backward_begin(rl_plan* h, void* stream) {
   if (!h || !h->p.ws) return rl_fail(RL_ERR_STATE, "rl_backward: plan not bound");
   Plan* p = &h->p;
   if (!p->training) return rl_fail(RL_ERR_STATE, "rl_backward: plan was created without training arenas");
+  RL_CUDA(cudaMemsetAsync(wsb(p) + p->acc_off_all, 0, p->acc_bytes, (cudaStream_t)stream));
+  return RL_OK;
+}
+
+extern "C" int rl_grad_accum(rl_plan* h, float* grads, long lo, long hi, float grad_scale, const float* grad_scale_dev, void* stream) {
+  if (!h || !h->p.ws) return rl_fail(RL_ERR_STATE, "rl_grad_accum: plan not bound");
+  Plan* p = &h->p;
+  if (!p->training || !grads) return rl_fail(RL_ERR_STATE, "rl_grad_accum: needs a training plan and a gradient arena");
+  if (lo < 0 || hi > p->n_params || lo >= hi) return rl_fail(RL_ERR_ARG, "rl_grad_accum: bad range [%ld, %ld)", lo, hi);
+  return launch_grad_accum(grads + lo, gstage_of(p) + lo, hi - lo, grad_scale, grad_scale_dev, (cudaStream_t)stream);
+}
+
+extern "C" int rl_backward(rl_plan* h, const float* params, float* grads, float grad_scale, const float* grad_scale_dev,
+                           void* stream) {
   if (!params || !grads) return rl_fail(RL_ERR_ARG, "rl_backward: null argument");
-  cudaStream_t st = (cudaStream_t)stream;
-  RL_CUDA(cudaMemsetAsync(wsb(p) + p->acc_off_all, 0, p->acc_bytes, st));
-  int rc = backward_range(p, params, (int)p->layers.size(), 0, st);
+  int rc = rl_backward_begin(h, stream);
   if (rc) return rc;
-  return launch_grad_accum(grads, gstage_of(p), p->n_params, grad_scale, grad_scale_dev, st);
+  Plan* p = &h->p;
+  if ((rc = backward_range(p, params, (int)p->layers.size(), 0, (cudaStream_t)stream))) return rc;
+  return rl_grad_accum(h, grads, 0, p->n_params, grad_scale, grad_scale_dev, stream);
 }
 
 extern "C" int rl_plan_set_option(rl_plan* h, const char* name, int value) {

@@ -229,7 +229,9 @@ int launch_adamw(float* p, const float* g, float* m, float* v, long n, double lr
                  long step, float grad_scale, cudaStream_t st);
 int launch_sgd_nesterov(float* p, const float* g, float* buf, long n, float lr, float momentum, float wd, int first,
                         float grad_scale, cudaStream_t st);
-int launch_fill_masks(float* masks, long n, float p_drop, unsigned long long seed, unsigned long long step, cudaStream_t st);
+int launch_fill_masks(float* masks, long n, float p_drop, unsigned long long seed, unsigned long long step,
+                      const long long* step_dev, cudaStream_t st);
+int launch_adamw_dev(float* p, const float* g, float* m, float* v, long n, const double* hyper, float grad_scale, cudaStream_t st);
 // grads[i] += scale * (*scale_dev) * stage[i]   (end of a backward pass; scale_dev may be null)
 int launch_grad_accum(float* grads, const float* stage, long n, float scale, const float* scale_dev, cudaStream_t st);
 

@@ -967,6 +967,34 @@ __global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, const
   }
 }
 
+// the same update with every hyper-parameter read from device memory: hyper = double[6] {lr, beta1, beta2, eps, weight_decay,
+// step}; nothing of the launch depends on host state, so a captured CUDA graph stays valid while lr and step change
+__global__ void __launch_bounds__(256) adamw_dev_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                                        float* __restrict__ v, long n, const double* __restrict__ hyper, float gs) {
+  const double lr = hyper[0], b1 = hyper[1], b2 = hyper[2], eps = hyper[3], wd = hyper[4], step = hyper[5];
+  const double bc1 = 1.0 - pow(b1, step), bc2 = 1.0 - pow(b2, step);
+  const float decay = (float)(1.0 - lr * wd), fb1 = (float)b1, fb2 = (float)b2, feps = (float)eps, omb1 = (float)(1.0 - b1),
+              omb2 = (float)(1.0 - b2), step_size = (float)(lr / bc1), inv_sqrt_bc2 = (float)(1.0 / sqrt(bc2));
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    const float gi = g[i] * gs;
+    float pi = p[i] * decay;
+    const float mi = fmaf(fb1, m[i], omb1 * gi);
+    const float vi = fmaf(fb2, v[i], omb2 * gi * gi);
+    const float denom = sqrtf(vi) * inv_sqrt_bc2 + feps;
+    pi -= step_size * (mi / denom);
+    p[i] = pi;
+    m[i] = mi;
+    v[i] = vi;
+  }
+}
+int launch_adamw_dev(float* p, const float* g, float* m, float* v, long n, const double* hyper, float grad_scale, cudaStream_t st) {
+  int grid = (int)std::min<long>((n + 255) / 256, 148L * 8);
+  { ProfScope _ps(KC_OPT, st);
+  adamw_dev_kernel<<<grid, 256, 0, st>>>(p, g, m, v, n, hyper, grad_scale); }
+  RL_CUDA(cudaGetLastError());
+  return RL_OK;
+}
+
 int launch_adamw(float* p, const float* g, float* m, float* v, long n, double lr, double b1, double b2, double eps, double wd,
                  long step, float grad_scale, cudaStream_t st) {
   int grid = (int)std::min<long>((n + 255) / 256, 148L * 8);
@@ -1022,17 +1050,20 @@ __device__ __forceinline__ unsigned long long splitmix64(unsigned long long x) {
   x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
   return x ^ (x >> 31);
 }
-__global__ void fill_masks_kernel(float* masks, long n, float p_drop, unsigned long long seed, unsigned long long step) {
+__global__ void fill_masks_kernel(float* masks, long n, float p_drop, unsigned long long seed, unsigned long long step,
+                                  const long long* step_dev) {
+  if (step_dev != nullptr) step += (unsigned long long)*step_dev;  // device-side step counter: the launch can live in a CUDA graph
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
     unsigned long long h = splitmix64(splitmix64(seed ^ (step * 0xD1B54A32D192ED03ull)) + (unsigned long long)i);
     float u = (float)(h >> 40) * (1.0f / 16777216.0f);
     masks[i] = (u >= p_drop) ? 1.0f / (1.0f - p_drop) : 0.f;
   }
 }
-int launch_fill_masks(float* masks, long n, float p_drop, unsigned long long seed, unsigned long long step, cudaStream_t st) {
+int launch_fill_masks(float* masks, long n, float p_drop, unsigned long long seed, unsigned long long step,
+                      const long long* step_dev, cudaStream_t st) {
   int grid = (int)std::min<long>((n + 255) / 256, 148L * 4);
   { ProfScope _ps(KC_MISC, st);
-  fill_masks_kernel<<<grid, 256, 0, st>>>(masks, n, p_drop, seed, step); }
+  fill_masks_kernel<<<grid, 256, 0, st>>>(masks, n, p_drop, seed, step, step_dev); }
   RL_CUDA(cudaGetLastError());
   return RL_OK;
 }

@@ -24,11 +24,25 @@ def bucket_ranges(n, n_buckets):
 
 
 class GradSync:
+    """NCCL all-reduce (SUM) of the flat gradient arena.  Attached to a runtime (`rt.grad_sync = GradSync()`), the backward
+    pass fires the all-reduce of a parameter range as soon as the layers that own it are done (`reduce_ranges`, called by
+    `Runtime.run_backward` after each of the three backward segments), so the exchange runs under the rest of backward;
+    `finish()` is called right before the optimizer step."""
+    collective = "ncclAllReduce(sum) over 3 arena buckets, issued from inside backward (up path, deep down path, shallow down path)"
+
     def __init__(self, group=None, n_buckets=3):
         self.group = group
         self.n_buckets = n_buckets
         self.handles = []
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+
+    def reduce_ranges(self, flat_grads, ranges):
+        """async all-reduce of the given [lo, hi) float ranges; ordered after everything enqueued on the current stream"""
+        if self.world == 1:
+            return
+        for lo, hi in ranges:
+            if hi > lo:
+                self.handles.append(dist.all_reduce(flat_grads[lo:hi], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
 
     def start(self, flat_grads):
         """launch the all-reduces (SUM); returns immediately"""

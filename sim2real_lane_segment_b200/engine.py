@@ -33,12 +33,16 @@ def _sigs(L):
     L.rl_plan_query.argtypes = [c_void_p, c_int, c_int, POINTER(c_long)]
     L.rl_pack_weights.argtypes = [c_void_p, c_void_p, c_void_p]
     L.rl_set_dropout.argtypes = [c_void_p, c_float, c_ulonglong, c_ulonglong, c_void_p]
+    L.rl_set_dropout_dev.argtypes = [c_void_p, c_float, c_ulonglong, c_ulonglong, c_void_p, c_void_p]
+    L.rl_adamw_step_dev.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_long, c_void_p, c_float, c_void_p]
     L.rl_forward.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p]
     L.rl_forward_range.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]
     L.rl_head.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_float,
                           c_void_p]
     L.rl_backward.argtypes = [c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_void_p]
     L.rl_backward_range.argtypes = [c_void_p, c_void_p, c_int, c_int, c_void_p]
+    L.rl_backward_begin.argtypes = [c_void_p, c_void_p]
+    L.rl_grad_accum.argtypes = [c_void_p, c_void_p, c_long, c_long, c_float, c_void_p, c_void_p]
     L.rl_plan_set_option.argtypes = [c_void_p, ctypes.c_char_p, c_int]
     L.rl_bn_running_update.argtypes = [c_void_p, c_void_p, c_float, c_void_p]
     L.rl_adamw_step.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_long, ctypes.c_double, ctypes.c_double,
@@ -157,8 +161,10 @@ class Engine:
         _need_cuda(params)
         _lib.check(self.L.rl_pack_weights(self.h, _lib.ptr(params), _lib.cur_stream()))
 
-    def set_dropout(self, p_drop, seed=0, step=0):
-        _lib.check(self.L.rl_set_dropout(self.h, float(p_drop), seed & 0xFFFFFFFFFFFFFFFF, step, _lib.cur_stream()))
+    def set_dropout(self, p_drop, seed=0, step=0, step_dev=None):
+        """step_dev: optional int64 device scalar added to `step` inside the kernel (graph-capturable step counter)"""
+        _lib.check(self.L.rl_set_dropout_dev(self.h, float(p_drop), seed & 0xFFFFFFFFFFFFFFFF, step, _lib.ptr(step_dev),
+                                             _lib.cur_stream()))
 
     def forward(self, params, bnbuf, x, train):
         _need_cuda(params, bnbuf, x)
@@ -188,6 +194,37 @@ class Engine:
         _need_cuda(params)
         _lib.check(self.L.rl_backward_range(self.h, _lib.ptr(params), hi, lo, _lib.cur_stream()))
 
+    def backward_begin(self):
+        _lib.check(self.L.rl_backward_begin(self.h, _lib.cur_stream()))
+
+    def grad_accum(self, grads, lo, hi, grad_scale=1.0, grad_scale_dev=None):
+        _need_cuda(grads, grad_scale_dev)
+        _lib.check(self.L.rl_grad_accum(self.h, _lib.ptr(grads), lo, hi, float(grad_scale), _lib.ptr(grad_scale_dev),
+                                        _lib.cur_stream()))
+
+    def backward_segments(self):
+        """Three segments of the backward pass in the order they complete, each with the parameter-arena ranges whose
+        gradients are final once it has run: [(layer_hi, layer_lo, [(lo, hi), ...]), ...] — up path + classifier first,
+        then bottleneck + deep down path, then the shallow down path + first conv."""
+        if getattr(self, "_segments", None) is None:
+            n = self.query(Q_NUM_LAYERS)
+            types = [self.query(Q_LAYER_TYPE, i) for i in range(n)]
+
+            def start(i):   # first float of layer i's parameters (BatchNorm weight where the layer has one, else conv weight)
+                g = self.query(Q_LAYER_PARAM_GAMMA, i)
+                return g if g >= 0 else self.query(Q_LAYER_PARAM_W, i)
+            tds = [i for i, t in enumerate(types) if t == 2]
+            tus = [i for i, t in enumerate(types) if t == 3]
+            first_tu, bott = tus[0], tds[-1] + 1
+            down2 = tds[1] + 1                       # first layer of the level-2 down block
+            self._segments = [
+                (n, first_tu, [(start(first_tu), self.n_params)]),
+                (first_tu - 1, down2, [(start(down2), start(tds[0])), (start(tds[2]), start(first_tu))]),
+                (down2 - 1, 0, [(0, start(down2)), (start(tds[0]), start(tds[2]))]),
+            ]
+            assert bott > down2
+        return self._segments
+
     def bn_running_update(self, bnbuf, momentum=0.1):
         _need_cuda(bnbuf)
         _lib.check(self.L.rl_bn_running_update(self.h, _lib.ptr(bnbuf), float(momentum), _lib.cur_stream()))
@@ -199,6 +236,16 @@ def adamw_step(params, grads, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, weight
     _need_cuda(params, grads, exp_avg, exp_avg_sq)
     _lib.check(L.rl_adamw_step(_lib.ptr(params), _lib.ptr(grads), _lib.ptr(exp_avg), _lib.ptr(exp_avg_sq), params.numel(),
                                lr, beta1, beta2, eps, weight_decay, int(step), grad_scale, _lib.cur_stream()))
+
+
+def adamw_step_dev(params, grads, exp_avg, exp_avg_sq, hyper_dev, grad_scale=1.0):
+    """hyper_dev: float64 device tensor [lr, beta1, beta2, eps, weight_decay, step]"""
+    L = _lib.lib()
+    _sigs(L)
+    _need_cuda(params, grads, exp_avg, exp_avg_sq, hyper_dev)
+    assert hyper_dev.dtype == torch.float64 and hyper_dev.numel() == 6
+    _lib.check(L.rl_adamw_step_dev(_lib.ptr(params), _lib.ptr(grads), _lib.ptr(exp_avg), _lib.ptr(exp_avg_sq), params.numel(),
+                                   _lib.ptr(hyper_dev), grad_scale, _lib.cur_stream()))
 
 
 def sgd_nesterov_step(params, grads, buf, lr, momentum, weight_decay, first_step, grad_scale=1.0):

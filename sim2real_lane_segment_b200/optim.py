@@ -86,8 +86,9 @@ class _FlatOptimizer(torch.optim.Optimizer):
         self.rt.grads.zero_()
 
     def _after_step(self):
-        for p in self._all_params():
-            self.state[p]["step"] = torch.tensor(float(self._steps))
+        if not torch.cuda.is_current_stream_capturing():
+            for p in self._all_params():
+                self.state[p]["step"] = torch.tensor(float(self._steps))
         self.rt.mark_weights_changed()
 
     def load_state_dict(self, state_dict):
@@ -123,14 +124,40 @@ class FusedAdamW(_FlatOptimizer):
     def exp_avg_sq(self):
         return self._flat["exp_avg_sq"]
 
+    # ---- CUDA-graph mode: lr / betas / eps / weight_decay / step live in device memory, so a captured step stays valid
+    # while the scheduler changes lr and the step counter advances (graphs.GraphedTrainStep)
+    def enable_device_hyper(self):
+        self._ensure()
+        dev = self.rt.params.device
+        self._hyper_host = [self._hyper_values(g) for g in self.param_groups]
+        self._hyper = [torch.tensor(h + [float(self._steps)], dtype=torch.float64, device=dev) for h in self._hyper_host]
+
+    @staticmethod
+    def _hyper_values(g):
+        return [float(g["lr"]), float(g["betas"][0]), float(g["betas"][1]), float(g["eps"]), float(g["weight_decay"])]
+
+    def sync_hyper(self):
+        """push changed hyper-parameters (learning-rate schedule) to the device copies; call before replaying a graph"""
+        for i, g in enumerate(self.param_groups):
+            h = self._hyper_values(g)
+            if h != self._hyper_host[i]:
+                self._hyper[i][:5].copy_(torch.tensor(h, dtype=torch.float64))
+                self._hyper_host[i] = h
+
     @torch.no_grad()
     def step(self, closure=None):
         loss = closure() if closure is not None else None
         self._ensure()
         self._steps += 1
-        for g, (lo, hi) in zip(self.param_groups, self._ranges):
-            engine.adamw_step(self.rt.params[lo:hi], self.rt.grads[lo:hi], self.exp_avg[lo:hi], self.exp_avg_sq[lo:hi],
-                              g["lr"], g["betas"][0], g["betas"][1], g["eps"], g["weight_decay"], self._steps, self.grad_scale)
+        if getattr(self, "_hyper", None) is not None:
+            for h, (lo, hi) in zip(self._hyper, self._ranges):
+                h[5:6] += 1.0                                   # device-side step counter (captured with the step)
+                engine.adamw_step_dev(self.rt.params[lo:hi], self.rt.grads[lo:hi], self.exp_avg[lo:hi],
+                                      self.exp_avg_sq[lo:hi], h, self.grad_scale)
+        else:
+            for g, (lo, hi) in zip(self.param_groups, self._ranges):
+                engine.adamw_step(self.rt.params[lo:hi], self.rt.grads[lo:hi], self.exp_avg[lo:hi], self.exp_avg_sq[lo:hi],
+                                  g["lr"], g["betas"][0], g["betas"][1], g["eps"], g["weight_decay"], self._steps, self.grad_scale)
         self._after_step()
         return loss
 

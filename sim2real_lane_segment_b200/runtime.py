@@ -56,6 +56,8 @@ class Runtime:
         self.dropout_step = 0              # one monotonically increasing counter for all plans of this network
         self._anchor = None
         self._counts = []
+        self.grad_sync = None              # ddp.GradSync: all-reduce buckets fired from inside the backward pass
+        self._drop_step_dev = None         # int64 device scalar: dropout step counter (device side: graph-capturable)
 
     # ------------------------------------------------------------------ flat arenas
     def attach_classifier(self, classifier):
@@ -194,7 +196,12 @@ class Runtime:
     def _run_extractor(self, x, train, need_grad):
         eng = self.engine_for(x, need_grad, train)
         if train:
-            eng.set_dropout(self.dropout_p, self._dropout_seed(), self.dropout_step)
+            # the step counter lives on the device (one in-place add per step), so a captured CUDA graph of the step draws
+            # fresh Dropout2d masks at every replay
+            if self._drop_step_dev is None or self._drop_step_dev.device != x.device:
+                self._drop_step_dev = torch.full((1,), self.dropout_step, dtype=torch.int64, device=x.device)
+            eng.set_dropout(self.dropout_p, self._dropout_seed(), 0, step_dev=self._drop_step_dev)
+            self._drop_step_dev += 1
             self.dropout_step += 1
         eng.forward(self.params, self.bnbuf, x, train)
         if train:
@@ -227,7 +234,15 @@ class Runtime:
                          feat_grad_sign=tok.sign)
             elif not head_done:
                 eng.head(self.params, y=y, weighted=weighted, backward=1, feat_grad_sign=tok.sign)
-            eng.backward(self.params, self.grads, grad_scale, grad_scale_dev)
+            if self.grad_sync is None or self.grad_sync.world == 1:
+                eng.backward(self.params, self.grads, grad_scale, grad_scale_dev)
+            else:   # data parallel: each segment's parameter ranges are final when it returns -> their all-reduce starts now
+                eng.backward_begin()
+                for hi, lo, ranges in eng.backward_segments():
+                    eng.backward_range(self.params, hi, lo)
+                    for a, b in ranges:
+                        eng.grad_accum(self.grads, a, b, grad_scale, grad_scale_dev)
+                    self.grad_sync.reduce_ranges(self.grads, ranges)
 
     def check_labels(self, eng):
         """labels outside [0, num_cls) are excluded from loss, gradient and metrics by the kernels; the reference's

@@ -112,20 +112,43 @@ class TrainingBase(LightningModule):
         self.log('test_dice', logs['dice'])
         self.log('test_iou', logs['iou'])
 
-    def evaluate_batch(self, batch, return_predictions=False):
+    EVAL_CHUNK_PIXELS = 32 * 480 * 640   # largest slice of a batch that goes through one plan (activation arenas ~12 GB)
+
+    def evaluate_batch(self, batch, return_predictions=False, return_probs=None):
+        """TrainingBase.evaluate_batch (TrainingBase.py:79-95) / the test.py loop body (test.py:93-101).  Large batches
+        (test.py's 256 x 3 x 480 x 640) run through the plan in slices along the batch axis; loss sums and the confusion
+        matrix are integer / linear in the slices, so the metrics of the whole batch are exactly those of one pass."""
         x, y = batch
         rt = self.runtime()
+        B = x.shape[0]
+        if return_probs is None:
+            return_probs = return_predictions       # masks + confusion matrix only: return_predictions=True, return_probs=False
+        per = max(1, self.EVAL_CHUNK_PIXELS // (x.shape[2] * x.shape[3]))
+        n_slices = (B + per - 1) // per
+        per = (B + n_slices - 1) // n_slices          # equal slices: one plan shape (plus at most one tail shape)
+        loss_sums, cm = None, None
+        probs_l, mask_l = [], []
         with torch.no_grad():
-            tok = self.featureExtractor(x)
-            probs, mask = rt.run_head(tok, y=y.contiguous(), weighted=False, want_probs=return_predictions,
-                                      want_mask=return_predictions)
-            loss, cm = rt.metrics_from_scalars(tok.engine)
-            loss, cm = loss.clone(), cm.clone()
+            for b0 in range(0, B, per):
+                xs, ys = x[b0:b0 + per], y[b0:b0 + per].contiguous()
+                tok = self.featureExtractor(xs)
+                probs, mask = rt.run_head(tok, y=ys, weighted=False, want_probs=return_probs, want_mask=return_predictions)
+                hist, cmi, ls, bad = tok.engine.scalars()
+                C = self.num_cls
+                loss_sums = ls.clone() if loss_sums is None else loss_sums + ls
+                cmi = cmi[:C * C].view(C, C).long()
+                cm = cmi.clone() if cm is None else cm + cmi
+                if return_predictions:
+                    probs_l.append(probs)
+                    mask_l.append(mask)
+        loss = (loss_sums[0] / loss_sums[1]).float()
         acc, dice, iou = metrics_from_confusion(cm)
-        weight = x.shape[0]
+        weight = B
         out = {'loss': loss * weight, 'acc': acc * weight, 'dice': dice * weight, 'iou': iou * weight, 'weight': weight}
         if return_predictions:
-            out.update(probs=probs, labels_hat=mask, confusion_matrix=cm)
+            out.update(labels_hat=mask_l[0] if len(mask_l) == 1 else torch.cat(mask_l), confusion_matrix=cm)
+            if return_probs:
+                out.update(probs=probs_l[0] if len(probs_l) == 1 else torch.cat(probs_l))
         return out
 
     @staticmethod

@@ -1,0 +1,123 @@
+"""Whole-step CUDA graph (include/rightlane.h promises capturability) and the overlapped data-parallel gradient exchange."""
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+from oracle import fcdensenet as net
+from oracle import steps
+from tests.util import rel_err
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _module(seed, dropout_p):
+    from sim2real_lane_segment_b200.trainingModules import SimpleTrainModule
+    m = SimpleTrainModule(lr=1e-3, decay=1e-4, lrRatio=1e3, num_cls=4)
+    m.load_state_dict(net.init_state_dict(num_cls=4, seed=seed))
+    m = m.cuda().train()
+    m.runtime().dropout_p = dropout_p
+    (opt,), (sched,) = m.configure_optimizers()
+    return m, opt, sched
+
+
+def test_graphed_training_step_matches_eager():
+    """zero_grad -> training_step -> backward -> AdamW captured as ONE CUDA graph and replayed on fresh batches equals the
+    eager step sequence (dropout off: the only run-to-run differences are the fp32 atomics of the weight gradients)"""
+    from sim2real_lane_segment_b200.graphs import GraphedTrainStep
+    B, H, W = 4, 64, 96
+    batches = [steps.synthetic_batch(B, H, W, 4, seed=20 + i) for i in range(6)]
+    batches = [(x.cuda(), y.cuda()) for x, y in batches]
+    m1, o1, s1 = _module(3, 0.0)
+    eager = []
+    for i, (x, y) in enumerate(batches):
+        if i == 4:
+            s1.step()                      # a learning-rate change between steps must reach the graph too
+        o1.zero_grad()
+        loss = m1.training_step((x, y), i)
+        loss.backward()
+        o1.step()
+        eager.append(float(loss))
+    m2, o2, s2 = _module(3, 0.0)
+    snap = {k: v.clone() for k, v in m2.state_dict().items()}
+    g = GraphedTrainStep(m2, o2, *batches[0], warmup=1)
+    # the warm-up step trained on batch 0: rewind the network and the optimizer to the initial state before comparing
+    m2.load_state_dict(snap)
+    o2.exp_avg.zero_(); o2.exp_avg_sq.zero_(); o2._steps = 0
+    for h in o2._hyper:
+        h[5] = 0.0
+    graphed = []
+    for i, (x, y) in enumerate(batches):
+        if i == 4:
+            s2.step()
+        graphed.append(float(g(x, y)))
+    torch.cuda.synchronize()
+    print("eager  ", eager)
+    print("graphed", graphed)
+    for a, b in zip(eager, graphed):
+        assert abs(a - b) < 5e-3 * max(1.0, abs(a)), (eager, graphed)
+    e = rel_err(m2.runtime().params, m1.runtime().params)
+    print(f"parameters after 6 steps, graphed vs eager: rel diff {e:.2e}")
+    # AdamW divides by sqrt(v): parameters whose gradient is at the fp32-atomics noise level move by +-lr per step in either
+    # run, so the parameter vectors agree to a fraction of 6 * lr / |w| only; the losses above are the functional check
+    assert e < 2e-2
+    assert o2._steps == o1._steps == 6
+    assert rel_err(o2.exp_avg_sq, o1.exp_avg_sq) < 5e-2
+
+
+def test_graph_replays_draw_fresh_dropout_masks():
+    from sim2real_lane_segment_b200.graphs import GraphedTrainStep
+    B, H, W = 2, 64, 64
+    x, y = steps.synthetic_batch(B, H, W, 4, seed=1)
+    m, o, _ = _module(1, 0.2)
+    g = GraphedTrainStep(m, o, x.cuda(), y.cuda(), warmup=1)
+    eng = next(iter(m.runtime().engines.values()))
+    seen = []
+    for _ in range(3):
+        g(x.cuda(), y.cuda())
+        torch.cuda.synchronize()
+        seen.append(torch.cat([eng.layer_mask_view(i).reshape(-1) for i in (1, 6, 40)]).clone())
+    assert not torch.equal(seen[0], seen[1]) and not torch.equal(seen[1], seen[2])
+    for s in seen:
+        assert 0.6 < float((s > 0).float().mean()) < 0.95
+
+
+def test_fused_optimizer_state_dict_roundtrip():
+    """optimizer.state_dict() / load_state_dict() carry the moments and the step (resume from a Lightning checkpoint);
+    the state is interchangeable with torch.optim.AdamW's"""
+    B, H, W = 2, 64, 64
+    x, y = steps.synthetic_batch(B, H, W, 4, seed=2)
+    x, y = x.cuda(), y.cuda()
+    m1, o1, _ = _module(5, 0.0)
+    for i in range(3):
+        o1.zero_grad(); m1.training_step((x, y), i).backward(); o1.step()
+    sd = o1.state_dict()
+    assert len(sd["state"]) == len(list(m1.parameters()))
+    st0 = sd["state"][0]
+    assert set(st0) >= {"step", "exp_avg", "exp_avg_sq"} and float(st0["step"]) == 3.0
+    m2, o2, _ = _module(5, 0.0)
+    m2.load_state_dict(m1.state_dict())
+    m2.prepare()
+    o2.load_state_dict(sd)
+    assert o2._steps == 3
+    assert torch.equal(o2.exp_avg, o1.exp_avg) and torch.equal(o2.exp_avg_sq, o1.exp_avg_sq)
+    for o, m in ((o1, m1), (o2, m2)):
+        o.zero_grad(); m.training_step((x, y), 3).backward(); o.step()
+    assert rel_err(m2.runtime().params, m1.runtime().params) < 1e-5
+    ref = torch.optim.AdamW(m1.parameters(), lr=1e-3, weight_decay=1e-4)   # same state layout as the stock optimizer
+    ref.load_state_dict(o1.state_dict())
+    assert float(ref.state[next(iter(m1.parameters()))]["step"]) == 4.0
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_overlapped_allreduce_two_ranks_nccl():
+    """2 ranks, NCCL: the gradients after the overlapped exchange equal g_rank0 + g_rank1 of the same batches without
+    exchange (plain BatchNorm: statistics stay local per rank, as under the reference's DDP)"""
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr",
+                        "127.0.0.1", "--master-port", str(29600 + os.getpid() % 300), os.path.join(ROOT, "tools", "ddp_check.py")],
+                       capture_output=True, text=True, timeout=600, cwd=ROOT)
+    print(r.stdout[-2000:], r.stderr[-2000:])
+    assert r.returncode == 0 and "ddp_check ok" in r.stdout

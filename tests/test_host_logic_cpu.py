@@ -76,6 +76,12 @@ def _worker(rank, world, port, n):
     want = torch.arange(n, dtype=torch.float32) * sum(range(1, world + 1))
     assert scale == 1.0 / world
     assert torch.equal(g, want)
+    # the ranges the backward pass fires while it is still running (Engine.backward_segments): async, awaited by finish()
+    g2 = torch.arange(n, dtype=torch.float32) * (rank + 1)
+    sync.reduce_ranges(g2, [(n // 2, n)])
+    sync.reduce_ranges(g2, [(0, n // 4), (n // 4, n // 2)])
+    assert sync.finish() == 1.0 / world
+    assert torch.equal(g2, want)
     buf = torch.full((10,), float(rank))
     cnt = [torch.tensor(rank * 5)]
     ddp.broadcast_buffers(buf, cnt)
@@ -86,6 +92,27 @@ def _worker(rank, world, port, n):
 def test_gradient_exchange_world_size_2_gloo():
     port = 29500 + os.getpid() % 2000
     mp.spawn(_worker, args=(2, port, 100003), nprocs=2, join=True)
+
+
+def test_backward_segments_partition_the_parameter_arena():
+    """the three all-reduce buckets (up path + classifier, deep down path, shallow down path) cover every parameter
+    exactly once and the segments walk the layer list from the classifier down to the first conv"""
+    from sim2real_lane_segment_b200.engine import Engine
+    eng = Engine(2, 120, 160, 4, training=True)      # host-side plan only: no device work before bind()
+    segs = eng.backward_segments()
+    n = eng.query(0)
+    assert segs[0][0] == n and segs[-1][1] == 0
+    for (h0, l0, _), (h1, l1, _) in zip(segs, segs[1:]):
+        assert h1 == l0 - 1
+    ranges = sorted(r for _, _, rs in segs for r in rs)
+    assert ranges[0][0] == 0 and ranges[-1][1] == eng.n_params
+    for (a0, b0), (a1, b1) in zip(ranges, ranges[1:]):
+        assert b0 == a1 and b0 > a0
+    pl, _, _, npar, _ = spec.layout(4)
+    up_start = pl["featureExtractor.transUpBlocks.0.convTrans.weight"][0]
+    assert segs[0][2] == [(up_start, npar)]
+    assert segs[2][2][0] == (0, pl["featureExtractor.denseBlocksDown.2.layers.0.norm.weight"][0])
+    eng.close()
 
 
 def test_checkpoint_roundtrip_has_lightning_121_layout(tmp_path):

@@ -13,6 +13,11 @@ for what in "$@"; do
     smoke)    python __graft_entry__.py smoke 2>&1 | tail -5 ;;
     bench)    python bench.py --steps 10 --warmup 3 > gpurun_out/bench.json 2> gpurun_out/bench.err; cat gpurun_out/bench.json; tail -3 gpurun_out/bench.err ;;
     benchq)   python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench.json 2> gpurun_out/bench.err; cat gpurun_out/bench.json; tail -3 gpurun_out/bench.err ;;
+    infer)    python bench.py --workload infer --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/bench_infer.json 2> gpurun_out/bench_infer.err; cat gpurun_out/bench_infer.json; tail -3 gpurun_out/bench_infer.err ;;
+    mme)      python bench.py --workload mme --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench_mme.json 2> gpurun_out/bench_mme.err; cat gpurun_out/bench_mme.json; tail -3 gpurun_out/bench_mme.err ;;
+    nograph)  python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-graph > gpurun_out/bench_nograph.json 2> gpurun_out/bench_nograph.err; cat gpurun_out/bench_nograph.json; tail -3 gpurun_out/bench_nograph.err ;;
+    bar)      for a in "train" "train --graph" "infer"; do python tools/stock_torch_bar.py $a 2>&1 | tail -1; done | tee gpurun_out/stock_torch_bar.jsonl ;;
+    graphtests) python -m pytest tests/test_graph_ddp_gpu.py -q -x -rP 2>&1 | tail -40 ;;
     perlaunch) python tools/per_launch.py > gpurun_out/per_launch.txt 2>&1; cat gpurun_out/per_launch.txt ;;
     perlaunch0) BWD_FUSED=0 python tools/per_launch.py > gpurun_out/per_launch_unfused.txt 2>&1; cat gpurun_out/per_launch_unfused.txt ;;
     launches) python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/plain.log 2>&1 &&
