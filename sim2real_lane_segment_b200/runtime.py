@@ -56,6 +56,7 @@ class Runtime:
         self.dropout_step = 0              # one monotonically increasing counter for all plans of this network
         self._anchor = None
         self._counts = []
+        self.dropout_mask_hook = None      # callable(engine) run after the Dropout2d keep-scales of a step have been drawn
         self.grad_sync = None              # ddp.GradSync: all-reduce buckets fired from inside the backward pass
         self._drop_step_dev = None         # int64 device scalar: dropout step counter (device side: graph-capturable)
 
@@ -203,6 +204,8 @@ class Runtime:
             eng.set_dropout(self.dropout_p, self._dropout_seed(), 0, step_dev=self._drop_step_dev)
             self._drop_step_dev += 1
             self.dropout_step += 1
+            if self.dropout_mask_hook is not None:     # parity tests inject the keep masks torch drew for the oracle
+                self.dropout_mask_hook(eng)
         eng.forward(self.params, self.bnbuf, x, train)
         if train:
             eng.bn_running_update(self.bnbuf, 0.1)
