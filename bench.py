@@ -352,10 +352,23 @@ def run_b200(args, rank, world, local_rank):
             opt.step()
             return loss
         step_fn = eager_step
-        if world == 1 and not args.no_graph:
-            graphed = GraphedTrainStep(model, opt, *devb[0], warmup=3)
-            graph_note = "whole step (zero_grad, forward, head+loss, backward, AdamW) replayed as ONE CUDA graph"
-            step_fn = lambda batch, i: graphed(batch[0], batch[1])
+        if not args.no_graph:
+            ok = True
+            try:
+                graphed = GraphedTrainStep(model, opt, *devb[0], warmup=3)
+            except Exception as e:                    # (a capture the NCCL build refuses: stay eager on every rank)
+                ok, graphed = False, None
+                sys.stderr.write(f"rank {rank}: CUDA-graph capture failed ({type(e).__name__}: {str(e)[:200]}); eager steps\n")
+            if world > 1:
+                flag = torch.tensor([1 if ok else 0], device=dev)
+                dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+                if int(flag) == 0:
+                    graphed = None
+            if graphed is not None:
+                graph_note = ("whole step (zero_grad, forward, head+loss, backward, AdamW) replayed as ONE CUDA graph" if world == 1 else
+                              "step replayed as FOUR CUDA graphs (forward + up-path backward | deep down path | shallow down path | "
+                              "AdamW) with the NCCL all-reduce of each finished parameter range launched between them")
+                step_fn = lambda batch, i: graphed(batch[0], batch[1])
         prof_step = eager_step
         h2d, d2h = B * 3 * H * W * 4 + B * H * W * 8, 4
         fetch = lambda out: result_host.copy_(out.detach().reshape(1), non_blocking=True)

@@ -24,20 +24,32 @@ m.runtime().dropout_p = 0.0
 rt = m.runtime()
 x, y = steps.synthetic_batch(B, H, W, C, seed=50 + rank)
 x, y = x.cuda(), y.cuda()
-opt.zero_grad()
-m.training_step((x, y), 0).backward()
-local_g = rt.grads.clone()
-want = local_g.clone()
-dist.all_reduce(want)                                   # reference exchange: one plain all-reduce after backward
+def local_then_plain_allreduce(i):
+    opt.zero_grad()
+    m.training_step((x, y), i).backward()
+    g = rt.grads.clone()
+    tot = g.clone()
+    dist.all_reduce(tot)                                # reference exchange: one plain all-reduce after backward
+    return g, tot
+
+
+local_g, want = local_then_plain_allreduce(0)
+_, want2 = local_then_plain_allreduce(1)                # run-to-run spread of the same computation (fp32 atomics upstream of
+noise = float((want2 - want).norm() / want.norm())      # bf16 roundings): the scale against which "equal" is judged
 rt.grad_sync = ddp.GradSync()
 opt.zero_grad()
-m.training_step((x, y), 1).backward()                   # buckets are all-reduced while backward is still running
+m.training_step((x, y), 2).backward()                   # buckets are all-reduced while backward is still running
 scale = rt.grad_sync.finish()
 torch.cuda.synchronize()
 err = float((rt.grads - want).norm() / want.norm())
 loc = float((rt.grads - local_g).norm() / local_g.norm())
-print(f"rank {rank}: overlapped vs plain all-reduce rel diff {err:.2e} (vs local gradient {loc:.2e}), scale {scale}")
-assert scale == 1.0 / world and err < 1e-4 and loc > 1e-2
+print(f"rank {rank}: overlapped vs plain all-reduce rel diff {err:.2e} (run-to-run spread of the plain exchange {noise:.2e}; "
+      f"vs this rank's local gradient {loc:.2e}), scale {scale}")
+assert scale == 1.0 / world and err < 3.0 * noise + 1e-5 and loc > 1e-2
+# every rank holds the same summed gradient
+chk = rt.grads.clone()
+dist.broadcast(chk, 0)
+assert torch.equal(chk, rt.grads)
 dist.barrier()
 if rank == 0:
     print("ddp_check ok")
