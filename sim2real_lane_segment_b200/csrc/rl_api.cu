@@ -24,6 +24,7 @@ int configure_kernels() {
   int rc;
   if ((rc = configure_fwd_kernels())) return rc;
   if ((rc = configure_bwd_kernels())) return rc;
+  if ((rc = configure_tu_kernels())) return rc;
   return configure_fused_kernels();
 }
 }
@@ -157,7 +158,7 @@ int rl_plan_bind(rl_plan* h, void* workspace, void* stream) {
       e.kind = 2; e.dst_off = (long)L.wpk_fwd; e.n16 = (long)nkc * 8 * L.cin; pk.push_back(e);
       e.kind = 3; e.dst_off = (long)L.wpk_bwd; e.n16 = (long)nmb * nkc * 8 * 128; pk.push_back(e);
     } else if (L.type == L_TU) {
-      e.kind = 4; e.dst_off = (long)L.wpk_fwd; e.n16 = 3L * 2 * 8 * 240; pk.push_back(e);
+      e.kind = 8; e.dst_off = (long)L.wpk_fwd; e.n16 = 9L * 10 * 80; pk.push_back(e);
       e.kind = 5; e.dst_off = (long)L.wpk_bwd; e.n16 = 12L * 8 * 80; pk.push_back(e);
     }
     if (L.type == L_DENSE && p.training) {
@@ -326,32 +327,29 @@ static int forward_layer(Plan* p, int li, const float* params, const float* bnbu
     if ((rc = launch_gemm_px(a, gx, nparts, st))) return rc;
     if (train && (rc = launch_channel_stats(act_of(p, L.lvl_out), lo.px, lo.Ct, 0, L.cout, stats_of(p, L.lvl_out), sm, st)))
       return rc;
-  } else {  // L_TU
-    GemmPxArgs a;
+  } else {  // L_TU: all four output parities of a tile of low-resolution positions in one kernel (rl_tu.cu)
+    TuFwdArgs a;
     memset(&a, 0, sizeof(a));
     a.A = act_of(p, L.lvl_in);
     a.lda = lin.Ct;
     a.a_off = L.in_off;
-    a.K = kUpCh;
-    a.M = lin.px;
-    a.ntiles = (lin.px + 127) / 128;
-    a.mode = GEMM_LINEAR;
-    a.transform = 0;
+    a.B = p->B;
+    a.h = lin.H;
+    a.w = lin.W;
+    a.H = lo.H;
+    a.W = lo.W;
     a.wpk = wsb(p) + L.wpk_fwd;
-    a.N = 720;
-    for (int q = 0; q < 3; ++q) {
-      a.part_n0[q] = q * 240;
-      a.part_np[q] = 240;
-    }
-    a.out = (__nv_bfloat16*)(wsb(p) + p->tmp_off);
-    a.ldo = 720;
-    a.o_off = 0;
-    int gx = (int)std::max(1L, std::min(a.ntiles, (long)(2 * sm) / 3));
-    if ((rc = launch_gemm_px(a, gx, 3, st))) return rc;
-    if ((rc = launch_tu_col2im((const __nv_bfloat16*)(wsb(p) + p->tmp_off), act_of(p, L.lvl_out),
-                               train ? xp_of(p, L.lvl_out) : nullptr, params + L.p_b, p->B, lin.H, lin.W, lo.H, lo.W, lo.Ct,
-                               L.out_off, st)))
-      return rc;
+    a.bias = params + L.p_b;
+    a.out = act_of(p, L.lvl_out);
+    a.ldo = lo.Ct;
+    a.o_off = L.out_off;
+    a.out_xp = train ? xp_of(p, L.lvl_out) : nullptr;
+    a.npx_out = lo.px;
+    a.TP = tu_tile_pitch(lin.W);
+    const int TR = 128 / a.TP;
+    a.ncolt = (lin.W + 1 + a.TP - 2) / (a.TP - 1);
+    a.ntiles = (long)((p->B * (lin.H + 1) + TR - 1) / TR) * a.ncolt;
+    if ((rc = launch_tu_fwd(a, (int)std::max(1L, std::min(a.ntiles, (long)sm)), st))) return rc;
     if (train && (rc = launch_channel_stats(act_of(p, L.lvl_out), lo.px, lo.Ct, L.out_off, kUpCh, stats_of(p, L.lvl_out), sm, st)))
       return rc;
   }

@@ -295,7 +295,7 @@ __global__ void __launch_bounds__(kFwdThreads, 2) dense_fwd_kernel(DenseFwdArgs 
 //                while the other roles are already on tile i+1.
 // Requires a full-width strip (W <= 160): the 128 input pixels of a tile are then 128 consecutive arena rows.
 // ================================================================================================
-constexpr int kF2Threads = 320;
+constexpr int kF2Threads = 448;  // warps 0-3 transform, 4-7 + 10-13 epilogue, 8 MMA issue, 9 activation TMA
 constexpr int kF2A = 6, kF2W = 3;  // maximum activation ring depth; weight ring depth in streaming mode
 constexpr int kF2ABytes = 16384, kF2WBytes = 18432;
 constexpr size_t kF2Cap = 224 * 1024;
@@ -308,7 +308,7 @@ struct alignas(64) DenseFwdTmaArgs {
   int strip_mode;  // 0: full-width rows through a 2-D map; 1: 128-column strips through a 3-D map (ch, x, row)
 };
 
-__device__ __forceinline__ void epilogue_sync() { asm volatile("bar.sync 2, 128;" ::: "memory"); }
+__device__ __forceinline__ void epilogue_sync(int group) { asm volatile("bar.sync %0, 128;" ::"r"(2 + group) : "memory"); }
 
 __global__ void __launch_bounds__(kF2Threads, 1) dense_fwd_tma_kernel(const __grid_constant__ DenseFwdTmaArgs P) {
   const DenseFwdArgs& a = P.a;
@@ -325,7 +325,7 @@ __global__ void __launch_bounds__(kF2Threads, 1) dense_fwd_tma_kernel(const __gr
   // a_full: TMA bytes landed; a_ready: 128 transform threads done; a_empty: the MMAs reading the stage retired
   __shared__ uint64_t a_full[kF2A], a_ready[kF2A], a_empty[kF2A], w_full[kF2W], w_empty[kF2W], acc_full[2], acc_empty[2];
   __shared__ uint32_t tmem_base_s;
-  __shared__ float red[4][32];
+  __shared__ float red[2][4][16];
   __shared__ __align__(16) float s_bias16[16];
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -356,7 +356,7 @@ __global__ void __launch_bounds__(kF2Threads, 1) dense_fwd_tma_kernel(const __gr
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&acc_full[i], 1);
-      mbar_init(&acc_empty[i], 4);  // one arrival per epilogue warp
+      mbar_init(&acc_empty[i], 8);  // one arrival per epilogue warp
     }
     fence_mbar_init();
   }
@@ -493,11 +493,18 @@ __global__ void __launch_bounds__(kF2Threads, 1) dense_fwd_tma_kernel(const __gr
         }
       }
   } else {
-    // =============================================================== epilogue warps 4-7
-    const int et = tid - 128, ew = warp - 4;
-    float st_sum[16], st_sq[16];
+    // =============================================================== epilogue: two groups of four warps.  Group g (warps
+    // 4-7: g = 0, warps 10-13: g = 1) owns output channels 8g .. 8g+7 of every pixel: its own half of the accumulator
+    // columns of each tap and its own two planes of the col2im ring, so the groups never meet and the shift-add of a tile
+    // (the latency-bound part of this kernel: TMEM read -> ring read-modify-write per tap) runs twice as wide.
+    const int eg = warp >= 10 ? 1 : 0;
+    const int ew = warp & 3;                       // TMEM lane quarter of this warp
+    const int et = ew * 32 + lane;                 // accumulator row = pixel of the tile
+    const int egw = eg ? warp - 10 : warp - 4;     // 0..3 inside the group (only used for the statistics scratch)
+    float* zsg = zs + (size_t)(2 * eg) * kRing * 4;  // ring planes 2g, 2g+1: [plane][slot][4 channels]
+    float st_sum[8], st_sq[8];
 #pragma unroll
-    for (int i = 0; i < 16; ++i) st_sum[i] = st_sq[i] = 0.f;
+    for (int i = 0; i < 8; ++i) st_sum[i] = st_sq[i] = 0.f;
     int emit_pos = 0;
     for (int tile = 0; tile < ntiles; ++tile) {
       const int t0 = tile * 128;
@@ -519,23 +526,23 @@ __global__ void __launch_bounds__(kF2Threads, 1) dense_fwd_tma_kernel(const __gr
       // SW >= 128 (a dy step moves the slot by SW): one barrier per dx group then suffices; narrower levels keep
       // one barrier per tap.
       const bool wide = SW >= 128;
-      const uint32_t tacc = tmem + buf * 256 + ((uint32_t)(ew * 32) << 16);
-      float v[48];
-      tmem_ld16_nowait(tacc, v);
-      tmem_ld16_nowait(tacc + 16, v + 16);
-      tmem_ld16_nowait(tacc + 32, v + 32);
+      const uint32_t tacc = tmem + buf * 256 + ((uint32_t)(ew * 32) << 16) + 8 * eg;
+      float v[24];
+      tmem_ld8_nowait(tacc, v);
+      tmem_ld8_nowait(tacc + 16, v + 8);
+      tmem_ld8_nowait(tacc + 32, v + 16);
       tmem_wait_ld();
-      reg_fence16(v);
-      reg_fence16(v + 16);
-      reg_fence16(v + 32);
+      reg_fence8(v);
+      reg_fence8(v + 8);
+      reg_fence8(v + 16);
 #pragma unroll
       for (int dxi = 0; dxi < 3; ++dxi) {
         const int dx = dxi - 1;
-        float vn[48];
+        float vn[24];
         if (dxi < 2) {  // next group's accumulator columns stream in behind this group's shift-add
-          tmem_ld16_nowait(tacc + (dxi + 1) * 48, vn);
-          tmem_ld16_nowait(tacc + (dxi + 1) * 48 + 16, vn + 16);
-          tmem_ld16_nowait(tacc + (dxi + 1) * 48 + 32, vn + 32);
+          tmem_ld8_nowait(tacc + (dxi + 1) * 48, vn);
+          tmem_ld8_nowait(tacc + (dxi + 1) * 48 + 16, vn + 8);
+          tmem_ld8_nowait(tacc + (dxi + 1) * 48 + 32, vn + 16);
         }
         const int qx = xx - dx;
         const bool okx = in_valid && qx >= x0 && qx < x1;
@@ -546,32 +553,32 @@ __global__ void __launch_bounds__(kF2Threads, 1) dense_fwd_tma_kernel(const __gr
           if (okx && qi >= 0 && qi < a.H && qr >= R0 && qr < R1) {
             const int uidx = (t - dy * SW - dx + SW + 1) & (kRing - 1);
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              float4* p = reinterpret_cast<float4*>(zs + ((size_t)q * kRing + uidx) * 4);
+            for (int q = 0; q < 2; ++q) {
+              float4* p = reinterpret_cast<float4*>(zsg + ((size_t)q * kRing + uidx) * 4);
               float4 o = *p;
-              o.x += v[dyi * 16 + q * 4 + 0];
-              o.y += v[dyi * 16 + q * 4 + 1];
-              o.z += v[dyi * 16 + q * 4 + 2];
-              o.w += v[dyi * 16 + q * 4 + 3];
+              o.x += v[dyi * 8 + q * 4 + 0];
+              o.y += v[dyi * 8 + q * 4 + 1];
+              o.z += v[dyi * 8 + q * 4 + 2];
+              o.w += v[dyi * 8 + q * 4 + 3];
               *p = o;
             }
           }
-          if (!wide) epilogue_sync();
+          if (!wide) epilogue_sync(eg);
         }
         if (dxi < 2) {
           tmem_wait_ld();
-          reg_fence16(vn);
-          reg_fence16(vn + 16);
-          reg_fence16(vn + 32);
+          reg_fence8(vn);
+          reg_fence8(vn + 8);
+          reg_fence8(vn + 16);
 #pragma unroll
-          for (int i = 0; i < 48; ++i) v[i] = vn[i];
+          for (int i = 0; i < 24; ++i) v[i] = vn[i];
           if (dxi == 1) {  // accumulator fully read by this thread: the MMAs two tiles ahead may overwrite it
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&acc_empty[buf]);
           }
         }
-        if (wide) epilogue_sync();
+        if (wide) epilogue_sync(eg);
       }
       const int lim = (tile == ntiles - 1) ? n_in : max(0, min(t0 + 128 - SW - 1, n_in));
       for (int e0 = emit_pos; e0 < lim; e0 += 128) {
@@ -582,10 +589,10 @@ __global__ void __launch_bounds__(kF2Threads, 1) dense_fwd_tma_kernel(const __gr
           if (orow >= R0 && orow < R1 && ox >= x0 && ox < x1) {
             const int uidx = (e + SW + 1) & (kRing - 1);
             const int img = orow / a.H;
-            float o[16];
+            float o[8];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              float4* p = reinterpret_cast<float4*>(zs + ((size_t)q * kRing + uidx) * 4);
+            for (int q = 0; q < 2; ++q) {
+              float4* p = reinterpret_cast<float4*>(zsg + ((size_t)q * kRing + uidx) * 4);
               float4 z = *p;
               *p = make_float4(0.f, 0.f, 0.f, 0.f);
               o[q * 4 + 0] = z.x;
@@ -593,25 +600,20 @@ __global__ void __launch_bounds__(kF2Threads, 1) dense_fwd_tma_kernel(const __gr
               o[q * 4 + 2] = z.z;
               o[q * 4 + 3] = z.w;
             }
-            uint32_t pk[8];
-            float mk[16];
+            uint32_t pk[4];
+            float mk[8];
             if (a.mask != nullptr) {
-              const float4* mp = reinterpret_cast<const float4*>(a.mask + (size_t)img * 16);
-#pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                const float4 m4 = __ldg(mp + q);
-                mk[4 * q] = m4.x;
-                mk[4 * q + 1] = m4.y;
-                mk[4 * q + 2] = m4.z;
-                mk[4 * q + 3] = m4.w;
-              }
+              const float4* mp = reinterpret_cast<const float4*>(a.mask + (size_t)img * 16 + 8 * eg);
+              const float4 m0 = __ldg(mp), m1 = __ldg(mp + 1);
+              mk[0] = m0.x; mk[1] = m0.y; mk[2] = m0.z; mk[3] = m0.w;
+              mk[4] = m1.x; mk[5] = m1.y; mk[6] = m1.z; mk[7] = m1.w;
             } else {
 #pragma unroll
-              for (int c = 0; c < 16; ++c) mk[c] = 1.f;
+              for (int c = 0; c < 8; ++c) mk[c] = 1.f;
             }
 #pragma unroll
-            for (int c = 0; c < 16; c += 2) {
-              float y0 = (o[c] + s_bias16[c]) * mk[c], y1 = (o[c + 1] + s_bias16[c + 1]) * mk[c + 1];
+            for (int c = 0; c < 8; c += 2) {
+              float y0 = (o[c] + s_bias16[8 * eg + c]) * mk[c], y1 = (o[c + 1] + s_bias16[8 * eg + c + 1]) * mk[c + 1];
               pk[c >> 1] = pack_bf16x2(y0, y1);
               float2 rb = unpack_bf16x2(pk[c >> 1]);
               st_sum[c] += rb.x;
@@ -619,31 +621,29 @@ __global__ void __launch_bounds__(kF2Threads, 1) dense_fwd_tma_kernel(const __gr
               st_sum[c + 1] += rb.y;
               st_sq[c + 1] += rb.y * rb.y;
             }
-            st256(a.act_out + ((size_t)orow * a.W + ox) * a.Ct + a.Cin, make_uint4(pk[0], pk[1], pk[2], pk[3]),
-                  make_uint4(pk[4], pk[5], pk[6], pk[7]));
-            if (a.x16 != nullptr)
-              st256(a.x16 + ((size_t)orow * a.W + ox) * 16, make_uint4(pk[0], pk[1], pk[2], pk[3]),
-                    make_uint4(pk[4], pk[5], pk[6], pk[7]));
+            const uint4 pv = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            *reinterpret_cast<uint4*>(a.act_out + ((size_t)orow * a.W + ox) * a.Ct + a.Cin + 8 * eg) = pv;
+            if (a.x16 != nullptr) *reinterpret_cast<uint4*>(a.x16 + ((size_t)orow * a.W + ox) * 16 + 8 * eg) = pv;
           }
         }
       }
       emit_pos = max(emit_pos, lim);
-      epilogue_sync();
+      epilogue_sync(eg);
     }
     if (a.stats_out != nullptr) {
 #pragma unroll
-      for (int c = 0; c < 16; ++c) {
+      for (int c = 0; c < 8; ++c) {
         float s1 = warp_sum(st_sum[c]), s2 = warp_sum(st_sq[c]);
         if (lane == 0) {
-          red[ew][c] = s1;
-          red[ew][16 + c] = s2;
+          red[eg][egw][c] = s1;
+          red[eg][egw][8 + c] = s2;
         }
       }
-      epilogue_sync();
-      if (et < 32) {
-        float v = red[0][et] + red[1][et] + red[2][et] + red[3][et];
-        const int c = et & 15;
-        atomicAdd(a.stats_out + (et < 16 ? 0 : a.Ct) + a.Cin + c, (double)v);
+      epilogue_sync(eg);
+      if (et < 16) {
+        float vsum = red[eg][0][et] + red[eg][1][et] + red[eg][2][et] + red[eg][3][et];
+        const int c = et & 7;
+        atomicAdd(a.stats_out + (et < 8 ? 0 : a.Ct) + a.Cin + 8 * eg + c, (double)vsum);
       }
     }
   }

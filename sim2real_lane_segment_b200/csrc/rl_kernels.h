@@ -236,3 +236,27 @@ int launch_adamw_dev(float* p, const float* g, float* m, float* v, long n, const
 int launch_grad_accum(float* grads, const float* stage, long n, float scale, const float* scale_dev, cudaStream_t st);
 
 }  // namespace rl
+
+namespace rl {
+// ---------------------------------------------------------------- TransitionUp (rl_tu.cu)
+// ConvTranspose2d(80 -> 80, k3, s2, p0) + bias + center_crop (offset 0) written straight into the concat slice
+// (reference layers.py:58-69, 82-86) as ONE kernel: the four output parities (Y%2, X%2) of a low-resolution position are
+// four accumulators fed by row-shifted views of one input halo tile; no column matrix, no col2im pass.
+struct TuFwdArgs {
+  const __nv_bfloat16* A;   // input level arena
+  int lda, a_off;           // its channel count, first input channel
+  int B, h, w;              // input resolution
+  int H, W;                 // output resolution (cropped)
+  const uint8_t* wpk;       // [tap 9][ci chunk 10][co 80][8 ci] bf16
+  const float* bias;        // [80]
+  __nv_bfloat16* out;       // output level arena (NHWC)
+  int ldo, o_off;
+  __nv_bfloat16* out_xp;    // planar mirror of the output level or null
+  long npx_out;
+  int TP, ncolt;            // tile pitch (8 / 16 / 32), tiles per row of tiles
+  long ntiles;
+};
+int launch_tu_fwd(const TuFwdArgs& a, int grid, cudaStream_t st);
+inline int tu_tile_pitch(int w) { return w + 2 <= 8 ? 8 : (w + 2 <= 16 ? 16 : 32); }
+int configure_tu_kernels();
+}  // namespace rl

@@ -94,6 +94,11 @@ __global__ void pack_weights_kernel(const PackEntry* tab, const float* __restric
           for (int k = 0; k < 8; ++k) v[k] = w[((long)(half * 8 + k) * C + ref_channel(c, e.cs_perm)) * 9 + tap];
         break;
       }
+      case 8: {  // TU fwd, parity kernel: [tap][ci chunk j][co][8 ci]; weight [ci][co][3][3]
+        int tap = (int)(i / 800), rem = (int)(i % 800), j = rem / 80, co = rem % 80;
+        for (int k = 0; k < 8; ++k) v[k] = w[((long)(j * 8 + k) * 80 + co) * 9 + tap];
+        break;
+      }
     }
     dst[i] = pack8(v);
   }

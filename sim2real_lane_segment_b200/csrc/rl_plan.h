@@ -76,7 +76,7 @@ struct Block {
 };
 
 struct PackEntry {
-  int kind;      // 0 dense fwd, 1 dense bwd, 2 TD fwd, 3 TD bwd, 4 TU fwd, 5 TU bwd, 6 dense chain bwd, 7 dense bulk bwd
+  int kind;      // 0 dense fwd, 1 dense bwd, 2 TD fwd, 3 TD bwd, 4 (retired), 5 TU bwd, 6 dense chain bwd, 7 dense bulk bwd, 8 TU fwd
   int cin, cs_perm, np0;
   int c_lo, nch;  // kind 6: channel range [c_lo, c_lo + nch); kind 7: c_lo = C0, nch = cbs
   long dst_off;  // bytes into workspace

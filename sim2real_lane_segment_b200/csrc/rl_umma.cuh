@@ -215,6 +215,17 @@ __device__ __forceinline__ void reg_fence16(float* v) {
                :
                : "memory");
 }
+__device__ __forceinline__ void tmem_ld8_nowait(uint32_t taddr, float* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x8.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+      : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void reg_fence8(float* v) {
+  asm volatile("" : "+f"(v[0]), "+f"(v[1]), "+f"(v[2]), "+f"(v[3]), "+f"(v[4]), "+f"(v[5]), "+f"(v[6]), "+f"(v[7]) : : "memory");
+}
 __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
   uint32_t r[8];
   asm volatile(

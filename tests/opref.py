@@ -97,17 +97,9 @@ def transition_down_fwd(x, sums, n, gamma, beta, w, bias, keep_scale):
 
 def transition_up_fwd(x, w, bias, Hout, Wout):
     """TransitionUp (layers.py:58-69, 82-86): ConvTranspose2d(80->80, k3, s2, p0) + bias, center_crop (offset 0).
-    The kernel pair rounds each tap's contribution to bf16 (column matrix) before the shift-add: mirrored here.
-    x [B,h,w,80], w [80(in),80(out),3,3].  Returns fp64 [B,Hout,Wout,80]."""
-    xin = nchw(x.double())
-    out = None
-    for ky in range(3):
-        for kx in range(3):
-            wt = torch.zeros_like(w, dtype=torch.float64)
-            wt[:, :, ky, kx] = w[:, :, ky, kx].double()
-            y = bf16r(F.conv_transpose2d(xin, wt, stride=2).float()).double()
-            out = y if out is None else out + y
-    out = out + bias.double()[None, :, None, None]
+    The parity kernel accumulates every tap in fp32 and rounds once.  x [B,h,w,80], w [80(in),80(out),3,3].
+    Returns fp64 [B,Hout,Wout,80]."""
+    out = F.conv_transpose2d(nchw(x.double()), w.double(), bias.double(), stride=2)
     return nhwc(out[:, :, :Hout, :Wout])
 
 
