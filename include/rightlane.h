@@ -144,9 +144,33 @@ int rl_sgd_nesterov_step(float* params, const float* grads, float* momentum_buf,
  * img_bgr: uint8 [B][Hs][Ws][3] (device), label: uint8 [B][Hs][Ws] or null.  x_out: float32 [B][3][H][W] =
  * Normalize(cv2.resize(img, (W,H), INTER_LINEAR)) -- the resize is cv2's uint8 fixed-point algorithm, bit-exact --
  * with ToGray applied in between when gray != 0; y_out: int64 [B][H][W] = cv2.resize(label, INTER_NEAREST), or null.
- * The random augmentations (HueSaturationValue, RandomSizedCrop, MotionBlur, GaussNoise) are not part of this call. */
+ * The random augmentations are rl_preprocess_augment below. */
 int rl_preprocess(const unsigned char* img_bgr, const unsigned char* label, int B, int Hs, int Ws, int H, int W, int gray,
                   float* x_out, long long* y_out, void* stream);
+
+/* Input pipeline with the random augmentations: MyTransform(width, height, gray, augment=True) of
+ * dataManagement/myTransforms.py:8-20 for caller-drawn parameters, one entry per frame:
+ *   HueSaturationValue -> lut_h/lut_s/lut_v: the three cv2.LUT tables albumentations builds from its hue / sat / val shifts
+ *                         (hsv = 0: all shifts were 0, albumentations returns the frame untouched);
+ *   RandomSizedCrop    -> the crop window (crop_x, crop_y, crop_w, crop_h) in source pixels, resized to (W, H);
+ *   MotionBlur         -> ksize (3, 5 or 7; 0: not chosen) and the normalised ksize x ksize float32 kernel, row major;
+ *   GaussNoise         -> noise != 0: noise_dev[b] (float64 [H][W][3], what RandomState.normal drew) is added.
+ * Every uint8 stage is bit-exact with what albumentations 0.5.2 makes cv2 compute (RGB2HSV / LUT / HSV2RGB, crop +
+ * resize INTER_LINEAR / INTER_NEAREST, filter2D BORDER_REFLECT_101, float32 + float64 noise clipped and truncated). */
+typedef struct rl_augment_params {
+  unsigned char lut_h[256], lut_s[256], lut_v[256];
+  int hsv;
+  int crop_x, crop_y, crop_w, crop_h;
+  int ksize;
+  float kernel[49];
+  int noise;
+} rl_augment_params;
+/* img_bgr uint8 [B][Hs][Ws][3], label uint8 [B][Hs][Ws] or null, params_dev [B], noise_dev float64 [B][H][W][3] or null,
+ * scratch_u8 uint8 [B][H][W][3] (receives the augmented uint8 frames), x_out float32 [B][3][H][W], y_out int64 [B][H][W]
+ * or null: all device pointers. */
+int rl_preprocess_augment(const unsigned char* img_bgr, const unsigned char* label, int B, int Hs, int Ws, int H, int W, int gray,
+                          const rl_augment_params* params_dev, const double* noise_dev, unsigned char* scratch_u8, float* x_out,
+                          long long* y_out, void* stream);
 
 /* Inference consumer (makeDemoVideo.py:36-42, comparison.py:44-58): out uint8 [B][H][W][3] = cv2.resize(frame, (W,H))
  * (INTER_LINEAR, bit-exact) with the predicted classes painted over it in BGR: 1 -> (0,255,0), 2 -> (255,0,0),

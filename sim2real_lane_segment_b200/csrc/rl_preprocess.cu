@@ -7,6 +7,7 @@
 // how the two fp32 operations of Normalize are fused.  One thread per output pixel; the 4 source pixels of the three
 // channels are adjacent bytes, the output is written as three coalesced fp32 planes.
 #include "rl_common.cuh"
+#include "rl_preprocess.cuh"
 
 namespace rl {
 
@@ -19,51 +20,6 @@ struct PrepArgs {
   double scale_x, scale_y;
   float m[3], d[3];      // mean*255, 1/(std*255)
 };
-
-__device__ __forceinline__ int cv_round_to_short(float v) {
-  int r = __float2int_rn(v);  // cvRound: round half to even
-  return max(-32768, min(32767, r));
-}
-
-// cv2.resize(src, (W, H)) with INTER_LINEAR (the default), uint8, 3 channels: one output pixel
-__device__ __forceinline__ void resize_linear_px(const uint8_t* src, int Hs, int Ws, int H, int W, double scale_x, double scale_y,
-                                                 int dx, int dy, int* v) {
-  if (Hs == H && Ws == W) {  // same size: copy
-    const uint8_t* p = src + ((size_t)dy * Ws + dx) * 3;
-    v[0] = p[0];
-    v[1] = p[1];
-    v[2] = p[2];
-    return;
-  }
-  float fx = (float)(((double)dx + 0.5) * scale_x - 0.5);
-  int sx = (int)floorf(fx);
-  fx -= (float)sx;
-  if (sx < 0) {
-    fx = 0.f;
-    sx = 0;
-  }
-  if (sx >= Ws - 1) {
-    fx = 0.f;
-    sx = Ws - 1;
-  }
-  const int a0 = cv_round_to_short((1.f - fx) * 2048.f), a1 = cv_round_to_short(fx * 2048.f);
-  const int sx1 = min(sx + 1, Ws - 1);
-  float fy = (float)(((double)dy + 0.5) * scale_y - 0.5);
-  const int sy = (int)floorf(fy);
-  fy -= (float)sy;
-  const int b0 = cv_round_to_short((1.f - fy) * 2048.f), b1 = cv_round_to_short(fy * 2048.f);
-  const int r0 = max(0, min(sy, Hs - 1)), r1 = max(0, min(sy + 1, Hs - 1));
-  const uint8_t* p00 = src + ((size_t)r0 * Ws + sx) * 3;
-  const uint8_t* p01 = src + ((size_t)r0 * Ws + sx1) * 3;
-  const uint8_t* p10 = src + ((size_t)r1 * Ws + sx) * 3;
-  const uint8_t* p11 = src + ((size_t)r1 * Ws + sx1) * 3;
-#pragma unroll
-  for (int c = 0; c < 3; ++c) {
-    const int S0 = p00[c] * a0 + p01[c] * a1, S1 = p10[c] * a0 + p11[c] * a1;
-    const int o = (((b0 * (S0 >> 4)) >> 16) + ((b1 * (S1 >> 4)) >> 16) + 2) >> 2;
-    v[c] = max(0, min(255, o));
-  }
-}
 
 __global__ void __launch_bounds__(256) preprocess_kernel(PrepArgs a) {
   const long n = (long)a.B * a.H * a.W;

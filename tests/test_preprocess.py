@@ -63,8 +63,6 @@ def test_rl_preprocess_batch_and_ragged_sizes():
             assert torch.equal(y[b].cpu(), torch.from_numpy(wy))
     x, y = MyTransform()(img[0])            # no label: returned unchanged (None)
     assert y is None and x.shape == (3, 120, 160)
-    with pytest.raises(NotImplementedError):
-        MyTransform(augment=True)
 
 
 @pytest.mark.gpu
