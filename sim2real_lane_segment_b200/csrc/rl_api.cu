@@ -159,7 +159,7 @@ int rl_plan_bind(rl_plan* h, void* workspace, void* stream) {
       e.kind = 3; e.dst_off = (long)L.wpk_bwd; e.n16 = (long)nmb * nkc * 8 * 128; pk.push_back(e);
     } else if (L.type == L_TU) {
       e.kind = 8; e.dst_off = (long)L.wpk_fwd; e.n16 = 9L * 10 * 80; pk.push_back(e);
-      e.kind = 5; e.dst_off = (long)L.wpk_bwd; e.n16 = 12L * 8 * 80; pk.push_back(e);
+      e.kind = 9; e.dst_off = (long)L.wpk_bwd; e.n16 = 9L * 10 * 80; pk.push_back(e);
     }
     if (L.type == L_DENSE && p.training) {
       const Block& b = p.blocks[L.blk];
@@ -723,48 +723,27 @@ int backward_layer(BwdCtx& c, int li) {
     if ((rc = before_dz(c, tq))) return rc;
     if ((rc = launch_dz_prepare(z, sm, c.st))) return rc;
     if ((rc = after_dz(c, tq))) return rc;
-    GemmPxArgs a;
-    memset(&a, 0, sizeof(a));
-    a.A = tmp;
-    a.lda = 720;
-    a.a_off = 0;
-    a.K = 720;
-    a.M = lin.px;
-    a.ntiles = (lin.px + 127) / 128;
-    a.mode = GEMM_LINEAR;
-    a.transform = 0;
-    a.wpk = wsb(p) + L.wpk_bwd;
-    a.N = kUpCh;
-    a.part_n0[0] = 0;
-    a.part_np[0] = kUpCh;
-    a.out = dact_of(p, L.lvl_in);
-    a.ldo = lin.Ct;
-    a.o_off = L.in_off;
-    a.out_planar_npx = lin.px;
-    int gx = (int)std::max(1L, std::min(a.ntiles, (long)3 * sm));  // N = 80: three CTAs per SM
-    if ((rc = launch_gemm_px(a, gx, 1, c.st))) return rc;
-    WgradArgs w;
-    memset(&w, 0, sizeof(w));
-    w.kind = WG_TU;
-    w.A = act_of(p, L.lvl_in);
-    w.Axp = xp_of(p, L.lvl_in);
-    w.lda = lin.Ct;
-    w.a_off = L.in_off;
-    w.Ca = kUpCh;
-    w.transform = 0;
-    w.Bm = tmp;
-    w.ldb = 720;
-    w.N = 720;
-    for (int q = 0; q < 3; ++q) {
-      w.part_n0[q] = q * 240;
-      w.part_np[q] = 240;
-    }
-    w.npx = lin.px;
-    w.H = lin.H;
-    w.W = lin.W;
-    w.gw = c.gs + L.p_w;
-    int wr = wgrad_runs(p, w.npx, 1, 3, &w.px_per_cta);
-    if ((rc = launch_wgrad(w, wr, 1, 3, c.st2))) return rc;
+    TuBwdArgs t;
+    memset(&t, 0, sizeof(t));
+    t.dzp = tmp;
+    t.npos = (long)p->B * (lin.H + 1) * (lin.W + 1);
+    t.B = p->B;
+    t.h = lin.H;
+    t.w = lin.W;
+    t.TP = tu_tile_pitch(lin.W - 1);  // TP - 1 own columns per tile
+    const int TR = 128 / t.TP;
+    t.ncolt = (lin.W + t.TP - 2) / (t.TP - 1);
+    t.ntiles = (long)((p->B * (lin.H + 1) + TR - 1) / TR) * t.ncolt;
+    t.wpk = wsb(p) + L.wpk_bwd;
+    t.dact = dact_of(p, L.lvl_in);
+    t.npx_in = lin.px;
+    t.in_off = L.in_off;
+    t.x = act_of(p, L.lvl_in);
+    t.ldx = lin.Ct;
+    t.x_off = L.in_off;
+    t.gw = c.gs + L.p_w;
+    if ((rc = launch_tu_dgrad(t, (int)std::max(1L, std::min(t.ntiles, (long)sm)), c.st))) return rc;
+    if ((rc = launch_tu_wgrad(t, (int)std::max(1L, std::min(t.ntiles, (long)(sm / 3))), c.st2))) return rc;
     return after_wg(c, tq);
   }
   // L_FIRST: weight gradient only (the image needs no gradient)

@@ -257,6 +257,23 @@ struct TuFwdArgs {
   long ntiles;
 };
 int launch_tu_fwd(const TuFwdArgs& a, int grid, cudaStream_t st);
+// backward of the transposed convolution from the four parity planes of dz (dz_tu_kernel, rl_misc.cu)
+struct TuBwdArgs {
+  const __nv_bfloat16* dzp;  // [4][npos][80], npos = B (h+1) (w+1)
+  long npos;
+  int B, h, w;               // input (low) resolution
+  int TP, ncolt;
+  long ntiles;
+  const uint8_t* wpk;        // input gradient: [tap][co chunk][ci][8 co]
+  __nv_bfloat16* dact;       // planar gradient arena of the input level (plain store of the 80 input channels)
+  long npx_in;
+  int in_off;
+  const __nv_bfloat16* x;    // weight gradient: input level arena (NHWC)
+  int ldx, x_off;
+  float* gw;                 // [ci][co][3][3] fp32, accumulated with atomics
+};
+int launch_tu_dgrad(const TuBwdArgs& a, int grid, cudaStream_t st);
+int launch_tu_wgrad(const TuBwdArgs& a, int grid_x, cudaStream_t st);
 inline int tu_tile_pitch(int w) { return w + 2 <= 8 ? 8 : (w + 2 <= 16 ? 16 : 32); }
 int configure_tu_kernels();
 }  // namespace rl

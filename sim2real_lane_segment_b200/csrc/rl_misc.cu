@@ -94,6 +94,11 @@ __global__ void pack_weights_kernel(const PackEntry* tab, const float* __restric
           for (int k = 0; k < 8; ++k) v[k] = w[((long)(half * 8 + k) * C + ref_channel(c, e.cs_perm)) * 9 + tap];
         break;
       }
+      case 9: {  // TU input gradient: [tap][co chunk j][ci][8 co]; weight [ci][co][3][3]
+        int tap = (int)(i / 800), rem = (int)(i % 800), j = rem / 80, ci = rem % 80;
+        for (int k = 0; k < 8; ++k) v[k] = w[((long)ci * 80 + (j * 8 + k)) * 9 + tap];
+        break;
+      }
       case 8: {  // TU fwd, parity kernel: [tap][ci chunk j][co][8 ci]; weight [ci][co][3][3]
         int tap = (int)(i / 800), rem = (int)(i % 800), j = rem / 80, co = rem % 80;
         for (int k = 0; k < 8; ++k) v[k] = w[((long)(j * 8 + k) * 80 + co) * 9 + tap];
@@ -825,13 +830,15 @@ __global__ void __launch_bounds__(256) dz_td_kernel(DzArgs a) {
   }
 }
 
-// TransitionUp output (80 channels): one thread per (output pixel, chunk) scatters into the column matrix
-// row (b,i,j), column tap*80 + c with (2i+ky, 2j+kx) = (Y, X); slots whose output pixel lies outside the cropped
-// image are zero-filled by the threads of the last input row / column.
+// TransitionUp output (80 channels): dz is written as four PARITY PLANES over the low-resolution position grid
+// (I, J) in [0, h] x [0, w]:  plane (py, px) at position (b, I, J) holds dz of output pixel (2I + py, 2J + px), or zeros when
+// that pixel lies outside the cropped output.  Layout [4][B][h+1][w+1][80] bf16: the transposed convolution's backward
+// GEMMs (rl_tu.cu) read row-shifted views of tiles of these planes, the [pixels x 720] column matrix never exists.
+// One thread per (position, 8-channel chunk); it handles the four parities of its position (one 2x2 output quad).
 __global__ void __launch_bounds__(250) dz_tu_kernel(DzArgs a) {
   extern __shared__ float sm[];
-  const int j = threadIdx.x % 10, pl = threadIdx.x / 10;   // 10 chunks of 8 channels, 25 pixel lanes
-  const int h = a.Hp, w = a.Wp;
+  const int j = threadIdx.x % 10, pl = threadIdx.x / 10;   // 10 chunks of 8 channels, 25 position lanes
+  const int hp = a.Hp + 1, wp = a.Wp + 1;
   DzConst* s_k = reinterpret_cast<DzConst*>(sm + 250 * 8);  // [80]
   for (int c = threadIdx.x; c < 80; c += blockDim.x) s_k[c] = dz_const(a, c);
   __syncthreads();
@@ -841,41 +848,27 @@ __global__ void __launch_bounds__(250) dz_tu_kernel(DzArgs a) {
   float bsum[8];
 #pragma unroll
   for (int c = 0; c < 8; ++c) bsum[c] = 0.f;
-  const long nout = (long)a.B * a.H * a.W;
-  for (long P = (long)blockIdx.x * 25 + pl; P < nout; P += (long)gridDim.x * 25) {
-    const int P32 = (int)P, b = P32 / (a.W * a.H), rem = P32 - b * (a.W * a.H), Y = rem / a.W, X = rem - Y * a.W;
-    float dx[8], xv[8], o[8];
-    unpack8(ldg128(a.dact + dact_index(a.npx_out, P, a.c_off + j * 8)), dx);
-    unpack8(ldg128(a.xp ? a.xp + dact_index(a.npx_out, P, a.c_off + j * 8) : a.act + P * a.Ct + a.c_off + j * 8), xv);
+  const long npos = (long)a.B * hp * wp;
+  for (long q = (long)blockIdx.x * 25 + pl; q < npos; q += (long)gridDim.x * 25) {
+    const int q32 = (int)q, b = q32 / (hp * wp), rem = q32 - b * (hp * wp), I = rem / wp, J = rem - I * wp;
 #pragma unroll
-    for (int c = 0; c < 8; ++c) {
-      const float xh = (xv[c] - k[c].mean) * k[c].rstd;
-      o[c] = dx[c] - k[c].A - xh * k[c].B;
-      bsum[c] += o[c];
-    }
-    const uint4 pk = pack8(o);
-    for (int ky = (Y & 1); ky < 3; ky += 2) {
-      const int ii = (Y - ky) >> 1;
-      if (ii < 0 || ii >= h) continue;
-      for (int kx = (X & 1); kx < 3; kx += 2) {
-        const int jj = (X - kx) >> 1;
-        if (jj < 0 || jj >= w) continue;
-        *reinterpret_cast<uint4*>(a.dz + (((long)b * h + ii) * w + jj) * 720 + (ky * 3 + kx) * 80 + j * 8) = pk;
+    for (int par = 0; par < 4; ++par) {
+      const int Y = 2 * I + (par >> 1), X = 2 * J + (par & 1);
+      uint4 pk = make_uint4(0, 0, 0, 0);
+      if (Y < a.H && X < a.W) {
+        const long P = ((long)b * a.H + Y) * a.W + X;
+        float dx[8], xv[8], o[8];
+        unpack8(ldg128(a.dact + dact_index(a.npx_out, P, a.c_off + j * 8)), dx);
+        unpack8(ldg128(a.xp ? a.xp + dact_index(a.npx_out, P, a.c_off + j * 8) : a.act + P * a.Ct + a.c_off + j * 8), xv);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const float xh = (xv[c] - k[c].mean) * k[c].rstd;
+          o[c] = dx[c] - k[c].A - xh * k[c].B;
+          bsum[c] += o[c];
+        }
+        pk = pack8(o);
       }
-    }
-  }
-  // zero fill: slots (i, j, ky, kx) with 2i+ky >= H or 2j+kx >= W (only ky = 2 at i = h-1 when H = 2h, same for x)
-  const bool zrow = 2 * (h - 1) + 2 >= a.H, zcol = 2 * (w - 1) + 2 >= a.W;
-  if (zrow || zcol) {
-    const long nin = (long)a.B * h * w;
-    for (long Pi = (long)blockIdx.x * 25 + pl; Pi < nin; Pi += (long)gridDim.x * 25) {
-      const int jj = (int)(Pi % w), ii = (int)((Pi / w) % h);
-      if (ii != h - 1 && jj != w - 1) continue;
-      for (int tap = 0; tap < 9; ++tap) {
-        const int ky = tap / 3, kx = tap % 3;
-        if (2 * ii + ky >= a.H || 2 * jj + kx >= a.W)
-          *reinterpret_cast<uint4*>(a.dz + Pi * 720 + tap * 80 + j * 8) = make_uint4(0, 0, 0, 0);
-      }
+      *reinterpret_cast<uint4*>(a.dz + ((long)par * npos + q) * 80 + j * 8) = pk;
     }
   }
   if (a.g_bias != nullptr) {
@@ -908,8 +901,8 @@ int launch_dz_prepare(const DzArgs& a, int sm, cudaStream_t st) {
     return RL_OK;
   }
   if (a.kind == 2 && a.nch == 80) {
-    long nout = (long)a.B * a.H * a.W;
-    int grid = (int)std::max<long>(1, std::min<long>((nout + 24) / 25, (long)sm * 8));
+    long npos = (long)a.B * (a.Hp + 1) * (a.Wp + 1);
+    int grid = (int)std::max<long>(1, std::min<long>((npos + 24) / 25, (long)sm * 8));
     { ProfScope _ps(KC_DZ_PREPARE, st);
     dz_tu_kernel<<<grid, 250, 250 * 8 * sizeof(float) + 80 * sizeof(DzConst), st>>>(a); }
   RL_CUDA(cudaGetLastError());

@@ -203,12 +203,12 @@ int build_plan(Plan* p, int B, int H, int W, int num_cls, int training) {
   for (int l = 0; l < kLevels; ++l) p->lv[l].dact_off = training ? carve((size_t)p->lv[l].px * p->lv[l].Ct * 2) : 0;
   for (Layer& L : p->layers)
     if (L.type == L_TD) L.amax_off = training ? carve((size_t)p->lv[L.lvl_out].px * L.cout) : 0;
-  // scratch: convT column matrices [px(l+1) x 720] bf16, TD output gradients [px(l) x C] bf16, dz16/dz48
+  // scratch (training): TransitionUp dz parity planes [4][B (h+1) (w+1)][80] bf16, TD output gradients [px(l) x C] bf16, dz16/dz48
   size_t tmp = 0;
   for (Layer& L : p->layers) {
     size_t need = 0;
-    if (L.type == L_TU) need = (size_t)p->lv[L.lvl_in].px * 720 * 2;
     if (training) {
+      if (L.type == L_TU) need = (size_t)4 * p->B * (p->lv[L.lvl_in].H + 1) * (p->lv[L.lvl_in].W + 1) * kUpCh * 2;
       if (L.type == L_TD) need = (size_t)p->lv[L.lvl_in].px * L.cout * 2;
       if (L.type == L_DENSE) need = (size_t)p->lv[L.lvl_in].px * 16 * 2;
       if (L.type == L_FIRST) need = (size_t)p->lv[0].px * kFirst * 2;
