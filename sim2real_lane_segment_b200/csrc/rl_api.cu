@@ -301,7 +301,6 @@ static int forward_layer(Plan* p, int li, const float* params, const float* bnbu
     a.lda = lin.Ct;
     a.a_off = 0;
     a.K = L.cin;
-    a.mode = GEMM_POOL;
     a.H = lin.H;
     a.W = lin.W;
     a.Hp = lo.H;

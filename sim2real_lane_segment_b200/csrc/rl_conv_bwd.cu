@@ -433,7 +433,6 @@ __device__ __forceinline__ long wgrad_index(const WgradArgs& a, int c, int ng) {
   switch (a.kind) {
     case WG_DENSE: return ((long)(ng & 15) * a.Cin_w + ref_channel(c, a.cs_perm)) * 9 + (ng >> 4);
     case WG_TD: return (long)ng * a.Cin_w + c;
-    case WG_TU: return ((long)c * kUpCh + ng % kUpCh) * 9 + ng / kUpCh;
     case WG_HEAD: return ng < a.num_cls ? (long)ng * 288 + ref_channel(c, 128) : -1;
     default: return (long)ng * 27 + c;  // WG_FIRST
   }

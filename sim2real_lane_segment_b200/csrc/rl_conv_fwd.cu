@@ -762,19 +762,14 @@ __global__ void __launch_bounds__(128, 2) gemm_px_kernel(GemmPxArgs a) {
   TileLoader<128> ld;
   const __nv_bfloat16* rowptr[4];
 
-  // row m of tile t -> arena pixel (or -1): POOL mode orders the rows window-major (4 pixels of a 2x2 window adjacent)
+  // row m of tile t -> arena pixel (or -1): the rows are window-major (the 4 pixels of a 2x2 pooling window adjacent)
   auto pixel_of = [&](long t, int m) -> long {
-    if (a.mode == GEMM_POOL) {
-      const int pr_ = (int)(t / a.wblocks), wb_ = (int)(t - (long)pr_ * a.wblocks);
-      const int win = m >> 2, q = m & 3;
-      const int wi = wb_ * 32 + win;
-      if (wi >= a.Wp) return -1;
-      const int img = pr_ / a.Hp, py = pr_ - img * a.Hp;
-      return ((long)img * a.H + 2 * py + (q >> 1)) * a.W + 2 * wi + (q & 1);
-    } else {
-      const long P = t * 128 + m;
-      return P < a.M ? P : -1;
-    }
+    const int pr_ = (int)(t / a.wblocks), wb_ = (int)(t - (long)pr_ * a.wblocks);
+    const int win = m >> 2, q = m & 3;
+    const int wi = wb_ * 32 + win;
+    if (wi >= a.Wp) return -1;
+    const int img = pr_ / a.Hp, py = pr_ - img * a.Hp;
+    return ((long)img * a.H + 2 * py + (q >> 1)) * a.W + 2 * wi + (q & 1);
   };
   auto set_rowptrs = [&](long t) {
 #pragma unroll
@@ -790,17 +785,14 @@ __global__ void __launch_bounds__(128, 2) gemm_px_kernel(GemmPxArgs a) {
   }
   for (long tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
     // ---- row -> pixel mapping
-    int pr = 0, wb = 0;
-    if (a.mode == GEMM_POOL) {
-      pr = (int)(tile / a.wblocks);
-      wb = (int)(tile % a.wblocks);
+    const int pr = (int)(tile / a.wblocks), wb = (int)(tile % a.wblocks);
+    {
       const int img = pr / a.Hp;
       if (a.mask != nullptr && img != mask_img) {  // visible to the epilogue through the main loop's barriers
         for (int c = tid; c < np; c += 128) s_mask[c] = a.mask[(size_t)img * a.N + n0 + c];
         mask_img = img;
       }
     }
-    auto pixel_of_row = [&](int m) -> long { return pixel_of(tile, m); };
     for (int kc = 0; kc < nkc; ++kc) {
       const int ck = min(64, a.K - kc * 64);
       const uint32_t s = g & 1, u = g >> 1;
@@ -853,8 +845,7 @@ __global__ void __launch_bounds__(128, 2) gemm_px_kernel(GemmPxArgs a) {
       tc_fence_after();
     }
     // ---- epilogue: thread = accumulator row
-    const long P = pixel_of_row(tid);
-    if (a.mode == GEMM_POOL) {
+    {
       const int win = tid >> 2, q = tid & 3, wi = wb * 32 + win;
       const int img = pr / a.Hp, py = pr % a.Hp;
       const bool valid = wi < a.Wp;
@@ -900,20 +891,6 @@ __global__ void __launch_bounds__(128, 2) gemm_px_kernel(GemmPxArgs a) {
             d2[1] = dst[1];
           }
           if (a.amax) *reinterpret_cast<uint4*>(a.amax + opx * a.N + n0 + c0) = make_uint4(am[0], am[1], am[2], am[3]);
-        }
-      }
-    } else {
-      for (int c0 = 0; c0 < np; c0 += 16) {
-        float v[16];
-        tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16) + c0, v);
-        if (P >= 0) {
-          uint32_t pk[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) pk[i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
-          uint4* dst = reinterpret_cast<uint4*>(a.out_planar_npx > 0 ? a.out + dact_index(a.out_planar_npx, P, a.o_off + n0 + c0)
-                                                                      : a.out + (size_t)P * a.ldo + a.o_off + n0 + c0);
-          dst[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-          dst[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
         }
       }
     }

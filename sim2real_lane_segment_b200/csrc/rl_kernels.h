@@ -27,14 +27,12 @@ int launch_dense_fwd_tma(const DenseFwdArgs& a, const void* tmap, int grid, cuda
 // host: encode a [pixels][Ct] bf16 arena as a 2-D tiled tensor map, box 128 px x 64 channels, SWIZZLE_128B
 int encode_arena_tmap(void* tmap_out, const void* arena, long npx, int Ct, int W);
 
-enum { GEMM_LINEAR = 0, GEMM_POOL = 1 };
+// TransitionDown forward: BN -> ReLU -> Conv1x1 (+bias, Dropout2d scale) -> MaxPool2d(2) in one kernel (gemm_px_kernel)
 struct GemmPxArgs {
   const __nv_bfloat16* A;
   int lda, a_off, K;
-  long M;           // rows (LINEAR)
   long ntiles;
-  int mode;
-  int H, W, Hp, Wp, wblocks;  // POOL geometry
+  int H, W, Hp, Wp, wblocks;  // input / pooled geometry, 32-window blocks per pooled row
   int transform;
   BnSrc bn;
   const uint8_t* wpk;
@@ -44,8 +42,7 @@ struct GemmPxArgs {
   const float* mask;
   __nv_bfloat16* out;
   int ldo, o_off;
-  long out_planar_npx;  // > 0: out is a planar gradient arena of that many pixels (LINEAR mode), ldo unused
-  __nv_bfloat16* out_xp;  // POOL mode, training: planar mirror of the pooled level (written besides out) or null
+  __nv_bfloat16* out_xp;  // training: planar mirror of the pooled level (written besides out) or null
   long out_xp_npx;
   uint8_t* amax;
 };
@@ -165,8 +162,6 @@ int launch_pack_weights(const Plan* p, const float* params, cudaStream_t st);
 int launch_first_fwd(const Plan* p, const float* x, const float* params, int train, cudaStream_t st);
 int launch_channel_stats(const __nv_bfloat16* arena, long npx, int Ct, int c_off, int nch, double* stats, int sm,
                          cudaStream_t st);
-int launch_tu_col2im(const __nv_bfloat16* ycol, __nv_bfloat16* out, __nv_bfloat16* out_xp, const float* bias, int B, int h,
-                     int w, int H, int W, int Ct, int o_off, cudaStream_t st);
 int launch_label_hist(const void* y, int y_is_i64, long n, int num_cls, Scalars* sc, cudaStream_t st);
 
 struct HeadArgs {

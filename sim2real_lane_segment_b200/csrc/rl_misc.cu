@@ -64,22 +64,6 @@ __global__ void pack_weights_kernel(const PackEntry* tab, const float* __restric
             if (co0 + k < C) v[k] = w[(long)(co0 + k) * C + c];
         break;
       }
-      case 4: {  // TU fwd: [q][kc][jc][nl][8 ci], n = q*240+nl = tap*80+co; weight [ci][co][3][3]
-        int q = (int)(i / (2 * 8 * 240)), kc = (int)((i / (8 * 240)) % 2), jc = (int)((i / 240) % 8), nl = (int)(i % 240);
-        int ci0 = kc * 64 + jc * 8, n = q * 240 + nl, tap = n / 80, co = n % 80;
-        for (int k = 0; k < 8; ++k)
-          if (ci0 + k < 80) v[k] = w[((long)(ci0 + k) * 80 + co) * 9 + tap];
-        break;
-      }
-      case 5: {  // TU bwd: [kc][jc][ci][8 n]
-        int kc = (int)(i / (8 * 80)), jc = (int)((i / 80) % 8), ci = (int)(i % 80);
-        int nb = kc * 64 + jc * 8;
-        for (int k = 0; k < 8; ++k) {
-          int n = nb + k;
-          if (n < 720) v[k] = w[((long)ci * 80 + n % 80) * 9 + n / 80];
-        }
-        break;
-      }
       case 6: {  // dense bwd, chain launch: [j=tap*2+half][cl][8 co], arena channel c_lo + cl (rows >= nch stay zero)
         int j = (int)(i / 128), cl = (int)(i % 128);
         int tap = j >> 1, half = j & 1, c = e.c_lo + cl;
@@ -229,54 +213,6 @@ int launch_channel_stats(const __nv_bfloat16* arena, long npx, int Ct, int c_off
   return RL_OK;
 }
 
-// ================================================================================================
-// ConvTranspose2d(80->80, k3, s2, p0) col2im + bias + center_crop (offset 0) -> concat slice
-// ycol[p_in][tap*80+co] holds in[p_in,:] · W[:,co,tap]   (reference layers.py:61-68, 82-86)
-// ================================================================================================
-__global__ void __launch_bounds__(256) tu_col2im_kernel(const __nv_bfloat16* __restrict__ ycol, __nv_bfloat16* out,
-                                                        __nv_bfloat16* out_xp, const float* __restrict__ bias, int B, int h, int w, int H, int W,
-                                                        int Ct, int o_off) {
-  const long total = (long)B * H * W * 10;
-  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
-    const int i32 = (int)i, P32 = i32 / 10, j = i32 - P32 * 10;   // < 2^31 work items: 32-bit index arithmetic
-    const long P = P32;
-    const int b = P32 / (W * H), rem = P32 - b * (W * H), Y = rem / W, X = rem - Y * W;
-    float acc[8];
-#pragma unroll
-    for (int k = 0; k < 8; ++k) acc[k] = bias[j * 8 + k];
-    for (int ky = (Y & 1); ky < 3; ky += 2) {
-      const int ii = (Y - ky) >> 1;
-      if (ii < 0 || ii >= h) continue;
-      for (int kx = (X & 1); kx < 3; kx += 2) {
-        const int jj = (X - kx) >> 1;
-        if (jj < 0 || jj >= w) continue;
-        uint4 v = ldg128(ycol + (((long)b * h + ii) * w + jj) * 720 + (ky * 3 + kx) * 80 + j * 8);
-        float2 a = unpack_bf16x2(v.x), bb = unpack_bf16x2(v.y), c = unpack_bf16x2(v.z), d = unpack_bf16x2(v.w);
-        acc[0] += a.x;
-        acc[1] += a.y;
-        acc[2] += bb.x;
-        acc[3] += bb.y;
-        acc[4] += c.x;
-        acc[5] += c.y;
-        acc[6] += d.x;
-        acc[7] += d.y;
-      }
-    }
-    const uint4 pk = pack8(acc);
-    *reinterpret_cast<uint4*>(out + P * Ct + o_off + j * 8) = pk;
-    if (out_xp != nullptr) *reinterpret_cast<uint4*>(out_xp + dact_index((long)B * H * W, P, o_off + j * 8)) = pk;
-  }
-}
-
-int launch_tu_col2im(const __nv_bfloat16* ycol, __nv_bfloat16* out, __nv_bfloat16* out_xp, const float* bias, int B, int h,
-                     int w, int H, int W, int Ct, int o_off, cudaStream_t st) {
-  long total = (long)B * H * W * 10;
-  int grid = (int)std::min<long>((total + 255) / 256, 148L * 16);
-  { ProfScope _ps(KC_TU_COL2IM, st);
-  tu_col2im_kernel<<<grid, 256, 0, st>>>(ycol, out, out_xp, bias, B, h, w, H, W, Ct, o_off); }
-  RL_CUDA(cudaGetLastError());
-  return RL_OK;
-}
 
 // ================================================================================================
 // label histogram (getClassWeight, reference TrainingBase.py:12-23: integer counts, reciprocal later)
