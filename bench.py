@@ -120,12 +120,12 @@ def algorithmic_bytes(B, H, W, train=True):
     for l in range(5):
         C = skips[l]
         out["gemm_px"] += px[l] * C * 2 + px[l + 1] * C * 2                      # TD forward
-        out["gemm_px"] += px[l + 1] * (80 * 2 + 720 * 2)                         # TU forward column matrix
+        out["gemm_px"] += px[l + 1] * 80 * 2 + px[l] * 80 * 2                    # TU forward: input slice, output slice
         if train:
             out["dgrad_td"] += px[l] * (2 * C + 4 * C + 2 * C)                   # x, dX rmw, dz
             out["wgrad"] += px[l] * (2 * C + 2 * C)
-            out["gemm_px"] += px[l + 1] * (720 * 2 + 80 * 2)                     # TU input gradient
-            out["wgrad"] += px[l + 1] * (80 * 2 + 720 * 2)
+            out["gemm_px"] += px[l] * 80 * 2 + px[l + 1] * 80 * 2                # TU input gradient: dz parity planes, dX slice
+            out["wgrad"] += px[l + 1] * 80 * 2 + px[l] * 80 * 2                  # TU weight gradient: x slice, dz parity planes
     if train:
         out["wgrad"] += px[0] * (288 * 2 + 32) + px[0] * (64 + 96)               # classifier, first conv
         out["head"] = px[0] * (288 * 2 + 288 * 2 + 32 + 1)                       # features, d(features), dl, label

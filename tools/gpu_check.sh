@@ -20,9 +20,10 @@ for what in "$@"; do
     graphtests) python -m pytest tests/test_graph_ddp_gpu.py -q -x -rP 2>&1 | tail -40 ;;
     perlaunch) python tools/per_launch.py > gpurun_out/per_launch.txt 2>&1; cat gpurun_out/per_launch.txt ;;
     perlaunch0) BWD_FUSED=0 python tools/per_launch.py > gpurun_out/per_launch_unfused.txt 2>&1; cat gpurun_out/per_launch_unfused.txt ;;
-    launches) python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/plain.log 2>&1 &&
-              ncu --metrics gpu__time_duration.sum --clock-control none -s 1200 -c 400 --csv --log-file gpurun_out/launches.csv \
-                  python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu.log 2>&1; tail -2 gpurun_out/ncu.log ;;
+    launches) # kernel list of one eager step (the graph replays the same kernels): skip the 3 warm-up steps, capture > 1 step
+              python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-graph > gpurun_out/plain.log 2>&1 &&
+              ncu --metrics gpu__time_duration.sum --clock-control none -s ${NCU_SKIP:-730} -c 300 --csv --log-file gpurun_out/launches.csv \
+                  python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-graph > gpurun_out/ncu.log 2>&1; tail -2 gpurun_out/ncu.log ;;
     ncu:*)    k="${what#ncu:}"   # one launch of kernel regex k (first occurrence after 3 warm-up steps) with the full metric set
               python tools/one_step.py > gpurun_out/plain_one_step.log 2>&1 &&
               ncu --set full --clock-control none --import-source on -k "regex:$k" -s ${NCU_SKIP:-0} -c 1 -f -o "gpurun_out/prof_$k" \
