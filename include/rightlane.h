@@ -205,6 +205,9 @@ int rl_selftest_umma_raw(const void* a_img, int a_bytes, unsigned long long a_de
 
 /* measurement hook: stream the channel window [c0, c0+nch) of an NHWC bf16 arena [npx][Ct] with 32-byte accesses
  * (mode 0 read, 1 read+write back) -- what the memory system delivers for the access pattern of the concat arenas */
+/* fragment layout probe of tcgen05.ld.16x256b.x4: out[128 threads][2 halves][16] receives the (lane << 8 | column) tags
+ * each thread read from a 128 x 32 TMEM block (tests/test_umma_selftest.py) */
+int rl_selftest_tmem_shapes(unsigned int* out, void* stream);
 int rl_selftest_stream(void* arena, long npx, int Ct, int c0, int nch, int mode, int grid, void* sink, void* stream);
 
 /* test hook: one 128 x N x K tcgen05 GEMM through the shared-memory operand conventions of csrc/rl_umma.cuh */

@@ -762,10 +762,12 @@ __global__ void __launch_bounds__(128, 2) gemm_px_kernel(GemmPxArgs a) {
   TileLoader<128> ld;
   const __nv_bfloat16* rowptr[4];
 
-  // row m of tile t -> arena pixel (or -1): the rows are window-major (the 4 pixels of a 2x2 pooling window adjacent)
+  // row m of tile t -> arena pixel (or -1).  Within each 32-row quarter (= the TMEM lanes one warp can read) the four
+  // positions of window w' sit in rows w', w' + 8, w' + 16, w' + 24: exactly the four lanes that two tcgen05.ld.16x256b
+  // deliver to ONE thread, so the 2x2 max-pool is a per-thread operation (no shuffles, no redundant lanes)
   auto pixel_of = [&](long t, int m) -> long {
     const int pr_ = (int)(t / a.wblocks), wb_ = (int)(t - (long)pr_ * a.wblocks);
-    const int win = m >> 2, q = m & 3;
+    const int win = ((m >> 5) << 3) | (m & 7), q = (m >> 3) & 3;  // m = 32 * (win / 8) + 8 * q + win % 8
     const int wi = wb_ * 32 + win;
     if (wi >= a.Wp) return -1;
     const int img = pr_ / a.Hp, py = pr_ - img * a.Hp;
@@ -844,53 +846,47 @@ __global__ void __launch_bounds__(128, 2) gemm_px_kernel(GemmPxArgs a) {
       mbar_wait(&bar_done[s], u & 1);
       tc_fence_after();
     }
-    // ---- epilogue: thread = accumulator row
+    // ---- epilogue: thread (warp, lane) owns window 8 * warp + lane / 4 and, in every 16-column block, the four columns
+    // 8k + 2(lane % 4) + e; the packed weights permute the output channels so that those are channels 4(lane % 4) + 2k + e
+    // of the block (rl_misc.cu pack kind 2): 8 contiguous bytes per thread, 32 per quad.  +bias and the non-negative
+    // Dropout2d scale are the same for the four pixels of a window, so they commute with the max.
     {
-      const int win = tid >> 2, q = tid & 3, wi = wb * 32 + win;
+      const int win = warp * 8 + (lane >> 2), qc = lane & 3, wi = wb * 32 + win;
       const int img = pr / a.Hp, py = pr % a.Hp;
       const bool valid = wi < a.Wp;
       const size_t opx = ((size_t)img * a.Hp + py) * a.Wp + wi;
+      const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);
       for (int c0 = 0; c0 < np; c0 += 16) {
-        float v[16];
-        tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16) + c0, v);
-        uint32_t pk[8];
-        uint32_t am[4] = {0, 0, 0, 0};
-        // 2x2 max-pool over the four lanes of a quad, on the raw accumulators (+bias and the non-negative Dropout2d scale
-        // are the same for the four pixels of a window, so they commute with the max and are applied to the pooled value
-        // only).  The window position rides in the two lowest mantissa bits (3 - q, so that the first position wins a
-        // tie): one max butterfly yields value and arg-max together; the 2-bit perturbation is far below bf16 rounding.
+        float r0[8], r1[8];
+        tmem_ld_16x256b_x2(lane_base + c0, r0);                      // positions 0 (regs 4k+e) and 1 (regs 4k+2+e)
+        tmem_ld_16x256b_x2(lane_base + (16u << 16) + c0, r1);        // positions 2 and 3
+        tmem_wait_ld();
+        reg_fence8(r0);
+        reg_fence8(r1);
+        const int cl = c0 + 4 * qc;  // first of this thread's four channels (part-local)
+        const float4 b4 = *reinterpret_cast<const float4*>(s_bias + cl), m4 = *reinterpret_cast<const float4*>(s_mask + cl);
+        const float bb[4] = {b4.x, b4.y, b4.z, b4.w}, mm[4] = {m4.x, m4.y, m4.z, m4.w};
+        float o[4];
+        uint32_t am = 0;
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          float t = __int_as_float((__float_as_int(v[i]) & ~3) | (3 - q));
-          t = fmaxf(t, __shfl_xor_sync(0xffffffffu, t, 1));
-          t = fmaxf(t, __shfl_xor_sync(0xffffffffu, t, 2));
-          am[i >> 2] |= (uint32_t)(3 - (__float_as_int(t) & 3)) << (8 * (i & 3));
-          v[i] = t;
+        for (int i = 0; i < 4; ++i) {  // channel cl + i = 2k + e
+          const int k = i >> 1, e = i & 1;
+          float mx = r0[4 * k + e];
+          uint32_t arg = 0;
+          const float v1 = r0[4 * k + 2 + e], v2 = r1[4 * k + e], v3 = r1[4 * k + 2 + e];
+          if (v1 > mx) { mx = v1; arg = 1; }   // strict: the first position wins a tie, as torch's max_pool2d
+          if (v2 > mx) { mx = v2; arg = 2; }
+          if (v3 > mx) { mx = v3; arg = 3; }
+          am |= arg << (8 * i);
+          o[i] = (mx + bb[i]) * mm[i];
         }
-        {
-          const float4* bp = reinterpret_cast<const float4*>(s_bias + c0);
-          const float4* mp = reinterpret_cast<const float4*>(s_mask + c0);
-#pragma unroll
-          for (int i4 = 0; i4 < 4; ++i4) {
-            const float4 b4 = bp[i4], m4 = mp[i4];
-            v[4 * i4 + 0] = (v[4 * i4 + 0] + b4.x) * m4.x;
-            v[4 * i4 + 1] = (v[4 * i4 + 1] + b4.y) * m4.y;
-            v[4 * i4 + 2] = (v[4 * i4 + 2] + b4.z) * m4.z;
-            v[4 * i4 + 3] = (v[4 * i4 + 3] + b4.w) * m4.w;
-          }
-        }
-        if (valid && q == 0) {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) pk[i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
-          uint4* dst = reinterpret_cast<uint4*>(a.out + opx * a.ldo + a.o_off + n0 + c0);
-          dst[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-          dst[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-          if (a.out_xp != nullptr) {
-            uint4* d2 = reinterpret_cast<uint4*>(a.out_xp + dact_index(a.out_xp_npx, (long)opx, a.o_off + n0 + c0));
-            d2[0] = dst[0];
-            d2[1] = dst[1];
-          }
-          if (a.amax) *reinterpret_cast<uint4*>(a.amax + opx * a.N + n0 + c0) = make_uint4(am[0], am[1], am[2], am[3]);
+        if (valid) {
+          const uint2 pk = make_uint2(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]));
+          const int ch = a.o_off + n0 + cl;
+          *reinterpret_cast<uint2*>(a.out + opx * a.ldo + ch) = pk;
+          if (a.out_xp != nullptr)
+            *reinterpret_cast<uint2*>(a.out_xp + ((size_t)(ch >> 4) * (size_t)a.out_xp_npx + opx) * 16 + (ch & 15)) = pk;
+          if (a.amax) *reinterpret_cast<uint32_t*>(a.amax + opx * a.N + n0 + cl) = am;
         }
       }
     }

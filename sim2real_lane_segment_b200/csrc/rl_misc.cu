@@ -38,7 +38,7 @@ __global__ void pack_weights_kernel(const PackEntry* tab, const float* __restric
           for (int k = 0; k < 8; ++k) v[k] = w[((long)(half * 8 + k) * C + ref_channel(c, e.cs_perm)) * 9 + tap];
         break;
       }
-      case 2: {  // TD fwd: parts back to back, [kc][jc][nl][8 c]
+      case 2: {  // TD fwd: parts back to back, [kc][jc][nl][8 c], nl = accumulator column
         int nkc = (C + 63) / 64;
         long p0 = (long)nkc * 8 * e.np0;
         int n0 = 0, np = e.np0;
@@ -49,7 +49,9 @@ __global__ void pack_weights_kernel(const PackEntry* tab, const float* __restric
           np = C - e.np0;
         }
         int kc = (int)(il / (8 * np)), jc = (int)((il % (8 * np)) / np), nl = (int)(il % np);
-        int c0 = kc * 64 + jc * 8, co = n0 + nl;
+        // accumulator column nl = 16 blk + 8k + 2q + e holds output channel 16 blk + 4q + 2k + e: the pooling epilogue's
+        // tcgen05.ld.16x256b hands thread (lane % 4 = q) the columns 8k + 2q + e, i.e. four contiguous channels
+        int c0 = kc * 64 + jc * 8, co = n0 + (nl & ~15) + 4 * ((nl >> 1) & 3) + 2 * ((nl >> 3) & 1) + (nl & 1);
         for (int k = 0; k < 8; ++k)
           if (c0 + k < C) v[k] = w[(long)co * C + c0 + k];
         break;

@@ -191,3 +191,54 @@ extern "C" int rl_selftest_umma_raw(const void* a_img, int a_bytes, unsigned lon
   RL_CUDA(cudaGetLastError());
   return RL_OK;
 }
+
+// ------------------------------------------------------------------------------------------------
+// Pins the register fragment layout of tcgen05.ld.16x256b (used by the pooling epilogue of TransitionDown): every TMEM
+// cell (lane, column) of a 128 x 32 block is written with the tag (lane << 8 | column) through tcgen05.st.32x32b, then each
+// warp reads its lane quarter back with two 16x256b.x4 loads (lanes +0..15 and +16..31).  out[tid][half][16] = the tags each
+// thread received.
+// ------------------------------------------------------------------------------------------------
+namespace rl {
+__global__ void __launch_bounds__(128, 1) tmem_shape_probe_kernel(uint32_t* out) {
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  if (warp == 0) tmem_alloc(&tmem_base_s, 32);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_s;
+  const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);
+  for (int c0 = 0; c0 < 32; c0 += 16) {
+    uint32_t r[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) r[i] = ((uint32_t)tid << 8) | (uint32_t)(c0 + i);
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(lane_base + c0),
+        "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
+        "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+        : "memory");
+  }
+  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  for (int half = 0; half < 2; ++half) {
+    uint32_t v[16];
+    tmem_ld_16x256b_x4(lane_base + ((uint32_t)(16 * half) << 16), v);
+    tmem_wait_ld();
+#pragma unroll
+    for (int i = 0; i < 16; ++i) out[(tid * 2 + half) * 16 + i] = v[i];
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 32);
+}
+}  // namespace rl
+
+extern "C" int rl_selftest_tmem_shapes(unsigned int* out, void* stream) {
+  using namespace rl;
+  if (!out) return rl_fail(RL_ERR_ARG, "rl_selftest_tmem_shapes: null argument");
+  tmem_shape_probe_kernel<<<1, 128, 0, (cudaStream_t)stream>>>(out);
+  RL_CUDA(cudaGetLastError());
+  return RL_OK;
+}

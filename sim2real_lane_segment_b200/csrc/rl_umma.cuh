@@ -207,6 +207,27 @@ __device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, float* v) {
       : "r"(taddr)
       : "memory");
 }
+// 16 lanes x 256 bits per instruction, x4 along the columns (32 columns): thread t receives, for k = 0..3, the cells
+// (lane t/4, column 8k + 2(t%4) + {0,1}) in v[4k], v[4k+1] and (lane t/4 + 8, same columns) in v[4k+2], v[4k+3]
+// (pinned by tests/test_umma_selftest.py::test_tmem_ld_16x256b_layout).  taddr's lane must be a multiple of 16.
+// x2: 16 columns, v[4k + {0,1}] = (lane t/4, column 8k + 2(t%4) + {0,1}), v[4k + {2,3}] = (lane t/4 + 8, same columns), k = 0..1
+__device__ __forceinline__ void tmem_ld_16x256b_x2(uint32_t taddr, float* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.16x256b.x2.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+      : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_16x256b_x4(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.16x256b.x4.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+        "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void reg_fence16(float* v) {
   asm volatile(""
