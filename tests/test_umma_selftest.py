@@ -120,3 +120,25 @@ def test_sw128_mnmajor_a_operand_from_tensor_map_box_layout():
     _lib.check(rc)
     torch.cuda.synchronize()
     torch.testing.assert_close(D.cpu(), ref, rtol=1e-4, atol=1e-3)
+
+
+@pytest.mark.gpu
+def test_tmem_ld_16x256b_layout():
+    """fragment layout of tcgen05.ld.16x256b.x4 that TransitionDown's pooling epilogue (csrc/rl_conv_fwd.cu) relies on:
+    thread t of a warp receives lanes t/4 and t/4 + 8 (first load) / t/4 + 16 and t/4 + 24 (second load, lane base + 16) of
+    the warp's 32-lane quarter, columns 8k + 2(t%4) + {0,1}"""
+    import ctypes
+    L = _lib.lib()
+    out = torch.zeros(128, 2, 16, dtype=torch.int32, device="cuda")
+    _lib.check(L.rl_selftest_tmem_shapes(ctypes.c_void_p(out.data_ptr()), _lib.cur_stream()))
+    torch.cuda.synchronize()
+    o = out.cpu()
+    for t in range(128):
+        w, l = t // 32, t % 32
+        for half in range(2):
+            for k in range(4):
+                for j in range(4):
+                    lane = 32 * w + 16 * half + l // 4 + (8 if j >= 2 else 0)
+                    col = 8 * k + 2 * (l % 4) + (j & 1)
+                    v = int(o[t, half, 4 * k + j])
+                    assert (v >> 8, v & 255) == (lane, col), (t, half, k, j, v >> 8, v & 255)

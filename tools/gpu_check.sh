@@ -28,6 +28,15 @@ for what in "$@"; do
               python tools/one_step.py > gpurun_out/plain_one_step.log 2>&1 &&
               ncu --set full --clock-control none --import-source on -k "regex:$k" -s ${NCU_SKIP:-0} -c 1 -f -o "gpurun_out/prof_$k" \
                   python tools/one_step.py > "gpurun_out/ncu_$k.log" 2>&1; tail -3 "gpurun_out/ncu_$k.log" ;;
+    refarm)   python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_reference.json 2> gpurun_out/bench_reference.err; cat gpurun_out/bench_reference.json ;;
+    final)    # everything the round-end driver runs, plus the secondary workloads; JSON lines land in gpurun_out/
+              python -m pytest tests -m gpu -q 2>&1 | tail -5
+              python __graft_entry__.py smoke 2>&1 | tail -1
+              python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err; cut -c1-400 gpurun_out/bench.json
+              python bench.py --workload infer --no-cpu-baseline > gpurun_out/bench_infer.json 2> gpurun_out/bench_infer.err; cut -c1-300 gpurun_out/bench_infer.json
+              python bench.py --workload mme --no-cpu-baseline > gpurun_out/bench_mme.json 2> gpurun_out/bench_mme.err; cut -c1-300 gpurun_out/bench_mme.json
+              python bench.py --no-graph --no-cpu-baseline > gpurun_out/bench_nograph.json 2> gpurun_out/bench_nograph.err; cut -c1-300 gpurun_out/bench_nograph.json
+              python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_reference.json 2> gpurun_out/bench_reference.err; cut -c1-400 gpurun_out/bench_reference.json ;;
     *) echo "unknown step $what" ;;
   esac
 done
