@@ -320,8 +320,10 @@ __global__ void __launch_bounds__(kF2Threads, 1) dense_fwd_tma_kernel(const __gr
   uint8_t* sA = smem;
   uint8_t* sW = smem + NA * kF2ABytes;
   float* zs = reinterpret_cast<float*>(sW + (wres ? nkc : kF2W) * kF2WBytes);  // col2im ring [4][kRing][4]
+  // per-channel BN scale / shift, stored per 64-channel chunk as [half][group j][4]: channel kc*64 + 8j + 4*half + i sits at
+  // kc*64 + 32*half + 4j + i, so that the eight groups read by a quarter-warp are 128 contiguous bytes (no bank conflict)
   float* s_s = zs + 4 * kRing * 4;
-  float* s_t = s_s + a.Cin;
+  float* s_t = s_s + ((a.Cin + 63) & ~63);
   // a_full: TMA bytes landed; a_ready: 128 transform threads done; a_empty: the MMAs reading the stage retired
   __shared__ uint64_t a_full[kF2A], a_ready[kF2A], a_empty[kF2A], w_full[kF2W], w_empty[kF2W], acc_full[2], acc_empty[2];
   __shared__ uint32_t tmem_base_s;
@@ -365,8 +367,9 @@ __global__ void __launch_bounds__(kF2Threads, 1) dense_fwd_tma_kernel(const __gr
   if (tid < 16) s_bias16[tid] = a.bias[tid];
   for (int c = tid; c < a.Cin; c += kF2Threads) {
     BnCoef k = bn_coef(a.bn, c);
-    s_s[c] = k.s;
-    s_t[c] = k.t;
+    const int o = (c & ~63) + 32 * ((c >> 2) & 1) + 4 * ((c >> 3) & 7) + (c & 3);
+    s_s[o] = k.s;
+    s_t[o] = k.t;
   }
   tc_fence_before();
   __syncthreads();
@@ -467,10 +470,10 @@ __global__ void __launch_bounds__(kF2Threads, 1) dense_fwd_tma_kernel(const __gr
         const int ck = min(64, a.Cin - kc * 64);
         mbar_wait(&a_full[s], ph);
         if (8 * j < ck) {
-          const float* sp = s_s + kc * 64 + 8 * j;
-          const float* tp = s_t + kc * 64 + 8 * j;
-          const float4 s0 = *reinterpret_cast<const float4*>(sp), s1 = *reinterpret_cast<const float4*>(sp + 4);
-          const float4 t0 = *reinterpret_cast<const float4*>(tp), t1 = *reinterpret_cast<const float4*>(tp + 4);
+          const float* sp = s_s + kc * 64 + 4 * j;
+          const float* tp = s_t + kc * 64 + 4 * j;
+          const float4 s0 = *reinterpret_cast<const float4*>(sp), s1 = *reinterpret_cast<const float4*>(sp + 32);
+          const float4 t0 = *reinterpret_cast<const float4*>(tp), t1 = *reinterpret_cast<const float4*>(tp + 32);
           uint4* base = reinterpret_cast<uint4*>(sA + s * kF2ABytes) + tid;
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
@@ -662,7 +665,7 @@ int launch_dense_fwd_tma(const DenseFwdArgs& a, const void* tmap, int grid, cuda
   P.a = a;
   P.strip_mode = strip_mode;
   const int nkc = (a.Cin + 63) / 64;
-  const size_t fixed = 1024 + 4 * kRing * 16 + (size_t)a.Cin * 8;
+  const size_t fixed = 1024 + 4 * kRing * 16 + (size_t)((a.Cin + 63) & ~63) * 8;
   const size_t wall = (size_t)nkc * kF2WBytes;
   if (fixed + wall + 3 * kF2ABytes <= kCap) {
     P.w_resident = 1;
