@@ -460,9 +460,12 @@ struct BwdCtx {
   size_t tmp_stride;
 };
 
+// pixel range per CTA of a weight-gradient launch.  Every CTA ends with a full set of atomics for its [channels x N] block, so
+// a CTA gets at least kMinChunks 64-pixel chunks: at the small levels the atomics, not the MMAs, are the cost.
 long wgrad_px_per_cta(long npx, long want_runs, int* nruns) {
+  constexpr long kMinChunks = 8;
   const long chunks = (npx + 63) / 64;
-  const long runs = std::max(1L, std::min(want_runs, chunks));
+  const long runs = std::max(1L, std::min(want_runs, (chunks + kMinChunks - 1) / kMinChunks));
   const long cpr = (chunks + runs - 1) / runs;
   *nruns = (int)((chunks + cpr - 1) / cpr);
   return cpr * 64;
