@@ -25,6 +25,7 @@ int configure_kernels() {
   if ((rc = configure_fwd_kernels())) return rc;
   if ((rc = configure_bwd_kernels())) return rc;
   if ((rc = configure_tu_kernels())) return rc;
+  if ((rc = configure_td_kernels())) return rc;
   return configure_fused_kernels();
 }
 }
@@ -322,8 +323,12 @@ static int forward_layer(Plan* p, int li, const float* params, const float* bnbu
     a.out_xp_npx = lo.px;
     int npmax = 0;
     for (int q = 0; q < nparts; ++q) npmax = std::max(npmax, a.part_np[q]);
-    int gx = (int)std::max(1L, std::min(a.ntiles, (long)((npmax <= 128 ? 3 : 2) * sm) / nparts));
-    if ((rc = launch_gemm_px(a, gx, nparts, st))) return rc;
+    if (td_fwd_fits(a.K, a.part_np, nparts)) {
+      if ((rc = launch_td_fwd(a, (int)std::max(1L, std::min(a.ntiles, (long)sm / nparts)), nparts, st))) return rc;
+    } else {
+      int gx = (int)std::max(1L, std::min(a.ntiles, (long)((npmax <= 128 ? 3 : 2) * sm) / nparts));
+      if ((rc = launch_gemm_px(a, gx, nparts, st))) return rc;
+    }
     if (train && (rc = launch_channel_stats(act_of(p, L.lvl_out), lo.px, lo.Ct, 0, L.cout, stats_of(p, L.lvl_out), sm, st)))
       return rc;
   } else {  // L_TU: all four output parities of a tile of low-resolution positions in one kernel (rl_tu.cu)

@@ -47,6 +47,10 @@ struct GemmPxArgs {
   uint8_t* amax;
 };
 int launch_gemm_px(const GemmPxArgs& a, int grid_x, int nparts, cudaStream_t st);
+// warp-specialised variant with the part's weights resident in shared memory (rl_td.cu); td_fwd_fits: its shared memory suffices
+bool td_fwd_fits(int K, const int* part_np, int nparts);
+int launch_td_fwd(const GemmPxArgs& a, int grid_x, int nparts, cudaStream_t st);
+int configure_td_kernels();
 
 // ---------------------------------------------------------------- backward, tensor core
 struct DgradArgs {

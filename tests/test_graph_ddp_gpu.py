@@ -106,7 +106,9 @@ def test_fused_optimizer_state_dict_roundtrip():
     assert torch.equal(o2.exp_avg, o1.exp_avg) and torch.equal(o2.exp_avg_sq, o1.exp_avg_sq)
     for o, m in ((o1, m1), (o2, m2)):
         o.zero_grad(); m.training_step((x, y), 3).backward(); o.step()
-    assert rel_err(m2.runtime().params, m1.runtime().params) < 1e-5
+    # two runs of the same step differ by the order of their fp32 atomics, and Adam's m / sqrt(v) amplifies that: measured
+    # 8e-6 .. 3.2e-5; a wrong step counter or hyper-parameter after the round trip shows up at 1e-3 and above
+    assert rel_err(m2.runtime().params, m1.runtime().params) < 2e-4
     ref = torch.optim.AdamW(m1.parameters(), lr=1e-3, weight_decay=1e-4)   # same state layout as the stock optimizer
     ref.load_state_dict(o1.state_dict())
     assert float(ref.state[next(iter(m1.parameters()))]["step"]) == 4.0
