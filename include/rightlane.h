@@ -208,6 +208,10 @@ int rl_selftest_umma_raw(const void* a_img, int a_bytes, unsigned long long a_de
 /* fragment layout probe of tcgen05.ld.16x256b.x4: out[128 threads][2 halves][16] receives the (lane << 8 | column) tags
  * each thread read from a 128 x 32 TMEM block (tests/test_umma_selftest.py) */
 int rl_selftest_tmem_shapes(unsigned int* out, void* stream);
+/* the tensor map with overlapping dimensions that delivers the im2col tile of a DenseLayer's dz planes in one TMA box
+ * (csrc/rl_bwd_fused.cu): planes = bf16 [2][npos][8] (device), box start coordinate c1 along the position dimension;
+ * out receives the 18 x 64 x 16-byte tile as it landed in shared memory */
+int rl_selftest_im2col_tmap(const void* planes, long npos, long positions, int W, int c1, void* out, void* stream);
 int rl_selftest_stream(void* arena, long npx, int Ct, int c0, int nch, int mode, int grid, void* sink, void* stream);
 
 /* test hook: one 128 x N x K tcgen05 GEMM through the shared-memory operand conventions of csrc/rl_umma.cuh */

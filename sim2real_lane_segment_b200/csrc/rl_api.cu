@@ -209,6 +209,9 @@ int rl_plan_bind(rl_plan* h, void* workspace, void* stream) {
         int rc = encode_dz_tmap(p.tmap_dz[l][q], wsb(&p) + lv.dzp_off + (size_t)q * lv.dzp_npos * 32, lv.dzp_npos, lv.dzp_guard,
                                 lv.W, (long)p.B * (lv.H + 1), bulk_tile_pitch(lv.W));
         if (rc) return rc;
+        rc = encode_dz_im2col_tmap(p.tmap_dz_im2col[l][q], wsb(&p) + lv.dzp_off + (size_t)q * lv.dzp_npos * 32, lv.dzp_npos,
+                                   lv.dzp_npos - 2 * (lv.W + 2) - 2, lv.W);
+        if (rc) return rc;
       }
   if (p.training && !p.side_stream) {
     cudaStream_t s2;
@@ -835,9 +838,12 @@ int backward_block(BwdCtx& c, int bi) {
     w.inv_n = 1.0 / (double)lv.px;
     w.acc = acc_of(p, b.lvl);
     w.C0 = b.C0;
+    w.B = p->B;
     int nruns;
-    w.px_per_cta = wgrad_px_per_cta(lv.px, std::max(1, (2 * sm) / std::max(1, groups_total)), &nruns);
-    if ((rc = launch_wgrad_dense2(w, nruns, groups_max, c.st2))) return rc;
+    w.pos_per_cta = wgrad_px_per_cta((long)p->B * (lv.H + 1) * (lv.W + 2), std::max(1, (2 * sm) / std::max(1, groups_total)), &nruns);
+    const void* tm5[kBlockLayers];
+    for (int j = 0; j < kBlockLayers; ++j) tm5[j] = p->tmap_dz_im2col[b.lvl][j];
+    if ((rc = launch_wgrad_dense2(w, tm5, nruns, groups_max, c.st2))) return rc;
   }
   if (c.overlap) {
     RL_CUDA(cudaEventRecord((cudaEvent_t)p->ev_blk[b.lvl], c.st2));

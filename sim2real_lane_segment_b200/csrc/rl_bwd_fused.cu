@@ -306,6 +306,57 @@ int encode_dz_tmap(void* tmap_out, const void* plane0, long npos, long guard, in
   return RL_OK;
 }
 
+// im2col of the dz planes as ONE tensor-map box.  The tap (dy, dx) of position pos sits at pos - dy (W+2) - dx, so the
+// nine taps of 64 consecutive positions are a box over the *overlapping* dimensions
+//   (64 positions x 8 channels [contiguous], 3 x-offsets [stride 16 B], 3 y-offsets [stride (W+2) 16 B], 2 planes)
+// starting at position pos0 - (W+2) - 1.  It lands in shared memory as [plane][iy][ix][64 rows][8] = the chunk layout
+// T[j][row][8] with j = 9 plane + 3 iy + ix, tap = 3 (2 - iy) + (2 - ix): the weight-gradient kernel's B operand, without a
+// single address computation.  positions: positions addressable along dimension 1 (the rest of the plane is slack for the
+// offset dimensions; out-of-range coordinates are zero-filled).
+int encode_dz_im2col_tmap(void* tmap_out, const void* plane0, long npos, long positions, int W) {
+  typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                               const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static EncodeFn fn = nullptr;
+  if (fn == nullptr) {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    RL_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q));
+    if (f == nullptr || q != cudaDriverEntryPointSuccess) return rl_fail(RL_ERR_CUDA, "cuTensorMapEncodeTiled not available");
+    fn = (EncodeFn)f;
+  }
+  CUtensorMap tm;
+  // the 64 positions x 8 channels of one (plane, iy, ix) are 1024 contiguous bytes: declared as 256 32-bit elements so that
+  // the box's inner dimension is one 1 KB row (a 16-byte inner dimension made the copy 1152 separate rows and slower than
+  // the cp.async gather it replaced)
+  const cuuint64_t dims[4] = {(cuuint64_t)positions * 4, 3, 3, 2};
+  const cuuint64_t strides[3] = {16, (cuuint64_t)(W + 2) * 16, (cuuint64_t)npos * 16};
+  const cuuint32_t box[4] = {256, 3, 3, 2};
+  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  const CUresult r = fn(&tm, CU_TENSOR_MAP_DATA_TYPE_UINT32, 4, const_cast<void*>(plane0), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return rl_fail(RL_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) for the dz im2col map (W=%d)", (int)r, W);
+  memcpy(tmap_out, &tm, sizeof(tm));
+  return RL_OK;
+}
+
+__global__ void __launch_bounds__(128, 1) im2col_tmap_probe_kernel(const __grid_constant__ CUtensorMap tm, int c1, uint4* out) {
+  __shared__ __align__(128) uint8_t tile[18 * 64 * 16];
+  __shared__ uint64_t bar;
+  if (threadIdx.x == 0) {
+    mbar_init(&bar, 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    mbar_arrive_expect_tx(&bar, 18 * 64 * 16);
+    tma_load_4d(tile, &tm, 4 * c1, 0, 0, 0, &bar);
+  }
+  mbar_wait(&bar, 0);
+  for (int i = threadIdx.x; i < 18 * 64; i += 128) out[i] = reinterpret_cast<const uint4*>(tile)[i];
+}
+
 // ================================================================================================
 // wgrad_dense2_kernel — D[row, n] = Σ_p A[p, row] · Bm[p, n],  K = pixels in chunks of 64, N = 144 (9 taps x 16).
 // A CTA owns a pixel range and up to two 64-channel blocks of one layer (grid.y = block group, grid.z = layer): rows
@@ -314,12 +365,14 @@ int encode_dz_tmap(void* tmap_out, const void* plane0, long npos, long guard, in
 // the relu decision fma(x, s, t) > 0 of a channel is monotone in x, so it equals a comparison of ±x with a per-channel
 // bf16 threshold (relu_threshold), exact for every bf16 x.  With D2'' and D1 the two accumulators of a channel,
 //   D2 = r·D2'' - r·(mean - c)·D1          (x̂ = r·(x - c) - r·(mean - c))
-// and dW, dγ, dβ follow as in the file header.  The im2col tile of dz is gathered once per chunk and shared by the
-// blocks' MMAs (4-deep rings); accumulators: 2 x 144 TMEM columns.  17 warps: 16 producers hand chunks to one MMA-issuing
-// warp through mbarriers (no block-wide barrier in the main loop).
+// and dW, dγ, dβ follow as in the file header.  K runs over the positions of the zero-padded dz planes, so the im2col tile
+// of a 64-position chunk is ONE TMA box (encode_dz_im2col_tmap above) shared by the blocks' MMAs, and the A rows of pad
+// positions are zero (4-deep rings); accumulators: 2 x 144 TMEM columns.  18 warps: 16 A-operand producers, one MMA-issuing
+// warp, one TMA warp; mbarriers only, no block-wide barrier in the main loop.  (The tile used to be gathered with 1152
+// cp.async per chunk: 38 % of the kernel's shared-memory wavefronts and half of the producers' instructions.)
 // ================================================================================================
-constexpr int kWg2Producers = 512;              // warps 0-15: operand producers (warps 0-7 also read the accumulators out)
-constexpr int kWg2Threads = kWg2Producers + 32;  // warp 16: MMA issue
+constexpr int kWg2Producers = 512;              // warps 0-15: A-operand producers (warps 0-7 also read the accumulators out)
+constexpr int kWg2Threads = kWg2Producers + 64;  // warp 16: MMA issue, warp 17: the im2col TMA
 constexpr int kWg2MaxMb = 2;
 constexpr int kWg2AccStride = 160;
 constexpr int kWg2BBytes = 18 * 64 * 16;  // 18432
@@ -357,7 +410,13 @@ __device__ __forceinline__ void relu_threshold(float s, float t, uint32_t* sgn_b
   *thr_bits = bf16_unkey(key);
 }
 
-__global__ void __launch_bounds__(kWg2Threads, 1) wgrad_dense2_kernel(const __grid_constant__ WgDenseArgs a) {
+struct alignas(64) WgDenseParams {
+  CUtensorMap tm[kBlockLayers];  // im2col maps of the layers' dz planes (encode_dz_im2col_tmap)
+  WgDenseArgs a;
+};
+
+__global__ void __launch_bounds__(kWg2Threads, 1) wgrad_dense2_kernel(const __grid_constant__ WgDenseParams P) {
+  const WgDenseArgs& a = P.a;
   const WgDenseLayer& L = a.L[blockIdx.z];
   const int nb_total = (L.Cin + 63) / 64;
   const int ngroups = (nb_total + kWg2MaxMb - 1) / kWg2MaxMb;
@@ -389,7 +448,7 @@ __global__ void __launch_bounds__(kWg2Threads, 1) wgrad_dense2_kernel(const __gr
 
   if (tid == 0) {
     for (int i = 0; i < kWg2BStages; ++i) {
-      mbar_init(&bar_full[i], kWg2Producers);
+      mbar_init(&bar_full[i], 4 + 1);  // the four warps of the stage's producer group + the TMA thread's expect-tx arrival
       mbar_init(&bar_done[i], 1);
     }
     fence_mbar_init();
@@ -415,9 +474,13 @@ __global__ void __launch_bounds__(kWg2Threads, 1) wgrad_dense2_kernel(const __gr
   const uint32_t tmem = tmem_base_s;
   const uint32_t idesc = umma_idesc_bf16(144, 1, 1);
 
-  const long P0 = (long)blockIdx.x * a.px_per_cta, P1 = min(P0 + a.px_per_cta, a.npx);
-  const int nchunks = P1 > P0 ? (int)((P1 - P0 + 63) / 64) : 0;
-  const long HW = (long)a.H * a.W;
+  // K runs over the POSITIONS of the zero-padded dz planes (vrow * (W+2) + col; col 0 / W+1 and row H of every image are
+  // pads, 2 % of the positions at 120x160): the im2col tile of 64 consecutive positions is then one TMA box, and the A rows
+  // of pad positions are zero
+  const int PW = a.W + 2;
+  const long nposK = (long)a.B * (a.H + 1) * PW;
+  const long Q0 = (long)blockIdx.x * a.pos_per_cta, Q1 = min(Q0 + a.pos_per_cta, nposK);
+  const int nchunks = Q1 > Q0 ? (int)((Q1 - Q0 + 63) / 64) : 0;
 
   if (warp == 16) {
     // =============================================================== MMA issue: no block-wide barrier anywhere in the main
@@ -450,15 +513,48 @@ __global__ void __launch_bounds__(kWg2Threads, 1) wgrad_dense2_kernel(const __gr
     __syncthreads();
     return;
   }
+  if (warp == 17) {
+    // =============================================================== im2col of dz: one TMA box per chunk
+    if (lane == 0) {
+      const long c1 = a.dz_guard + Q0 - PW - 1;  // tap (dy,dx) of position q sits at q - dy*PW - dx: box offsets iy = 1 - dy, ix = 1 - dx
+      for (int k = 0; k < nchunks; ++k) {
+        const uint32_t s = (uint32_t)k & 3;
+        if (k >= 4) mbar_wait(&bar_done[s], ((k - 4) >> 2) & 1);  // the MMAs that read this stage have retired
+        mbar_arrive_expect_tx(&bar_full[s], kWg2BBytes);
+        tma_load_4d(sBring + s * kWg2BBytes, &P.tm[blockIdx.z], (int)(4 * (c1 + 64L * k)), 0, 0, 0, &bar_full[s]);
+      }
+    }
+    tc_fence_before();
+    __syncthreads();
+    return;
+  }
 
-  // ================================================================= producers, warps 0-15
-  // A tile: thread <-> (pixel row of the chunk, 16-channel group, 64-channel block): warps 0-7 serve block 0, warps 8-15
-  // block 1; one 32-byte load per chunk, carried pointer (consecutive pixels are contiguous in the planar mirror)
-  const int a_blk = warp >> 3, a_row = (warp & 7) * 8 + (lane & 7), a_g = lane >> 3;
+  // ================================================================= producers, warps 0-15, in four groups of four warps.
+  // Group g produces the A operands of the chunks k = g, g+4, ... into ring stage g.  fence.proxy.async, which every
+  // published stage needs, waits for the loads its thread has outstanding: a producer that prefetches its next chunk before
+  // publishing the current one runs at one DRAM latency per chunk (that was this kernel's pace: ~1600 cycles per chunk).  Here a
+  // thread issues the loads of its next chunk right AFTER the fence and meets them again three chunks of other groups' work
+  // later.
+  // thread <-> (64-channel block, 16-channel group) fixed, four pixel rows of the chunk: one 32-byte load per row
+  const int grp = warp >> 2, tg = tid & 127;
+  const int a_blk = tg >> 6, a_g = (tg >> 4) & 3, a_r0 = tg & 15;
   const int a_c = cbase + 64 * a_blk + 16 * a_g;
   const bool a_on = a_blk < nb && a_c < L.Cin;
-  const __nv_bfloat16* a_ptr = a.xp + dact_index(a.npx, P0 + a_row, a_on ? a_c : 0);
-  long a_P = P0 + a_row;
+  // carried position state of each of the thread's rows: column inside the padded plane row, image row (H = the pad row),
+  // pixel index of that row's first pixel ((b*H + y)*W; the pad row takes the next image's first row, so a wrap leaves it
+  // unchanged)
+  long a_q[4], a_pxrow[4];
+  int a_col[4], a_y[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    a_q[i] = Q0 + 64L * grp + a_r0 + 16 * i;
+    const long vrow = a_q[i] / PW;
+    a_col[i] = (int)(a_q[i] - vrow * PW);
+    const long b = vrow / (a.H + 1);
+    a_y[i] = (int)(vrow - b * (a.H + 1));
+    a_pxrow[i] = (b * a.H + a_y[i]) * a.W;
+  }
+  const __nv_bfloat16* a_base = a.xp + (size_t)((a_on ? a_c : 0) >> 4) * (size_t)a.npx * 16;
   // this thread's pair constants stay in registers for the whole kernel
   uint32_t kc2[8], kg2[8], kt2[8];
   {
@@ -468,110 +564,65 @@ __global__ void __launch_bounds__(kWg2Threads, 1) wgrad_dense2_kernel(const __gr
     kg2[0] = g0.x; kg2[1] = g0.y; kg2[2] = g0.z; kg2[3] = g0.w; kg2[4] = g1.x; kg2[5] = g1.y; kg2[6] = g1.z; kg2[7] = g1.w;
     kt2[0] = t0.x; kt2[1] = t0.y; kt2[2] = t0.z; kt2[3] = t0.w; kt2[4] = t1.x; kt2[5] = t1.y; kt2[6] = t1.z; kt2[7] = t1.w;
   }
-  // B tile (im2col of dz): row = tid & 63, column chunks j = (tid >> 6) + 8q, q = 0..2.  The pixel row advances by 64 pixels
-  // per chunk; its position in the zero-padded planes is carried along.  The tap at (dy,dx) of pixel (b,y,x) sits at
-  // pos - dy*(W+2) - dx, always in range.
-  const int b_row = tid & 63, b_j0 = tid >> 6;
-  long bpos = 0, b_P = P0 + b_row;
-  int bx = 0, by = 0;
-  long boff[3];
-  {
-    const long b = b_P / HW;
-    const int hw = (int)(b_P - b * HW);
-    by = hw / a.W;
-    bx = hw - by * a.W;
-    bpos = a.dz_guard + (b * (a.H + 1) + by) * (a.W + 2) + bx + 1;
+  u32x8 av[4];
+  bool avalid[4];
+  auto load_a = [&](int kc) {  // this group's chunk kc; advances the rows by four chunks
 #pragma unroll
-    for (int q = 0; q < 3; ++q) {
-      const int j = b_j0 + 8 * q, tap = j >> 1, half = j & 1;
-      boff[q] = j < 18 ? (long)half * a.dz_npos - (long)(tap / 3 - 1) * (a.W + 2) - (tap % 3 - 1) : 0;
-    }
-  }
-  const uint32_t sB_thr = smem_u32(sBring) + (uint32_t)(b_j0 * 64 + b_row) * 16;  // + stage, + q * 8 * 64 * 16
-  auto issue_b = [&](int kc, uint32_t stage) {
-    if (kc < nchunks) {
-      const bool pv = b_P < P1;
-      const __nv_bfloat16* src = L.dz + (pv ? bpos : (long)a.dz_guard) * 8;
-      const uint32_t dst = sB_thr + stage * kWg2BBytes;
-      const uint32_t sz = pv ? 16u : 0u;
-#pragma unroll
-      for (int q = 0; q < 3; ++q)
-        if (b_j0 + 8 * q < 18)
-          asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst + q * (8 * 64 * 16)), "l"(src + boff[q] * 8), "r"(sz)
-                       : "memory");
-      b_P += 64;
-      bx += 64;
-      bpos += 64;
-      while (bx >= a.W) {
-        bx -= a.W;
-        bpos += 2;  // the two pad columns of a plane row
-        if (++by == a.H) {
-          by = 0;
-          bpos += a.W + 2;  // the pad row between images
+    for (int i = 0; i < 4; ++i) {
+      avalid[i] = kc < nchunks && a_q[i] < Q1 && a_col[i] >= 1 && a_col[i] <= a.W && a_y[i] < a.H;
+      if (a_on && avalid[i]) av[i] = ldg256_nc(a_base + (size_t)(a_pxrow[i] + a_col[i] - 1) * 16);
+      else av[i].lo = av[i].hi = make_uint4(0, 0, 0, 0);
+      a_q[i] += 256;
+      a_col[i] += 256;
+      while (a_col[i] >= PW) {
+        a_col[i] -= PW;
+        if (a_y[i] == a.H) {
+          a_y[i] = 0;
+        } else {
+          ++a_y[i];
+          a_pxrow[i] += a.W;
         }
       }
     }
-    cp_async_commit();  // always: keeps the group count uniform
   };
-  struct ARegs {
-    u32x8 v;
-    bool valid;
-  };
-  auto load_a = [&](int kc, ARegs& r) {
-    r.valid = kc < nchunks && a_P < P1;
-    if (a_on && r.valid) r.v = ldg256_nc(a_ptr);
-    else r.v.lo = r.v.hi = make_uint4(0, 0, 0, 0);
-    a_ptr += 64 * 16;
-    a_P += 64;
-  };
-  const uint32_t sA_thr = smem_u32(sAring) + (uint32_t)(a_blk * 16384 + ((2 * a_g) * 64 + a_row) * 16);
-  uint32_t st_cur = 0;  // ring stage of chunk k (A and B rings have the same depth)
-  auto step = [&](int k, ARegs& r) {
-    if (a_blk < nb) {  // stage k%4: its last readers, the MMAs of chunk k-4, were waited for two steps ago
-      uint32_t xm[8], mm[8];
-      const uint32_t xs[8] = {r.v.lo.x, r.v.lo.y, r.v.lo.z, r.v.lo.w, r.v.hi.x, r.v.hi.y, r.v.hi.z, r.v.hi.w};
+  const uint32_t sA_thr = smem_u32(sAring) + (uint32_t)(grp * kAStage + a_blk * 16384 + ((2 * a_g) * 64 + a_r0) * 16);
+  load_a(grp);
+  for (int k = grp, u = 0; k < nchunks; k += 4, ++u) {
+    if (u > 0) mbar_wait(&bar_done[grp], (u - 1) & 1);  // the MMAs of chunk k-4 (this stage's previous tenant) have retired
+    if (a_blk < nb) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const __nv_bfloat162 xv = *reinterpret_cast<const __nv_bfloat162*>(&xs[i]);
-        const __nv_bfloat162 cv = *reinterpret_cast<const __nv_bfloat162*>(&kc2[i]);
-        const __nv_bfloat162 gv = *reinterpret_cast<const __nv_bfloat162*>(&kg2[i]);
-        const __nv_bfloat162 tv = *reinterpret_cast<const __nv_bfloat162*>(&kt2[i]);
-        uint32_t m = __hge2_mask(__hmul2(xv, gv), tv);  // 0xFFFF per channel whose relu is open
-        if (!(a_on && r.valid)) m = 0u;
-        const __nv_bfloat162 d = __hsub2(xv, cv);
-        xm[i] = *reinterpret_cast<const uint32_t*>(&d) & m;
-        mm[i] = m & 0x3F803F80u;
+      for (int i = 0; i < 4; ++i) {
+        uint32_t xm[8], mm[8];
+        const uint32_t xs[8] = {av[i].lo.x, av[i].lo.y, av[i].lo.z, av[i].lo.w, av[i].hi.x, av[i].hi.y, av[i].hi.z, av[i].hi.w};
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const __nv_bfloat162 xv = *reinterpret_cast<const __nv_bfloat162*>(&xs[e]);
+          const __nv_bfloat162 cv = *reinterpret_cast<const __nv_bfloat162*>(&kc2[e]);
+          const __nv_bfloat162 gv = *reinterpret_cast<const __nv_bfloat162*>(&kg2[e]);
+          const __nv_bfloat162 tv = *reinterpret_cast<const __nv_bfloat162*>(&kt2[e]);
+          uint32_t m = __hge2_mask(__hmul2(xv, gv), tv);  // 0xFFFF per channel whose relu is open
+          if (!(a_on && avalid[i])) m = 0u;
+          const __nv_bfloat162 d = __hsub2(xv, cv);
+          xm[e] = *reinterpret_cast<const uint32_t*>(&d) & m;
+          mm[e] = m & 0x3F803F80u;
+        }
+        // chunk layout T[j][row][8], 64 rows: channels 16g .. 16g+15 -> chunks 2g, 2g+1 (m·(x-c)) and 8+2g, 8+2g+1 (m)
+        const uint32_t d = sA_thr + i * 16 * 16;
+        asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(d), "r"(xm[0]), "r"(xm[1]), "r"(xm[2]), "r"(xm[3]) : "memory");
+        asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(d + 64 * 16), "r"(xm[4]), "r"(xm[5]), "r"(xm[6]), "r"(xm[7]) : "memory");
+        asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(d + 8 * 64 * 16), "r"(mm[0]), "r"(mm[1]), "r"(mm[2]), "r"(mm[3]) : "memory");
+        asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(d + 9 * 64 * 16), "r"(mm[4]), "r"(mm[5]), "r"(mm[6]), "r"(mm[7]) : "memory");
       }
-      // chunk layout T[j][row][8], 64 rows: channels 16g .. 16g+15 -> chunks 2g, 2g+1 (m·(x-c)) and 8+2g, 8+2g+1 (m)
-      const uint32_t d = sA_thr + st_cur * kAStage;
-      asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(d), "r"(xm[0]), "r"(xm[1]), "r"(xm[2]), "r"(xm[3]) : "memory");
-      asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(d + 64 * 16), "r"(xm[4]), "r"(xm[5]), "r"(xm[6]), "r"(xm[7]) : "memory");
-      asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(d + 8 * 64 * 16), "r"(mm[0]), "r"(mm[1]), "r"(mm[2]), "r"(mm[3]) : "memory");
-      asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(d + 9 * 64 * 16), "r"(mm[4]), "r"(mm[5]), "r"(mm[6]), "r"(mm[7]) : "memory");
     }
-    // Publish chunk k BEFORE the next global loads are issued: fence.proxy.async waits for the thread's outstanding
-    // memory operations, so a fence placed after the loads would expose a full DRAM latency in every step.
-    cp_async_wait<1>();  // this thread's part of B(k) has landed (B(k+1) may still be in flight)
-    fence_proxy_async();
-    mbar_arrive(&bar_full[st_cur]);
-    // stage (k+2)%4 is recycled next: the MMAs of chunk k-2, issued two steps ago, must have retired
-    const uint32_t st_next = (st_cur + 2) & 3;
-    if (k >= 2) mbar_wait(&bar_done[st_next], ((k - 2) >> 2) & 1);
-    load_a(k + 2, r);
-    issue_b(k + 2, st_next);
-    st_cur = (st_cur + 1) & 3;
-  };
-
-  ARegs r0, r1;
-  load_a(0, r0);
-  issue_b(0, 0);
-  load_a(1, r1);
-  issue_b(1, 1);
-  for (int kc = 0; kc < nchunks; kc += 2) {
-    step(kc, r0);
-    if (kc + 1 < nchunks) step(kc + 1, r1);
+    fence_proxy_async();  // nothing of this thread is in flight here: the next chunk's loads are issued below
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&bar_full[grp]);
+    load_a(k + 4);
   }
-  cp_async_wait<0>();
+  // The groups finish at different times.  A parity wait is only meaningful within one phase of its barrier: a warp that asked
+  // for the last chunk's phase while that stage's barrier was still two phases behind would be let through at once.  After
+  // this rendezvous every chunk has been published, so each stage's barrier is in (or past) its final phase.
+  asm volatile("bar.sync 1, 512;" ::: "memory");
   if (nchunks > 0 && warp < 8 && (warp >> 2) < nb) {
     const uint32_t s = (nchunks - 1) % kWg2BStages, u = (nchunks - 1) / kWg2BStages;
     mbar_wait(&bar_done[s], u & 1);
@@ -595,8 +646,10 @@ __global__ void __launch_bounds__(kWg2Threads, 1) wgrad_dense2_kernel(const __gr
     float acc = 0.f;
 #pragma unroll 1
     for (int tap = 0; tap < 9; ++tap) {
+      // accumulator column of (tap, co): the TMA tile's chunk order is j = 9 * (co / 8) + 8 - tap (plane, y offset, x offset)
       float v[16];
-      tmem_ld16(tmem + ((uint32_t)((warp & 3) * 32) << 16) + b * kWg2AccStride + tap * 16, v);
+      tmem_ld8(tmem + ((uint32_t)((warp & 3) * 32) << 16) + b * kWg2AccStride + (8 - tap) * 8, v);
+      tmem_ld8(tmem + ((uint32_t)((warp & 3) * 32) << 16) + b * kWg2AccStride + (17 - tap) * 8, v + 8);
       if (valid) {
         float w[16];
         unpack8(__ldg(wrow + (size_t)(2 * tap) * 128), w);
@@ -625,11 +678,15 @@ __global__ void __launch_bounds__(kWg2Threads, 1) wgrad_dense2_kernel(const __gr
   if (warp == 0) tmem_dealloc(tmem, 512);
 }
 
-int launch_wgrad_dense2(const WgDenseArgs& a, int nruns, int ngroups, cudaStream_t st) {
+int launch_wgrad_dense2(const WgDenseArgs& a, const void* const* tmaps, int nruns, int ngroups, cudaStream_t st) {
   if (a.nl < 1 || a.nl > kBlockLayers) return rl_fail(RL_ERR_ARG, "wgrad_dense2: bad layer count");
+  WgDenseParams P;
+  P.a = a;
+  for (int j = 0; j < a.nl; ++j) memcpy(&P.tm[j], tmaps[j], sizeof(CUtensorMap));
+  for (int j = a.nl; j < kBlockLayers; ++j) memcpy(&P.tm[j], tmaps[0], sizeof(CUtensorMap));
   {
     ProfScope _ps(KC_WGRAD_DENSE, st);
-    wgrad_dense2_kernel<<<dim3(nruns, ngroups, a.nl), kWg2Threads, kWg2Smem, st>>>(a);
+    wgrad_dense2_kernel<<<dim3(nruns, ngroups, a.nl), kWg2Threads, kWg2Smem, st>>>(P);
   }
   RL_CUDA(cudaGetLastError());
   return RL_OK;
@@ -642,3 +699,14 @@ int configure_fused_kernels() {
 }
 
 }  // namespace rl
+
+extern "C" int rl_selftest_im2col_tmap(const void* planes, long npos, long positions, int W, int c1, void* out, void* stream) {
+  using namespace rl;
+  if (!planes || !out) return rl_fail(RL_ERR_ARG, "rl_selftest_im2col_tmap: null argument");
+  CUtensorMap tm;
+  int rc = encode_dz_im2col_tmap(&tm, planes, npos, positions, W);
+  if (rc) return rc;
+  im2col_tmap_probe_kernel<<<1, 128, 0, (cudaStream_t)stream>>>(tm, c1, (uint4*)out);
+  RL_CUDA(cudaGetLastError());
+  return RL_OK;
+}

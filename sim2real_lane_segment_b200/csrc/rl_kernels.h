@@ -153,11 +153,14 @@ struct WgDenseArgs {
   const double* stats;
   int Ct;
   double inv_n;
-  long px_per_cta;
+  long pos_per_cta;              // K range of a CTA in positions of the padded dz planes (multiple of 64)
+  int B;
   double* acc;                   // level accumulators (A at [c], B at [Ct + c]); channels below C0 receive the layers' mean terms
   int C0;
 };
-int launch_wgrad_dense2(const WgDenseArgs& a, int nruns, int ngroups, cudaStream_t st);
+// tmaps[j]: the 5-D im2col tensor map of layer j's dz planes (encode_dz_im2col_tmap)
+int launch_wgrad_dense2(const WgDenseArgs& a, const void* const* tmaps, int nruns, int ngroups, cudaStream_t st);
+int encode_dz_im2col_tmap(void* tmap_out, const void* plane0, long npos, long positions, int W);
 // once per device / plan bind: opt the kernels into their dynamic shared-memory sizes
 int configure_kernels();
 

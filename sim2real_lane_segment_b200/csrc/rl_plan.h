@@ -109,6 +109,7 @@ struct Plan {
   void* ws;                           // bound workspace (device)
   alignas(64) unsigned char tmap_act[6][128];  // CUtensorMap per level arena: [pixels][Ct] bf16, box 128 px x 64 ch, 128-byte swizzle
   alignas(64) unsigned char tmap_dz[kLevels][kDzBufs][128];  // CUtensorMap per padded dz16 buffer (dgrad_bulk_kernel halo tiles)
+  alignas(64) unsigned char tmap_dz_im2col[kLevels][kDzBufs][128];  // im2col map of the same buffer (wgrad_dense2_kernel)
   bool tmap_ok;
   size_t gstage_off;                  // training: fp32 [n_params] raw gradients of one backward pass (scaled into `grads` at its end)
   void* side_stream;                  // cudaStream_t: weight gradients run here, concurrently with the input-gradient chain

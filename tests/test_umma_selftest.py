@@ -142,3 +142,31 @@ def test_tmem_ld_16x256b_layout():
                     col = 8 * k + 2 * (l % 4) + (j & 1)
                     v = int(o[t, half, 4 * k + j])
                     assert (v >> 8, v & 255) == (lane, col), (t, half, k, j, v >> 8, v & 255)
+
+
+@pytest.mark.gpu
+def test_im2col_tensor_map_with_overlapping_dimensions():
+    """the tensor map of the weight-gradient kernel's B operand (csrc/rl_bwd_fused.cu encode_dz_im2col_tmap): dimensions
+    (64 positions x 8 ch as one 1 KB row, 3 x-offsets, 3 y-offsets, 2 planes) where the x-offset dimension overlaps the rows.  One
+    box must deliver tile[plane][iy][ix][row][:] = planes[plane][c1 + row + iy*(W+2) + ix][:], zero where the position
+    coordinate c1 + row is outside [0, positions)"""
+    import ctypes
+    L = _lib.lib()
+    W, npos = 24, 4000
+    positions = npos - 2 * (W + 2) - 2
+    planes = torch.arange(2 * npos * 8, dtype=torch.int32, device="cuda").to(torch.int16).view(2, npos, 8)
+    pc = planes.cpu()
+    out = torch.zeros(18, 64, 8, dtype=torch.int16, device="cuda")
+    for c1 in (100, -5, npos - 100):
+        _lib.check(L.rl_selftest_im2col_tmap(ctypes.c_void_p(planes.data_ptr()), ctypes.c_long(npos), ctypes.c_long(positions), W, c1,
+                                             ctypes.c_void_p(out.data_ptr()), _lib.cur_stream()))
+        torch.cuda.synchronize()
+        want = torch.zeros(18, 64, 8, dtype=torch.int16)
+        rows = torch.arange(64) + c1
+        ok = (rows >= 0) & (rows < positions)
+        for half in range(2):
+            for iy in range(3):
+                for ix in range(3):
+                    src = (rows + iy * (W + 2) + ix).clamp(0, npos - 1)
+                    want[half * 9 + iy * 3 + ix] = torch.where(ok[:, None], pc[half, src], torch.zeros(1, dtype=torch.int16))
+        assert torch.equal(out.cpu(), want), c1
