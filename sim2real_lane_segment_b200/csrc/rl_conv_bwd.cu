@@ -266,10 +266,12 @@ __global__ void __launch_bounds__(128, 3) dgrad_dense_kernel(DgradArgs a) {
       const __nv_bfloat16* xrow = P < 0 ? nullptr : (a.xp ? a.xp + dact_index(a.npx, P, cb0) : a.act + (size_t)P * a.Ct + cb0);
       __nv_bfloat16* drow = P >= 0 ? a.dact + dact_index(a.npx, P, cb0) : nullptr;
       DgradPre pre[2];
-      dgrad_prefetch(pre[0], xrow, drow, 0, nvalid, cb0 >= a.rmw_from, 16 * a.npx, a.xp ? 16 * a.npx : 0);
-      dgrad_prefetch(pre[1], xrow, drow, 16, nvalid, (cb0 + 16) >= a.rmw_from, 16 * a.npx, a.xp ? 16 * a.npx : 0);
       load_dz(tile);           // previous tile's MMAs were waited for before its epilogue: the buffer is free
       fence_proxy_async();
+      // the epilogue's first x / dX groups are requested only now: fence.proxy.async waits for the loads a thread has
+      // outstanding, so requested before it they would sit in front of the MMAs instead of behind them
+      dgrad_prefetch(pre[0], xrow, drow, 0, nvalid, cb0 >= a.rmw_from, 16 * a.npx, a.xp ? 16 * a.npx : 0);
+      dgrad_prefetch(pre[1], xrow, drow, 16, nvalid, (cb0 + 16) >= a.rmw_from, 16 * a.npx, a.xp ? 16 * a.npx : 0);
       __syncthreads();         // also: every thread is past the epilogue of tile-1 -> TMEM reusable
       if (tid == 0) {
         if (tile == 0) mbar_wait(&bar_w, n_w & 1);
@@ -357,8 +359,6 @@ __global__ void __launch_bounds__(128, 3) dgrad_td_kernel(DgradArgs a) {
       const __nv_bfloat16* xrow = P < 0 ? nullptr : (a.xp ? a.xp + dact_index(a.npx, P, mb * 128) : a.act + (size_t)P * a.Ct + mb * 128);
       __nv_bfloat16* drow = P >= 0 ? a.dact + dact_index(a.npx, P, mb * 128) : nullptr;
       DgradPre pre[2];
-      dgrad_prefetch(pre[0], xrow, drow, 0, nvalid, (mb * 128) >= a.rmw_from, 16 * a.npx, a.xp ? 16 * a.npx : 0);
-      dgrad_prefetch(pre[1], xrow, drow, 16, nvalid, (mb * 128 + 16) >= a.rmw_from, 16 * a.npx, a.xp ? 16 * a.npx : 0);
       ld.load(rowptr, min(8, a.Kdz / 8));
       for (int kc = 0; kc < nkc; ++kc) {
         const int ck = min(64, a.Kdz - kc * 64);
@@ -378,6 +378,10 @@ __global__ void __launch_bounds__(128, 3) dgrad_td_kernel(DgradArgs a) {
 #pragma unroll
           for (int i = 0; i < 4; ++i) rp[i] = rowptr[i] ? rowptr[i] + (kc + 1) * 64 : nullptr;
           ld.load(rp, min(8, (a.Kdz - (kc + 1) * 64) / 8));
+        } else {
+          // after the tile's last fence (fence.proxy.async waits for outstanding loads): the epilogue's first x / dX groups
+          dgrad_prefetch(pre[0], xrow, drow, 0, nvalid, (mb * 128) >= a.rmw_from, 16 * a.npx, a.xp ? 16 * a.npx : 0);
+          dgrad_prefetch(pre[1], xrow, drow, 16, nvalid, (mb * 128 + 16) >= a.rmw_from, 16 * a.npx, a.xp ? 16 * a.npx : 0);
         }
         __syncthreads();
         if (tid == 0) {

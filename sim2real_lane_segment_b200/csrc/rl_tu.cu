@@ -77,11 +77,12 @@ __global__ void __launch_bounds__(kTuThreads, 1) tu_fwd_kernel(TuFwdArgs a) {
   for (; tile < a.ntiles; tile += gridDim.x, ++it) {
     uint8_t* cur = sX + (it & 1) * kTuTileBytes;
     const long next = tile + gridDim.x;
-    if (next < a.ntiles) issue_tile(next, sX + ((it + 1) & 1) * kTuTileBytes);  // its last readers (MMAs of tile it-1) retired
-    else cp_async_commit();
-    cp_async_wait<1>();
+    cp_async_wait<0>();
     fence_proxy_async();
     __syncthreads();  // tile `it` is in shared memory; every thread is past the epilogue of tile it-1 (TMEM reusable)
+    // the next tile's copies start only now (their buffer's last readers, the MMAs of tile it-1, have retired): issued before
+    // the fence they would be waited for by it
+    if (next < a.ntiles) issue_tile(next, sX + ((it + 1) & 1) * kTuTileBytes);
     if (tid == 0) {
       if (it == 0) mbar_wait(&bar_w, 0);
       tc_fence_after();
@@ -312,15 +313,13 @@ __global__ void __launch_bounds__(256, 1) tu_wgrad_kernel(TuBwdArgs a) {
   if (tile < a.ntiles) issue_tile(tile, smem);
   for (; tile < a.ntiles; tile += gridDim.x, ++it) {
     const long next = tile + gridDim.x;
-    if (next < a.ntiles) {
-      if (it >= 1) mbar_wait(&bar_mma[(it + 1) & 1], ((it - 1) >> 1) & 1);  // MMAs of tile it-1 have read that buffer
-      issue_tile(next, smem + ((it + 1) & 1) * kTuWgBuf);
-    } else {
-      cp_async_commit();
-    }
-    cp_async_wait<1>();
+    cp_async_wait<0>();
     fence_proxy_async();
     __syncthreads();
+    if (next < a.ntiles) {  // after the fence (which would wait for these copies), into the buffer the MMAs of tile it-1 read
+      if (it >= 1) mbar_wait(&bar_mma[(it + 1) & 1], ((it - 1) >> 1) & 1);
+      issue_tile(next, smem + ((it + 1) & 1) * kTuWgBuf);
+    }
     if (tid == 0) {
       tc_fence_after();
       uint8_t* buf = smem + (it & 1) * kTuWgBuf;
