@@ -172,9 +172,9 @@ __device__ __forceinline__ void dgrad_flush(float* s_sum /*[2][128]*/, const flo
 __global__ void __launch_bounds__(128, 3) dgrad_dense_kernel(DgradArgs a) {
   extern __shared__ __align__(128) uint8_t smem[];
   uint8_t* sW = smem;                 // W of one channel block: [18][128][8] bf16 = 36864 B   (B operand, rows = channels)
-  uint8_t* sDz = smem + 36864;        // halo tile [2][kDzRows][8] bf16 = 14848 B              (A operand, rows = pixels)
+  uint8_t* sDz = smem + 36864;        // two halo tiles [2][kDzRows][8] bf16 = 14848 B each    (A operand, rows = pixels)
   constexpr int kDzBytes = 2 * kDzRows * 16;
-  DgradConsts* kc = reinterpret_cast<DgradConsts*>(smem + 36864 + kDzBytes);
+  DgradConsts* kc = reinterpret_cast<DgradConsts*>(smem + 36864 + 2 * kDzBytes);
   float* s_rstd = reinterpret_cast<float*>(kc + 1);
   float* s_sum = s_rstd + 128;
   __shared__ uint64_t bar_w, bar_mma, bar_dz[2];
@@ -213,15 +213,17 @@ __global__ void __launch_bounds__(128, 3) dgrad_dense_kernel(DgradArgs a) {
   const long PW = a.W + 2;  // padded row pitch (positions)
   const uint4* plane0 = reinterpret_cast<const uint4*>(a.dz);
   const uint4* plane1 = plane0 + a.dz_npos;
-  auto load_dz = [&](int tile) {
+  // asynchronous copies (cp.async), issued one tile ahead into the other buffer: the copy of tile t+1 runs under the MMAs and
+  // the epilogue of tile t, and no register-staged load sits in front of the fence that publishes a tile
+  auto load_dz = [&](int tile, int buf) {
     const int t0 = t_begin + tile * 128;
-    uint4* d0 = reinterpret_cast<uint4*>(sDz);
-    uint4* d1 = d0 + kDzRows;
+    uint8_t* d0 = sDz + buf * kDzBytes;
+    uint8_t* d1 = d0 + kDzRows * 16;
     if (SW == PW) {
       const long pos0 = a.dz_guard + (long)(V0 - 1) * PW + (t0 - SW - 1);
       for (int rr = tid; rr < nrows; rr += 128) {
-        d0[rr] = __ldg(plane0 + pos0 + rr);
-        d1[rr] = __ldg(plane1 + pos0 + rr);
+        cp_async16(d0 + rr * 16, plane0 + pos0 + rr, true);
+        cp_async16(d1 + rr * 16, plane1 + pos0 + rr, true);
       }
     } else {
       for (int rr = tid; rr < nrows; rr += 128) {
@@ -229,10 +231,11 @@ __global__ void __launch_bounds__(128, 3) dgrad_dense_kernel(DgradArgs a) {
         const int rrow = (t >= 0) ? t / SW : -1;
         const int cc = t - rrow * SW;
         const long pos = a.dz_guard + (long)(V0 - 1 + rrow) * PW + (x0 - 1 + cc) + 1;
-        d0[rr] = __ldg(plane0 + pos);
-        d1[rr] = __ldg(plane1 + pos);
+        cp_async16(d0 + rr * 16, plane0 + pos, true);
+        cp_async16(d1 + rr * 16, plane1 + pos, true);
       }
     }
+    cp_async_commit();
   };
 
   // channel blocks: all of them in this CTA (large levels: W^T is reused across the CTA's tiles), or one per
@@ -251,6 +254,7 @@ __global__ void __launch_bounds__(128, 3) dgrad_dense_kernel(DgradArgs a) {
       mbar_arrive_expect_tx(&bar_w, 36864);
       bulk_g2s(sW, a.wpk + (size_t)mb * 36864, 36864, &bar_w);
     }
+    if (ntiles > 0) load_dz(0, 0);  // (the previous channel block's MMAs were all waited for: both buffers are free)
     for (int tile = 0; tile < ntiles; ++tile) {
       const int t0 = t_begin + tile * 128;
       int P = -1;  // accumulator row -> pixel
@@ -266,7 +270,7 @@ __global__ void __launch_bounds__(128, 3) dgrad_dense_kernel(DgradArgs a) {
       const __nv_bfloat16* xrow = P < 0 ? nullptr : (a.xp ? a.xp + dact_index(a.npx, P, cb0) : a.act + (size_t)P * a.Ct + cb0);
       __nv_bfloat16* drow = P >= 0 ? a.dact + dact_index(a.npx, P, cb0) : nullptr;
       DgradPre pre[2];
-      load_dz(tile);           // previous tile's MMAs were waited for before its epilogue: the buffer is free
+      cp_async_wait<0>();      // this thread's part of the tile (requested one tile ago)
       fence_proxy_async();
       // the epilogue's first x / dX groups are requested only now: fence.proxy.async waits for the loads a thread has
       // outstanding, so requested before it they would sit in front of the MMAs instead of behind them
@@ -276,7 +280,7 @@ __global__ void __launch_bounds__(128, 3) dgrad_dense_kernel(DgradArgs a) {
       if (tid == 0) {
         if (tile == 0) mbar_wait(&bar_w, n_w & 1);
         tc_fence_after();
-        const uint32_t wa = smem_u32(sW), da = smem_u32(sDz);
+        const uint32_t wa = smem_u32(sW), da = smem_u32(sDz + (tile & 1) * kDzBytes);
 #pragma unroll
         for (int tap = 0; tap < 9; ++tap) {
           const int dy = tap / 3 - 1, dx = tap % 3 - 1;
@@ -285,13 +289,8 @@ __global__ void __launch_bounds__(128, 3) dgrad_dense_kernel(DgradArgs a) {
         }
         umma_commit(&bar_mma);
       }
-      // the 128 positions the next tile's halo adds (the rest is this tile's, still in L1): pull them into L1 now so
-      // that the next load_dz does not start with an exposed L2 round trip
-      if (SW == PW && tile + 1 < ntiles) {
-        const long pn = a.dz_guard + (long)(V0 - 1) * PW + (t0 + 128 - SW - 1) + (nrows - 128) + tid;
-        asm volatile("prefetch.global.L1 [%0];" ::"l"(plane0 + pn));
-        asm volatile("prefetch.global.L1 [%0];" ::"l"(plane1 + pn));
-      }
+      // next tile's halo into the other buffer (its last readers, the MMAs of tile-1, were waited for before that epilogue)
+      if (tile + 1 < ntiles) load_dz(tile + 1, (tile + 1) & 1);
       mbar_wait(&bar_mma, n_mma & 1);
       ++n_mma;
       tc_fence_after();
@@ -411,7 +410,7 @@ __global__ void __launch_bounds__(128, 3) dgrad_td_kernel(DgradArgs a) {
   if (warp == 0) tmem_dealloc(tmem, 128);
 }
 
-constexpr size_t kDgradDenseSmem = 36864 + 2 * kDzRows * 16 + sizeof(DgradConsts) + 384 * sizeof(float);
+constexpr size_t kDgradDenseSmem = 36864 + 2 * (2 * kDzRows * 16) + sizeof(DgradConsts) + 384 * sizeof(float);
 constexpr size_t kDgradTdSmem = 2 * 32768 + sizeof(DgradConsts) + 384 * sizeof(float);
 
 int launch_dgrad(const DgradArgs& a, int grid, cudaStream_t st) {
