@@ -772,50 +772,61 @@ __global__ void __launch_bounds__(256) dz_td_kernel(DzArgs a) {
 // (I, J) in [0, h] x [0, w]:  plane (py, px) at position (b, I, J) holds dz of output pixel (2I + py, 2J + px), or zeros when
 // that pixel lies outside the cropped output.  Layout [4][B][h+1][w+1][80] bf16: the transposed convolution's backward
 // GEMMs (rl_tu.cu) read row-shifted views of tiles of these planes, the [pixels x 720] column matrix never exists.
-// One thread per (position, 8-channel chunk); it handles the four parities of its position (one 2x2 output quad).
+// One thread per (position, 16-channel group); it handles the four parities of its position (one 2x2 output quad) with
+// 32-byte accesses (a whole group of the planar arenas per load).
 __global__ void __launch_bounds__(250) dz_tu_kernel(DzArgs a) {
   extern __shared__ float sm[];
-  const int j = threadIdx.x % 10, pl = threadIdx.x / 10;   // 10 chunks of 8 channels, 25 position lanes
+  const int g = threadIdx.x % 5, pl = threadIdx.x / 5;   // 5 groups of 16 channels, 50 position lanes
   const int hp = a.Hp + 1, wp = a.Wp + 1;
-  DzConst* s_k = reinterpret_cast<DzConst*>(sm + 250 * 8);  // [80]
+  DzConst* s_k = reinterpret_cast<DzConst*>(sm + 250 * 16);  // [80]
   for (int c = threadIdx.x; c < 80; c += blockDim.x) s_k[c] = dz_const(a, c);
   __syncthreads();
-  DzConst k[8];
+  float kA[16], kB[16];  // dz = dX - A' - x * B',  B' = rstd * B,  A' = A - mean * B'
 #pragma unroll
-  for (int c = 0; c < 8; ++c) k[c] = s_k[j * 8 + c];
-  float bsum[8];
+  for (int c = 0; c < 16; ++c) {
+    const DzConst k = s_k[g * 16 + c];
+    kB[c] = k.rstd * k.B;
+    kA[c] = k.A - k.mean * kB[c];
+  }
+  float bsum[16];
 #pragma unroll
-  for (int c = 0; c < 8; ++c) bsum[c] = 0.f;
+  for (int c = 0; c < 16; ++c) bsum[c] = 0.f;
   const long npos = (long)a.B * hp * wp;
-  for (long q = (long)blockIdx.x * 25 + pl; q < npos; q += (long)gridDim.x * 25) {
+  const __nv_bfloat16* dplane = a.dact + (size_t)((a.c_off >> 4) + g) * (size_t)a.npx_out * 16;
+  const __nv_bfloat16* xplane = a.xp ? a.xp + (size_t)((a.c_off >> 4) + g) * (size_t)a.npx_out * 16 : nullptr;
+  for (long q = (long)blockIdx.x * 50 + pl; q < npos; q += (long)gridDim.x * 50) {
     const int q32 = (int)q, b = q32 / (hp * wp), rem = q32 - b * (hp * wp), I = rem / wp, J = rem - I * wp;
 #pragma unroll
     for (int par = 0; par < 4; ++par) {
       const int Y = 2 * I + (par >> 1), X = 2 * J + (par & 1);
-      uint4 pk = make_uint4(0, 0, 0, 0);
+      uint4 lo = make_uint4(0, 0, 0, 0), hi = lo;
       if (Y < a.H && X < a.W) {
         const long P = ((long)b * a.H + Y) * a.W + X;
-        float dx[8], xv[8], o[8];
-        unpack8(ldg128(a.dact + dact_index(a.npx_out, P, a.c_off + j * 8)), dx);
-        unpack8(ldg128(a.xp ? a.xp + dact_index(a.npx_out, P, a.c_off + j * 8) : a.act + P * a.Ct + a.c_off + j * 8), xv);
+        const u32x8 dv = ld256_nohint(dplane + (size_t)P * 16);
+        const u32x8 xv = ldg256_nc_nohint(xplane ? xplane + (size_t)P * 16 : a.act + (size_t)P * a.Ct + a.c_off + g * 16);
+        float dx[16], xx[16], o[16];
+        unpack8(dv.lo, dx);
+        unpack8(dv.hi, dx + 8);
+        unpack8(xv.lo, xx);
+        unpack8(xv.hi, xx + 8);
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          const float xh = (xv[c] - k[c].mean) * k[c].rstd;
-          o[c] = dx[c] - k[c].A - xh * k[c].B;
+        for (int c = 0; c < 16; ++c) {
+          o[c] = dx[c] - fmaf(xx[c], kB[c], kA[c]);
           bsum[c] += o[c];
         }
-        pk = pack8(o);
+        lo = pack8(o);
+        hi = pack8(o + 8);
       }
-      *reinterpret_cast<uint4*>(a.dz + ((long)par * npos + q) * 80 + j * 8) = pk;
+      st256(a.dz + ((long)par * npos + q) * 80 + g * 16, lo, hi);
     }
   }
   if (a.g_bias != nullptr) {
 #pragma unroll
-    for (int c = 0; c < 8; ++c) sm[threadIdx.x * 8 + c] = bsum[c];
+    for (int c = 0; c < 16; ++c) sm[threadIdx.x * 16 + c] = bsum[c];
     __syncthreads();
     for (int c = threadIdx.x; c < 80; c += blockDim.x) {
       float acc = 0.f;
-      for (int l = 0; l < 25; ++l) acc += sm[(l * 10 + c / 8) * 8 + (c % 8)];
+      for (int l = 0; l < 50; ++l) acc += sm[(l * 5 + c / 16) * 16 + (c % 16)];
       atomicAdd(a.g_bias + c, acc);
     }
   }
@@ -839,10 +850,11 @@ int launch_dz_prepare(const DzArgs& a, int sm, cudaStream_t st) {
     return RL_OK;
   }
   if (a.kind == 2 && a.nch == 80) {
+    if (a.c_off & 15) return rl_fail(RL_ERR_ARG, "dz_tu: the up-sampled channels must start on a 16-channel group");
     long npos = (long)a.B * (a.Hp + 1) * (a.Wp + 1);
-    int grid = (int)std::max<long>(1, std::min<long>((npos + 24) / 25, (long)sm * 8));
+    int grid = (int)std::max<long>(1, std::min<long>((npos + 49) / 50, (long)sm * 8));
     { ProfScope _ps(KC_DZ_PREPARE, st);
-    dz_tu_kernel<<<grid, 250, 250 * 8 * sizeof(float) + 80 * sizeof(DzConst), st>>>(a); }
+    dz_tu_kernel<<<grid, 250, 250 * 16 * sizeof(float) + 80 * sizeof(DzConst), st>>>(a); }
   RL_CUDA(cudaGetLastError());
     return RL_OK;
   }
